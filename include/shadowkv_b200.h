@@ -1,0 +1,231 @@
+/*
+ * shadowkv_b200.h -- C-ABI of the B200-native ShadowKV sparse-KV decode step.
+ *
+ * Every entry point takes plain device/host pointers, sizes and a cudaStream_t
+ * (passed as void*; NULL = legacy default stream).  No torch types cross this
+ * boundary.  All functions return 0 on success, a positive cudaError_t value if
+ * the CUDA runtime reported an error at launch, or a negative SKV_ERR_* code
+ * for an argument the kernels do not support.  Launches are asynchronous.
+ *
+ * Part 1 mirrors, one to one, the 12 functions the reference binds with
+ * pybind11 (reference kernels/main.cu:45-80, signatures kernels/functions.h);
+ * each comment cites the reference interface it replaces.  Tensors that the
+ * reference receives as torch::Tensor arrive here as their data_ptr(); element
+ * strides stay in elements, exactly as the reference's Python wrappers compute
+ * them (models/tensor_op.py:154-238, models/kv_cache.py:1006-1150).
+ *
+ * Part 2 adds the fused entry points of the B200 path (scoring + selection +
+ * chunk-table update in two launches, tcgen05 K rebuild with RoPE epilogue,
+ * cluster-staged hit compaction, miss fetch from pinned host memory, split-K
+ * decode attention).  ShadowKVCache_CPU in shadowkv_b200/kv_cache.py routes
+ * its reference-named methods to these.
+ */
+#ifndef SHADOWKV_B200_H
+#define SHADOWKV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKV_OK 0
+#define SKV_ERR_UNSUPPORTED (-1) /* shape/size outside what the kernels handle */
+#define SKV_ERR_ARGUMENT (-2)    /* null pointer / inconsistent sizes           */
+#define SKV_ERR_DRIVER (-3)      /* driver entry point (tensor map) unavailable */
+
+typedef void *skv_stream_t; /* cudaStream_t */
+typedef uint16_t skv_bf16;  /* raw bfloat16 bits */
+
+/* Library / build identification; returns a static string. */
+const char *skv_version(void);
+/* Last error message of the calling thread ("" if none). */
+const char *skv_last_error(void);
+
+/* ======================================================================
+ * Part 1 -- the reference's 12 extension entry points
+ * ====================================================================== */
+
+/* functions.h:71-79  gather_copy (kernels/gather_copy.cu:63-146, copy.cuh:481-508)
+ * Uncached gather: for every (b,h) block and i < map_size,
+ *   dst[block*gpu_v_length + i*1024 ..] <- values[block*cpu_v_length + position_ids[block*map_size+i]*1024 ..]
+ * (1024 bf16 = one 2 KiB chunk).  values may be pinned host memory.
+ * map_size must be 128, 256, 512 or 1024. */
+int skv_gather_copy(const skv_bf16 *values, skv_bf16 *v_cache_buffer, const int64_t *position_ids,
+                    int batch_size, int heads, int cpu_v_length, int gpu_v_length, int map_size,
+                    skv_stream_t stream);
+
+/* functions.h:97-106  gather_copy_d2d_with_offsets (gather_copy.cu:165-240, copy.cuh:649-687)
+ * In-place forward compaction of cache-hit chunks of the K buffer:
+ *   for i < cnts[block]:  slot i <- slot offsets[block*map_size + i]
+ * slot s of block lives at keys + block*gpu_k_stride + gpu_k_offset + s*1024 (elements). */
+int skv_gather_copy_d2d_with_offsets(skv_bf16 *keys, const int32_t *offsets, const int32_t *cnts,
+                                     int batch_size, int heads, int gpu_k_length, int gpu_k_offset,
+                                     int gpu_k_stride, int map_size, skv_stream_t stream);
+
+/* functions.h:123-128  reorder_keys_and_compute_offsets (gather_copy.cu:259-307, map.cuh:754-796)
+ * Per block: classify cur_pos_ids against the resident table cached_pos_ids;
+ * hits first (ordered by old slot, offset = old slot), misses after (ordered by
+ * chunk id, offset = chunk id); cached_pos_ids is rewritten IN PLACE,
+ * cnts[block] = number of hits.  Ids are truncated to int32; -1 is reserved. */
+int skv_reorder_keys_and_compute_offsets(int64_t *cached_pos_ids, const int64_t *cur_pos_ids,
+                                         int32_t *offsets, int32_t *cnts, int batch_size, int heads,
+                                         int map_size, skv_stream_t stream);
+
+/* functions.h:151-158  gather_copy_with_offsets (gather_copy.cu:332-419, copy.cuh:785-846)
+ * Cached V fetch: hits compacted in place inside v_cache_buffer, misses read
+ * from the pinned host store `values`.  temp and signals are accepted for
+ * signature compatibility and are not used (no inter-block handshake here). */
+int skv_gather_copy_with_offsets(const skv_bf16 *values, skv_bf16 *v_cache_buffer, skv_bf16 *temp,
+                                 const int32_t *offsets, const int32_t *cnts, int32_t *signals,
+                                 int batch_size, int heads, int cpu_v_length, int gpu_v_length,
+                                 int gpu_v_offset, int gpu_v_stride, int map_size, skv_stream_t stream);
+
+/* functions.h:187-193  apply_rotary_pos_emb (kernels/rope.cu:61-107): separate cos / sin tables,
+ * int64 token positions, neox half-split, bf16 arithmetic. */
+int skv_apply_rotary_pos_emb(const skv_bf16 *x, const skv_bf16 *cos, const skv_bf16 *sin,
+                             const int64_t *position_ids, skv_bf16 *output, int batch_size, int heads,
+                             int seq_len, int embed_dim, int stride_xb, int stride_xh, int stride_xs,
+                             int stride_xe, int stride_cos, int stride_sin, int stride_pid_b,
+                             int stride_pid_h, int stride_pid_s, int half_dim, skv_stream_t stream);
+
+/* functions.h:240-246  apply_rotary_pos_emb_new (rope_new.cu:55-126): combined [cos|sin] table. */
+int skv_apply_rotary_pos_emb_new(const skv_bf16 *x, const skv_bf16 *cos_sin, const int64_t *position_ids,
+                                 skv_bf16 *output, int batch_size, int heads, int seq_len, int embed_dim,
+                                 int stride_xb, int stride_xh, int stride_xs, int stride_xe,
+                                 int stride_cos_sin, int stride_pid_b, int stride_pid_h, int stride_pid_s,
+                                 int half_dim, skv_stream_t stream);
+
+/* functions.h:281-287  apply_rotary_pos_emb_new_v2 (rope_new.cu:135-205): int32 CHUNK ids,
+ * token position = id*chunk_size + s%chunk_size. */
+int skv_apply_rotary_pos_emb_new_v2(const skv_bf16 *x, const skv_bf16 *cos_sin, const int32_t *position_ids,
+                                    skv_bf16 *output, int batch_size, int heads, int seq_len, int embed_dim,
+                                    int stride_xb, int stride_xh, int stride_xs, int stride_xe,
+                                    int stride_cos_sin, int stride_pid_b, int stride_pid_h,
+                                    int stride_pid_s, int half_dim, int chunk_size, skv_stream_t stream);
+
+/* functions.h:328-337 / 362-371 / 396-405  apply_rotary_pos_emb_push_cache{,_opt,_opt_glm}
+ * (rope_new.cu:219-300, 321-411, 429-534): RoPE rows of chunks >= cnts[b,h] and write them into
+ * the K buffer at sequence offset offset_output_s_start + s (rows at or beyond offset_output_s_end
+ * are skipped).  _opt and the plain variant compute the same thing; _glm rotates interleaved pairs
+ * of the first 64 dims with a [cos(32)|sin(32)] table and copies dims 64..127. */
+int skv_apply_rotary_pos_emb_push_cache(const skv_bf16 *x, const skv_bf16 *cos_sin, const int32_t *position_ids,
+                                        skv_bf16 *output_cache, const int32_t *cnts, int batch_size, int heads,
+                                        int seq_len, int embed_dim, int stride_xb, int stride_xh, int stride_xs,
+                                        int stride_xe, int stride_cos_sin, int stride_pid_b, int stride_pid_h,
+                                        int stride_pid_s, int stride_output_b, int stride_output_h,
+                                        int stride_output_s, int offset_output_s_start, int offset_output_s_end,
+                                        int half_dim, int chunk_size, skv_stream_t stream);
+int skv_apply_rotary_pos_emb_push_cache_opt(const skv_bf16 *x, const skv_bf16 *cos_sin, const int32_t *position_ids,
+                                            skv_bf16 *output_cache, const int32_t *cnts, int batch_size, int heads,
+                                            int seq_len, int embed_dim, int stride_xb, int stride_xh, int stride_xs,
+                                            int stride_xe, int stride_cos_sin, int stride_pid_b, int stride_pid_h,
+                                            int stride_pid_s, int stride_output_b, int stride_output_h,
+                                            int stride_output_s, int offset_output_s_start,
+                                            int offset_output_s_end, int half_dim, int chunk_size,
+                                            skv_stream_t stream);
+int skv_apply_rotary_pos_emb_push_cache_opt_glm(const skv_bf16 *x, const skv_bf16 *cos_sin,
+                                                const int32_t *position_ids, skv_bf16 *output_cache,
+                                                const int32_t *cnts, int batch_size, int heads, int seq_len,
+                                                int embed_dim, int stride_xb, int stride_xh, int stride_xs,
+                                                int stride_xe, int stride_cos_sin, int stride_pid_b,
+                                                int stride_pid_h, int stride_pid_s, int stride_output_b,
+                                                int stride_output_h, int stride_output_s,
+                                                int offset_output_s_start, int offset_output_s_end, int half_dim,
+                                                int chunk_size, skv_stream_t stream);
+
+/* functions.h:431-437  batch_gather_gemm (kernels/batch_gather_gemm.cu:193-287)
+ * output[bh, r, :] = bf16( sum_k a[b, ids[bh, r/chunk]*chunk + r%chunk, k] * b[bh, :, k] )  (pre-RoPE K)
+ * for the 128-row tiles not entirely below offset_array[bh]*chunk_size (the reference skips whole
+ * tiles of cache hits, gemm_universal_batch_gather_indices.h:727-738).  a = U [batch, seq_len, rank],
+ * b = SV [batch*heads, embed_dim, rank], ids int32 [batch*heads, sparse_budget/chunk_size].
+ * cos / sin / max_seq_len are accepted and unused, as in the reference (its RoPE epilogue is disabled). */
+int skv_batch_gather_gemm(const skv_bf16 *a, const skv_bf16 *b, const skv_bf16 *cos, const skv_bf16 *sin,
+                          const int32_t *position_ids, skv_bf16 *output, int batch_size, int heads,
+                          int seq_len, int embed_dim, int rank, int sparse_budget, int max_seq_len,
+                          int chunk_size, const int32_t *offset_array, skv_stream_t stream);
+
+/* functions.h:460-463  batch_gemm_softmax (kernels/batch_gemm_softmax.cu:229-293)
+ * D[bc, i, j] = bf16(alpha * sum_k A[bc, i, k] * B[bc, j, k]);  Softmax = bf16(exp(D - rowmax) / rowsum).
+ * A [batch_count, m, k], B [batch_count, n, k], D / Softmax [batch_count, m, n] bf16.
+ * Norm / Sum [batch_count, m, ceil(n/256)] f32 scratch: on return Norm[bc, i, 0] holds the row maximum
+ * and Sum[bc, i, 0] the reciprocal of the row sum (what the reference's final reduction leaves there).
+ * beta must be 0.  m <= 16, k == 128. */
+int skv_batch_gemm_softmax(const skv_bf16 *A, const skv_bf16 *B, skv_bf16 *D, float *Norm, float *Sum,
+                           skv_bf16 *Softmax, int batch_count, int m, int n, int k, float alpha, float beta,
+                           skv_stream_t stream);
+
+/* ======================================================================
+ * Part 2 -- fused B200 entry points
+ * ====================================================================== */
+
+/* Geometry shared by the fused calls.  All strides in elements. */
+typedef struct skv_geom {
+  int32_t batch;        /* B                                   */
+  int32_t kv_heads;     /* H                                   */
+  int32_t q_groups;     /* G = q heads per kv head (<= 16)     */
+  int32_t head_dim;     /* D, must be 128                      */
+  int32_t chunk;        /* C, must be 8                        */
+  int32_t select;       /* S chunks in the sparse budget: 128/256/512/1024 */
+  int32_t n_landmarks;  /* N, multiple of 8                    */
+  int32_t rank;         /* R, multiple of 8, <= 256            */
+  int32_t seq_len;      /* L rows of U per sequence            */
+  int32_t buf_len;      /* Lbuf rows of the K/V buffers        */
+  int32_t sparse_start; /* first row of the sparse region      */
+  int32_t rope_glm;     /* 0: neox [cos64|sin64]; 1: GLM [cos32|sin32] */
+  int32_t cos_sin_rows; /* rows of the cos_sin table           */
+  int32_t reserved;
+} skv_geom;
+
+/* Bytes of device scratch skv_select_chunks needs for `geom` (scores + partials). */
+int64_t skv_select_workspace_bytes(const skv_geom *geom);
+
+/* (a3)+(a4)+(a5) in two launches: landmark scoring with fused scale/bf16 round and per-tile
+ * softmax partials; then per (b,h): final softmax, max over the G query heads, top-S selection
+ * (ties: lowest landmark index), chunk-id gather and the chunk-table update of
+ * skv_reorder_keys_and_compute_offsets.  q [B, H*G, D] bf16 (post-RoPE); landmarks [B,H,N,D];
+ * landmark_idx [B,H,N] int64; resident [B,H,S] int64 in/out; offsets [B*H*S], cnts [B*H] out.
+ * selected_out (optional, may be NULL) receives the S selected chunk ids per (b,h) in ascending
+ * landmark order; score_out (optional) the bf16 max-over-groups softmax [B,H,N]. */
+int skv_select_chunks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *landmarks,
+                      const int64_t *landmark_idx, int64_t *resident, int32_t *offsets, int32_t *cnts,
+                      int64_t *selected_out, skv_bf16 *score_out, void *workspace, skv_stream_t stream);
+
+/* (a6)+(a7) hit compaction for K and V in one cluster-staged launch (no temp buffer):
+ * for i < cnts[bh]: slot i <- slot offsets[bh*S+i] in both buffers.  Either buffer may be NULL. */
+int skv_compact_hits(const skv_geom *geom, skv_bf16 *k_buf, skv_bf16 *v_buf, const int32_t *offsets,
+                     const int32_t *cnts, skv_stream_t stream);
+
+/* (a6) miss fetch: for i >= cnts[bh]: V slot i <- v_host[bh, offsets[bh*S+i]] (pinned host memory,
+ * read over PCIe by the SMs).  host_stride = elements between consecutive (b,h) blocks of v_host. */
+int skv_fetch_misses(const skv_geom *geom, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
+                     const int32_t *offsets, const int32_t *cnts, skv_stream_t stream);
+
+/* (a7) K rebuild for the missed chunks with RoPE in the epilogue (TMA-fed tcgen05, fp32 accumulate in
+ * TMEM, bf16 round, bf16 RoPE at token position id*C+r), written straight into the sparse region of
+ * k_buf.  U [B,L,R], SV [B,H,D,R], cos_sin [rows, D] or [rows, D/2] (GLM), resident [B,H,S] int64.
+ * impl: 0 = tcgen05 (product path), 1 = SIMT cross-check used by the tests. */
+int skv_rebuild_keys(const skv_geom *geom, const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin,
+                     const int64_t *resident, const int32_t *cnts, skv_bf16 *k_buf, int impl,
+                     skv_stream_t stream);
+
+/* (a2) append the new token's K and V rows at buffer row `pos` of every (b,h). k_new/v_new [B,H,D]. */
+int skv_append_kv(const skv_geom *geom, const skv_bf16 *k_new, const skv_bf16 *v_new, skv_bf16 *k_buf,
+                  skv_bf16 *v_buf, int pos, skv_stream_t stream);
+
+/* Bytes of device scratch skv_attention_decode needs (split partials + arrival counters). */
+int64_t skv_attention_workspace_bytes(int batch, int kv_heads, int q_groups, int head_dim, int max_splits);
+
+/* (a8) replacement for flash_attn_with_kvcache(q, k_cache, v_cache, causal=True) with one query token
+ * (reference models/base.py:341): out[b, h*G+g, :] = softmax(q K^T / sqrt(D)) V over rows [0, kv_len).
+ * k/v element strides: (batch, head, row); rows are D contiguous elements.  workspace must be zeroed
+ * once at allocation (the kernel leaves its counters at zero).  num_splits <= 0 picks a split count. */
+int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch,
+                         int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b,
+                         int64_t stride_h, int64_t stride_row, float scale, int num_splits, void *workspace,
+                         skv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHADOWKV_B200_H */

@@ -1,0 +1,20 @@
+// Error reporting and identification for the C-ABI.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace skv {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace skv
+
+extern "C" {
+const char *skv_version(void) { return "shadowkv_b200 0.1 (sm_100a; tcgen05 K rebuild, TMA bulk compaction)"; }
+const char *skv_last_error(void) { return skv::g_err; }
+}

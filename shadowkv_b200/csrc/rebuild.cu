@@ -1,0 +1,442 @@
+// Low-rank pre-RoPE key rebuild for the missed chunks:  K[r,:] = U[b, id*8 + r%8, :R] . SV[b,h,:, :R]^T
+// (reference kernels/batch_gather_gemm.cu:193-287 + rope_new.cu:321-370/429-493, three launches and a bf16
+// scratch round trip there).  Here: one launch.  The chunk-gathered U rows (8 contiguous rows of 2R bytes
+// per chunk = exactly one 128B-swizzle atom per 64-column slab) and the SV panel are brought in by TMA, the
+// 128x128xR product runs on tcgen05 with the fp32 accumulator in TMEM, and the epilogue rounds to bf16,
+// applies the rotary embedding in bf16 at token position id*8+r and writes straight into the K buffer.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace skv {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarrier_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbarrier_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_addr(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_alloc(uint32_t *smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
+__device__ __forceinline__ void tcgen05_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (sm_100 UMMA): start>>4 | LBO=1 (unused for
+// swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | layout SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+// bf16 x bf16 -> f32, A and B K-major, M=128, N=128
+constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;                 // 16 chunks
+constexpr int kTileChunks = kTileRows / kChunkTokens;
+constexpr int kSlabCols = 64;                  // 128 B of bf16 = one swizzle span
+constexpr int kMaxSlabs = 4;                   // rank <= 256
+constexpr int kSlabBytesA = kTileRows * 128;   // 16 KiB
+constexpr int kSlabBytesB = kHeadDim * 128;    // 16 KiB
+
+struct RebuildParams {
+  const int64_t *resident;   // [BH, S] chunk ids (after reorder)
+  const int32_t *ids32;      // alternative int32 ids (drop-in batch_gather_gemm); one of the two is set
+  const int32_t *cnts;       // [BH]
+  const __nv_bfloat16 *cos_sin;
+  __nv_bfloat16 *out;        // K buffer (fused) or scratch [BH, S*8, 128] (drop-in)
+  int64_t out_stride_bh;     // elements
+  int64_t out_row0;          // first row of slot 0 inside a (b,h) block
+  int H, S, L, R, n_slabs, k_steps;
+  int rope;                  // 0 none (drop-in pre-RoPE), 1 neox, 2 glm
+  int tile_skip;             // 1: skip by whole tiles like the reference and write every row of a kept tile
+};
+
+__global__ void __launch_bounds__(128, 1)
+    rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sv,
+                           RebuildParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem;                                   // n_slabs x 16 KiB
+  unsigned char *sB = smem + kMaxSlabs * kSlabBytesA;         // n_slabs x 16 KiB
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kMaxSlabs * (kSlabBytesA + kSlabBytesB));
+  uint64_t *mma_bar = full_bar + kMaxSlabs;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 1);
+  int *s_ids = reinterpret_cast<int *>(tmem_slot + 2);        // [16]
+
+  const int tile = blockIdx.x, bh = blockIdx.y, b = bh / p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cnt = p.cnts ? p.cnts[bh] : 0;
+  const int first_slot = tile * kTileChunks;
+  if (first_slot + kTileChunks <= cnt) return;                // tile entirely cache hits (uniform per CTA)
+
+  if (threadIdx.x < kTileChunks) {
+    const int slot = first_slot + threadIdx.x;
+    int id = -1;
+    if (slot < p.S && (p.tile_skip || slot >= cnt))
+      id = p.resident ? static_cast<int>(p.resident[size_t(bh) * p.S + slot]) : p.ids32[size_t(bh) * p.S + slot];
+    s_ids[threadIdx.x] = id;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_slabs; ++s) mbarrier_init(&full_bar[s], 1);
+    mbarrier_init(mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_sv) : "memory");
+  }
+  if (warp == 0) tcgen05_alloc(tmem_slot, 128);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    int n_valid = 0;
+    for (int j = 0; j < kTileChunks; ++j) n_valid += s_ids[j] >= 0;
+    // producer: one barrier per 64-column slab so the MMAs of slab 0 overlap the loads of slabs 1..
+    for (int s = 0; s < p.n_slabs; ++s) {
+      mbarrier_expect_tx(&full_bar[s], kSlabBytesB + n_valid * 1024);
+      tma_load_2d(sB + s * kSlabBytesB, &map_sv, s * kSlabCols, bh * kHeadDim, &full_bar[s]);
+      for (int j = 0; j < kTileChunks; ++j)
+        if (s_ids[j] >= 0)
+          tma_load_2d(sA + s * kSlabBytesA + j * 1024, &map_u, s * kSlabCols, b * p.L + s_ids[j] * kChunkTokens,
+                      &full_bar[s]);
+    }
+    // MMA issuer
+    int step = 0;
+    for (int s = 0; s < p.n_slabs; ++s) {
+      mbarrier_wait(&full_bar[s], 0);
+      tcgen05_fence_after();
+      const uint64_t da = umma_desc_k_sw128(smem_addr(sA + s * kSlabBytesA));
+      const uint64_t db = umma_desc_k_sw128(smem_addr(sB + s * kSlabBytesB));
+      for (int kk = 0; kk < 4 && step < p.k_steps; ++kk, ++step)
+        tcgen05_mma_bf16(tmem_base, da + uint64_t(kk * 2), db + uint64_t(kk * 2), kIdescBf16M128N128, step > 0);
+    }
+    tcgen05_commit(mma_bar);
+  }
+  __syncwarp();
+  mbarrier_wait(mma_bar, 0);
+  tcgen05_fence_after();
+
+  // ---- epilogue: thread = tile row ---------------------------------------------------------------
+  const int row = threadIdx.x;                     // warp w owns TMEM lanes 32w..32w+31
+  const int j = row >> 3, r = row & 7;
+  const int id = s_ids[j];
+  const int slot = first_slot + j;
+  const bool write = id >= 0;
+  const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
+  __nv_bfloat16 *orow = p.out + size_t(bh) * p.out_stride_bh + (p.out_row0 + size_t(slot) * kChunkTokens + r) * kHeadDim;
+  const long long token = (long long)id * kChunkTokens + r;
+
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    uint32_t lo[32], hi[32];
+    tcgen05_ld32(taddr + half * 32, lo);            // columns [32*half, 32*half+32)
+    tcgen05_ld32(taddr + 64 + half * 32, hi);       // columns [64+32*half, ...)
+    tcgen05_wait_ld();
+    if (!write) continue;
+    uint32_t olo[16], ohi[16];
+    if (p.rope == 1) {
+      const __nv_bfloat16 *cs = p.cos_sin + token * kHeadDim;
+      const uint4 *c4 = reinterpret_cast<const uint4 *>(cs + half * 32);
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(cs + 64 + half * 32);
+      uint32_t cw[16], sw[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 a = c4[q], bq = s4[q];
+        cw[4 * q] = a.x; cw[4 * q + 1] = a.y; cw[4 * q + 2] = a.z; cw[4 * q + 3] = a.w;
+        sw[4 * q] = bq.x; sw[4 * q + 1] = bq.y; sw[4 * q + 2] = bq.z; sw[4 * q + 3] = bq.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat162 x1 = __floats2bfloat162_rn(__uint_as_float(lo[2 * e]), __uint_as_float(lo[2 * e + 1]));
+        const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
+        const __nv_bfloat162 s = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
+        const __nv_bfloat162 o1 = __hfma2(x1, c, __hmul2(__hneg2(x2), s));
+        const __nv_bfloat162 o2 = __hfma2(x2, c, __hmul2(x1, s));
+        olo[e] = *reinterpret_cast<const uint32_t *>(&o1);
+        ohi[e] = *reinterpret_cast<const uint32_t *>(&o2);
+      }
+    } else if (p.rope == 2 ) {
+      // GLM: interleaved pairs over dims [0,64) with [cos32|sin32]; dims [64,128) copied.
+      // lo holds dims [32*half, 32*half+32) = pairs [16*half, 16*half+16)
+      const __nv_bfloat16 *cs = p.cos_sin + token * (kHeadDim / 2);
+      const uint4 *c4 = reinterpret_cast<const uint4 *>(cs + half * 16);
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(cs + 32 + half * 16);
+      uint32_t cw[8], sw[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4 a = c4[q], bq = s4[q];
+        cw[4 * q] = a.x; cw[4 * q + 1] = a.y; cw[4 * q + 2] = a.z; cw[4 * q + 3] = a.w;
+        sw[4 * q] = bq.x; sw[4 * q + 1] = bq.y; sw[4 * q + 2] = bq.z; sw[4 * q + 3] = bq.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {         // two pairs per iteration: elements 4e..4e+3
+        const __nv_bfloat162 xe = __floats2bfloat162_rn(__uint_as_float(lo[4 * e]), __uint_as_float(lo[4 * e + 2]));
+        const __nv_bfloat162 xo = __floats2bfloat162_rn(__uint_as_float(lo[4 * e + 1]), __uint_as_float(lo[4 * e + 3]));
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
+        const __nv_bfloat162 s = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
+        const __nv_bfloat162 oe = __hfma2(xe, c, __hmul2(__hneg2(xo), s));
+        const __nv_bfloat162 oo = __hfma2(xo, c, __hmul2(xe, s));
+        olo[2 * e] = pack_bf16(__low2bfloat16(oe), __low2bfloat16(oo));
+        olo[2 * e + 1] = pack_bf16(__high2bfloat16(oe), __high2bfloat16(oo));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
+        ohi[e] = *reinterpret_cast<const uint32_t *>(&x2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat162 x1 = __floats2bfloat162_rn(__uint_as_float(lo[2 * e]), __uint_as_float(lo[2 * e + 1]));
+        const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
+        olo[e] = *reinterpret_cast<const uint32_t *>(&x1);
+        ohi[e] = *reinterpret_cast<const uint32_t *>(&x2);
+      }
+    }
+    uint4 *d1 = reinterpret_cast<uint4 *>(orow + half * 32);
+    uint4 *d2 = reinterpret_cast<uint4 *>(orow + 64 + half * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      d1[q] = make_uint4(olo[4 * q], olo[4 * q + 1], olo[4 * q + 2], olo[4 * q + 3]);
+      d2[q] = make_uint4(ohi[4 * q], ohi[4 * q + 1], ohi[4 * q + 2], ohi[4 * q + 3]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tcgen05_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check of the same computation (tests only; impl = 1).  One CTA per missed chunk.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    rebuild_simt_kernel(const __nv_bfloat16 *__restrict__ U, const __nv_bfloat16 *__restrict__ SV, RebuildParams p) {
+  __shared__ float s_u[kChunkTokens][256];
+  __shared__ __nv_bfloat16 s_k[kChunkTokens][kHeadDim];
+  const int slot = blockIdx.x, bh = blockIdx.y, b = bh / p.H, d = threadIdx.x;
+  const int cnt = p.cnts ? p.cnts[bh] : 0;
+  if (p.tile_skip ? (slot / kTileChunks + 1) * kTileChunks <= cnt : slot < cnt) return;
+  const int id = p.resident ? static_cast<int>(p.resident[size_t(bh) * p.S + slot]) : p.ids32[size_t(bh) * p.S + slot];
+  const __nv_bfloat16 *u = U + (size_t(b) * p.L + size_t(id) * kChunkTokens) * p.R;
+  for (int i = threadIdx.x; i < kChunkTokens * p.R; i += 128) s_u[i / p.R][i % p.R] = __bfloat162float(u[i]);
+  __syncthreads();
+  const __nv_bfloat16 *sv = SV + (size_t(bh) * kHeadDim + d) * p.R;
+  float acc[kChunkTokens] = {};
+  for (int k = 0; k < p.R; ++k) {
+    const float w = __bfloat162float(sv[k]);
+#pragma unroll
+    for (int r = 0; r < kChunkTokens; ++r) acc[r] = fmaf(s_u[r][k], w, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kChunkTokens; ++r) s_k[r][d] = __float2bfloat16_rn(acc[r]);
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < kChunkTokens; ++r) {
+    const long long token = (long long)id * kChunkTokens + r;
+    __nv_bfloat16 o = s_k[r][d];
+    if (p.rope == 1) {
+      const __nv_bfloat16 *cs = p.cos_sin + token * kHeadDim;
+      __nv_bfloat16 o1, o2;
+      if (d < 64) { rope_pair_bf16(s_k[r][d], s_k[r][d + 64], cs[d], cs[64 + d], o1, o2); o = o1; }
+      else        { rope_pair_bf16(s_k[r][d - 64], s_k[r][d], cs[d - 64], cs[d], o1, o2); o = o2; }
+    } else if (p.rope == 2 && d < 64) {
+      const __nv_bfloat16 *cs = p.cos_sin + token * (kHeadDim / 2);
+      const int pr = d >> 1;
+      __nv_bfloat16 o1, o2;
+      rope_pair_bf16(s_k[r][2 * pr], s_k[r][2 * pr + 1], cs[pr], cs[32 + pr], o1, o2);
+      o = (d & 1) ? o2 : o1;
+    }
+    p.out[size_t(bh) * p.out_stride_bh + (p.out_row0 + size_t(slot) * kChunkTokens + r) * kHeadDim + d] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps (cached per pointer/shape) and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box {64 cols, box_rows}, 128-byte swizzle, zero OOB fill.
+static int make_map(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  typedef std::tuple<const void *, uint64_t, uint64_t, uint32_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key(base, rows, cols, box_rows);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return SKV_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SKV_ERR_DRIVER; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {kSlabCols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return SKV_ERR_DRIVER; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return SKV_OK;
+}
+
+static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p, int B, int impl, cudaStream_t st) {
+  const int BH = B * p.H;
+  if (p.R % 8 || p.R < 8 || p.R > kMaxSlabs * kSlabCols) { set_error("rebuild: rank %d unsupported", p.R); return SKV_ERR_UNSUPPORTED; }
+  p.n_slabs = (p.R + kSlabCols - 1) / kSlabCols;
+  p.k_steps = (p.R + 15) / 16;
+  if (impl == 1) {
+    dim3 grid(p.S, BH);
+    rebuild_simt_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(U),
+                                              reinterpret_cast<const __nv_bfloat16 *>(SV), p);
+    return launch_status("rebuild_simt_kernel");
+  }
+  CUtensorMap map_u, map_sv;
+  int rc = make_map(&map_u, U, uint64_t(B) * p.L, p.R, kChunkTokens);
+  if (rc) return rc;
+  rc = make_map(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim);
+  if (rc) return rc;
+  const int smem = kMaxSlabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 16 * 4 + 64;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  dim3 grid((p.S + kTileChunks - 1) / kTileChunks, BH);
+  rebuild_tcgen05_kernel<<<grid, 128, smem, st>>>(map_u, map_sv, p);
+  return launch_status("rebuild_tcgen05_kernel");
+}
+
+}  // namespace skv
+
+using namespace skv;
+
+extern "C" {
+
+int skv_rebuild_keys(const skv_geom *g, const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin,
+                     const int64_t *resident, const int32_t *cnts, skv_bf16 *k_buf, int impl, skv_stream_t stream) {
+  if (!g || !U || !SV || !cos_sin || !resident || !cnts || !k_buf) { set_error("rebuild_keys: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select)) {
+    set_error("rebuild_keys: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
+  }
+  RebuildParams p{};
+  p.resident = resident; p.cnts = cnts;
+  p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(cos_sin);
+  p.out = reinterpret_cast<__nv_bfloat16 *>(k_buf);
+  p.out_stride_bh = int64_t(g->buf_len) * g->head_dim;
+  p.out_row0 = g->sparse_start;
+  p.H = g->kv_heads; p.S = g->select; p.L = g->seq_len; p.R = g->rank;
+  p.rope = g->rope_glm ? 2 : 1;
+  p.tile_skip = 0;
+  return launch_rebuild(U, SV, p, g->batch, impl, as_stream(stream));
+}
+
+int skv_batch_gather_gemm(const skv_bf16 *a, const skv_bf16 *b, const skv_bf16 *cos, const skv_bf16 *sin,
+                          const int32_t *position_ids, skv_bf16 *output, int batch_size, int heads, int seq_len,
+                          int embed_dim, int rank, int sparse_budget, int max_seq_len, int chunk_size,
+                          const int32_t *offset_array, skv_stream_t stream) {
+  (void)cos; (void)sin; (void)max_seq_len;
+  if (!a || !b || !position_ids || !output) { set_error("batch_gather_gemm: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (embed_dim != kHeadDim || chunk_size != kChunkTokens || sparse_budget % (kChunkTokens * kTileChunks)) {
+    set_error("batch_gather_gemm: need embed_dim=128, chunk_size=8, budget %% 128 == 0"); return SKV_ERR_UNSUPPORTED;
+  }
+  RebuildParams p{};
+  p.ids32 = position_ids; p.cnts = offset_array;
+  p.out = reinterpret_cast<__nv_bfloat16 *>(output);
+  p.out_stride_bh = int64_t(sparse_budget) * embed_dim;
+  p.out_row0 = 0;
+  p.H = heads; p.S = sparse_budget / chunk_size; p.L = seq_len; p.R = rank;
+  p.rope = 0;
+  p.tile_skip = 1;
+  const char *impl_env = getenv("SKV_REBUILD_IMPL");
+  return launch_rebuild(a, b, p, batch_size, impl_env && impl_env[0] == '1' ? 1 : 0, as_stream(stream));
+}
+
+}  // extern "C"
