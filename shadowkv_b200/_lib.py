@@ -1,0 +1,78 @@
+"""ctypes binding of include/shadowkv_b200.h.  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libshadowkv_b200.so")
+
+
+class SkvError(RuntimeError):
+    pass
+
+
+class Geom(C.Structure):
+    """struct skv_geom (include/shadowkv_b200.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "batch", "kv_heads", "q_groups", "head_dim", "chunk", "select", "n_landmarks", "rank", "seq_len",
+        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "reserved")]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`)."
+        " shadowkv_b200 has no CPU/PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+_SIGS = {
+    "skv_gather_copy": [_p, _p, _p] + [_i] * 5 + [_p],
+    "skv_gather_copy_d2d_with_offsets": [_p, _p, _p] + [_i] * 6 + [_p],
+    "skv_reorder_keys_and_compute_offsets": [_p, _p, _p, _p] + [_i] * 3 + [_p],
+    "skv_gather_copy_with_offsets": [_p] * 6 + [_i] * 7 + [_p],
+    "skv_apply_rotary_pos_emb": [_p] * 5 + [_i] * 14 + [_p],
+    "skv_apply_rotary_pos_emb_new": [_p] * 4 + [_i] * 13 + [_p],
+    "skv_apply_rotary_pos_emb_new_v2": [_p] * 4 + [_i] * 14 + [_p],
+    "skv_apply_rotary_pos_emb_push_cache": [_p] * 5 + [_i] * 19 + [_p],
+    "skv_apply_rotary_pos_emb_push_cache_opt": [_p] * 5 + [_i] * 19 + [_p],
+    "skv_apply_rotary_pos_emb_push_cache_opt_glm": [_p] * 5 + [_i] * 19 + [_p],
+    "skv_batch_gather_gemm": [_p] * 6 + [_i] * 9 + [_p, _p],
+    "skv_batch_gemm_softmax": [_p] * 6 + [_i] * 4 + [_f, _f, _p],
+    "skv_select_chunks": [C.POINTER(Geom)] + [_p] * 10,
+    "skv_compact_hits": [C.POINTER(Geom)] + [_p] * 5,
+    "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p],
+    "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 6 + [_i, _p],
+    "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p],
+    "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p],
+}
+# every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
+EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",
+                                "skv_attention_workspace_bytes"])
+
+for _name, _args in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = C.c_int
+lib.skv_version.restype = C.c_char_p
+lib.skv_last_error.restype = C.c_char_p
+lib.skv_select_workspace_bytes.argtypes = [C.POINTER(Geom)]
+lib.skv_select_workspace_bytes.restype = C.c_int64
+lib.skv_attention_workspace_bytes.argtypes = [_i] * 5
+lib.skv_attention_workspace_bytes.restype = C.c_int64
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.skv_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"{what}: unsupported argument: {msg}")
+        if rc == -2:
+            raise ValueError(f"{what}: bad argument: {msg}")
+        raise SkvError(f"{what}: rc={rc}: {msg}")
+
+
+def version() -> str:
+    return lib.skv_version().decode()

@@ -1,0 +1,378 @@
+"""Host-side mirror of the reference's ShadowKV caches (reference models/kv_cache.py).
+
+``ShadowKVCache_CPU`` keeps the reference's method names, argument meaning and state layout
+ so ``models/base.py:296-341`` can drive it unchanged, but every decode-step
+method lands in the fused sm_100a kernels behind the C ABI:
+
+=============================  =================================================================
+reference method (kv_cache.py)  here
+=============================  =================================================================
+update_kv_cache  (:1227-1271)   ``skv_append_kv``                         (1 launch, was 2 copies)
+get_retrieval_position_ids      ``skv_select_chunks``: scoring + softmax + GQA max + top-k + id
+  (:983-1057)                   gather + chunk-table update               (2 launches, was 8+)
+get_value_cache  (:1059-1106)   ``skv_compact_hits`` (V) + ``skv_fetch_misses`` from pinned host
+get_key_cache    (:1108-1176)   ``skv_compact_hits`` (K) + ``skv_rebuild_keys`` (tcgen05, RoPE in the
+                                epilogue; no bf16 scratch round trip)     (2 launches, was 3)
+=============================  =================================================================
+
+``decode_layer`` runs the whole per-layer step with the reference's stream choreography
+(``base.py:326-338``: V fetch on ``copy_stream`` overlapped with the K path) and the attention kernel.
+The prefill-side methods (``get_svd``, ``prefill_kv_cache``) build the state with torch ops; they are
+outside the hot path and kept only so the class is usable end to end.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import Geom, check, lib
+
+
+def _cs() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class ShadowKVCache_CPU:
+    """Batched ShadowKV cache: V chunked in pinned host memory, sparse K/V ring on the GPU, low-rank
+    K factors and landmarks on the GPU after ``H2D``.  Reference: models/kv_cache.py:509-1319."""
+
+    def __init__(self, config, batch_size: int = 1, max_length: int = 32 * 1024, device: str = "cuda:0",
+                 dtype=torch.bfloat16, sparse_budget: int = 2048, chunk_size: int = 8, rank: int = 160) -> None:
+        if dtype != torch.bfloat16:
+            raise ValueError("the sm_100a kernels compute in bf16 only")
+        self.config = config
+        self.batch_size = batch_size
+        self.max_length = max_length
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.num_attention_heads = config.num_attention_heads
+        self.num_key_value_heads = config.num_key_value_heads
+        self.num_key_value_groups = config.num_attention_heads // config.num_key_value_heads
+        self.head_dim = config.hidden_size // config.num_attention_heads
+        self.num_layers = config.num_hidden_layers
+
+        self.sparse_budget = int(sparse_budget)
+        self.chunk_size = chunk_size
+        self.rank = rank
+        self.local_chunk = 4                                             # kv_cache.py:547
+        self.outlier_chunk = int((self.sparse_budget // 1024) * 24)      # kv_cache.py:548
+        self.select_sets = self.sparse_budget // self.chunk_size
+        assert self.select_sets * self.chunk_size == self.sparse_budget, \
+            f"({self.select_sets}) * {self.chunk_size} != {self.sparse_budget}"
+        if self.head_dim != 128 or self.chunk_size != 8:
+            raise ValueError("kernels are built for head_dim 128 and chunk_size 8 (2 KiB chunks)")
+        if self.select_sets not in (128, 256, 512, 1024):
+            raise ValueError("sparse_budget must be 1024, 2048, 4096 or 8192")
+
+        L, B, H, D = self.num_layers, batch_size, self.num_key_value_heads, self.head_dim
+        # pinned-host chunk-major V store                      kv_cache.py:554-563
+        self.v_cache_cpu = torch.zeros(L, B, H, max_length // chunk_size, D * chunk_size, dtype=dtype,
+                                       device="cpu", pin_memory=True)
+        self.buf_len = self.sparse_budget + 128 + (self.outlier_chunk + self.local_chunk) * chunk_size   # :574
+        self.k_cache_buffer = torch.zeros(L, B, H, self.buf_len, D, dtype=dtype, device=self.device)
+        self.v_cache_buffer = torch.zeros(L, B, H, self.buf_len, D, dtype=dtype, device=self.device)
+
+        self.kv_offset = 0
+        self.prefill = 0
+        self.gen_offset = 0
+        self.prefilled_batch = 0
+        self.k_landmark = None
+        self.k_landmark_idx = None
+        self.U = None
+        self.SV = None
+
+        self.block_num = B * H
+        self.offsets = torch.zeros(self.block_num * self.select_sets, dtype=torch.int32, device=self.device)
+        self.cnts = torch.zeros(self.block_num, dtype=torch.int32, device=self.device)
+        self.position_ids = torch.full((L, B, H, self.select_sets), -1, dtype=torch.int64, device=self.device)
+
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._fetch_done = torch.cuda.Event()
+        self._geom = None
+        self._sel_ws = None
+        self._attn_ws = None
+        self.rebuild_impl = 0      # 0: tcgen05 (product); 1: SIMT cross-check (tests only)
+        self.rope_glm = False
+
+    # ------------------------------------------------------------------------------------------
+    def print_stats(self):
+        print(f"ShadowKV_CPU | sparse budget {self.sparse_budget} | chunk size {self.chunk_size} |rank {self.rank} "
+              f"| cached {self.kv_offset} | local_chunk {self.local_chunk} | outlier_chunk {self.outlier_chunk}")
+
+    def get_kv_len(self):
+        return self.kv_offset
+
+    def clear(self):
+        self.k_cache_buffer.zero_()
+        self.v_cache_buffer.zero_()
+        self.k_landmark = self.k_landmark_idx = self.U = self.SV = None
+        self.kv_offset = self.prefill = self.gen_offset = self.prefill_local = 0
+        self.prefilled_batch = 0
+        self.position_ids.fill_(-1)
+        self._geom = None
+
+    # ------------------------------------------------------------------------------------------
+    # geometry / scratch
+    # ------------------------------------------------------------------------------------------
+    def _set_layout(self, incoming: int) -> None:
+        """Region boundaries of the K/V buffers for a prompt of `incoming` tokens (kv_cache.py:819-894)."""
+        self.prefill = incoming
+        self.max_ctx_chunks_len = (incoming // self.chunk_size) * self.chunk_size
+        self.chunks = incoming // self.chunk_size - self.local_chunk
+        self.chunks -= self.chunks % 8                                   # :836
+        self.prefill_local = incoming - self.chunks * self.chunk_size
+        self.sparse_start = self.prefill_local + self.outlier_chunk * self.chunk_size
+        self.sparse_end = self.sparse_start + self.sparse_budget
+        self.kernel_offset = self.sparse_start * self.head_dim
+        self.kernel_stride = self.buf_len * self.head_dim
+        if self.sparse_end > self.buf_len:
+            raise ValueError("prompt leaves no room for the sparse region in the K/V buffers")
+
+    def _geometry(self, cos_sin_cache=None) -> Geom:
+        if self._geom is None:
+            if self.k_landmark is None or self.U is None:
+                raise RuntimeError("cache state not built: run prefill (or load_state) and H2D() first")
+            g = Geom()
+            g.batch, g.kv_heads, g.q_groups = self.batch_size, self.num_key_value_heads, self.num_key_value_groups
+            g.head_dim, g.chunk, g.select = self.head_dim, self.chunk_size, self.select_sets
+            g.n_landmarks = self.k_landmark.shape[-2]
+            g.rank = self.U.shape[-1]
+            g.seq_len = self.U.shape[-2]
+            g.buf_len, g.sparse_start = self.buf_len, self.sparse_start
+            self._geom = g
+            self._sel_ws = torch.empty(lib.skv_select_workspace_bytes(C.byref(g)), dtype=torch.uint8,
+                                       device=self.device)
+            self._attn_ws = torch.zeros(
+                lib.skv_attention_workspace_bytes(g.batch, g.kv_heads, g.q_groups, g.head_dim, 0),
+                dtype=torch.uint8, device=self.device)
+        if cos_sin_cache is not None:
+            width = cos_sin_cache.shape[-1]
+            if width not in (self.head_dim, self.head_dim // 2):
+                raise ValueError(f"Invalid cos_sin shape {tuple(cos_sin_cache.shape)}")     # tensor_op.py:197
+            self._geom.rope_glm = 1 if width == self.head_dim // 2 else 0
+            self._geom.cos_sin_rows = cos_sin_cache.shape[0]
+        return self._geom
+
+    # ------------------------------------------------------------------------------------------
+    # prefill side (torch ops; outside the hot path)
+    # ------------------------------------------------------------------------------------------
+    def get_svd(self, new_k_cache, layer_idx):
+        """Rank-`rank` factorisation of the pre-RoPE keys (kv_cache.py:666-737)."""
+        if new_k_cache.shape[1] <= 32:
+            k = new_k_cache.transpose(1, 2).reshape(new_k_cache.shape[0], -1, self.num_key_value_heads * self.head_dim)
+        else:
+            k = new_k_cache
+        bsz, L = k.shape[0], k.shape[1]
+        if layer_idx == 0 and self.prefilled_batch == 0:
+            self.U = torch.zeros(self.num_layers, self.batch_size, L, self.rank, dtype=self.dtype, device="cpu")
+            self.SV = torch.zeros(self.num_layers, self.batch_size, self.num_key_value_heads, self.head_dim,
+                                  self.rank, dtype=self.dtype, device="cpu")
+        u, s, vh = torch.linalg.svd(k.float(), full_matrices=False)
+        sl = slice(self.prefilled_batch, self.prefilled_batch + bsz)
+        self.U[layer_idx][sl].copy_(u[:, :, :self.rank].to(self.dtype))
+        sv = (s[:, :self.rank, None] * vh[:, :self.rank]).to(self.dtype)             # [bsz, rank, H*D]
+        sv = sv.view(bsz, self.rank, self.num_key_value_heads, self.head_dim).permute(0, 2, 3, 1)
+        self.SV[layer_idx][sl].copy_(sv)                                             # [bsz, H, D, rank]
+
+    def register_k_landmark(self, k_landmark, k_landmark_idx, layer_idx):
+        """kv_cache.py:739-786"""
+        n = k_landmark.shape[-2]
+        bsz = k_landmark.shape[0]
+        if layer_idx == 0 and self.prefilled_batch == 0:
+            self.k_landmark = torch.zeros(self.num_layers, self.batch_size, self.num_key_value_heads, n,
+                                          self.head_dim, dtype=self.dtype, device="cpu")
+            self.k_landmark_idx = torch.zeros(self.num_layers, self.batch_size, self.num_key_value_heads, n,
+                                              dtype=torch.long, device="cpu")
+        sl = slice(self.prefilled_batch, self.prefilled_batch + bsz)
+        self.k_landmark[layer_idx][sl].copy_(k_landmark)
+        self.k_landmark_idx[layer_idx][sl].copy_(k_landmark_idx)
+
+    def prefill_kv_cache(self, new_v_cache, layer_idx, key_states_roped, last_query_states=None):
+        """Builds one layer of decode state from the prompt's K/V (kv_cache.py:788-980)."""
+        bsz, H, incoming, D = new_v_cache.shape
+        C_ = self.chunk_size
+        self._set_layout(incoming)
+        sl = slice(self.prefilled_batch, self.prefilled_batch + bsz)
+        n_chunks_all = incoming // C_
+        self.v_cache_cpu[layer_idx][sl, :, :n_chunks_all].copy_(
+            new_v_cache[:, :, :self.max_ctx_chunks_len].reshape(bsz, H, n_chunks_all, C_ * D), non_blocking=True)
+        # local window = the tail of the prompt
+        self.k_cache_buffer[layer_idx][sl, :, :self.prefill_local].copy_(key_states_roped[:, :, -self.prefill_local:])
+        self.v_cache_buffer[layer_idx][sl, :, :self.prefill_local].copy_(new_v_cache[:, :, -self.prefill_local:])
+
+        n = self.chunks
+        k_ctx = key_states_roped[:, :, :n * C_].view(bsz, H, n, C_, D)
+        v_ctx = new_v_cache[:, :, :n * C_].view(bsz, H, n, C_, D)
+        means = k_ctx.mean(dim=-2)
+        cos = torch.nn.functional.cosine_similarity(means.unsqueeze(3).expand(-1, -1, -1, C_, -1), k_ctx, dim=-1)
+        outlier = cos.min(dim=-1).values.topk(self.outlier_chunk, largest=False).indices        # [bsz,H,o]
+        ex = outlier[..., None, None].expand(-1, -1, -1, C_, D)
+        lo, hi = self.prefill_local, self.sparse_start
+        self.k_cache_buffer[layer_idx][sl, :, lo:hi].copy_(k_ctx.gather(2, ex).reshape(bsz, H, -1, D))
+        self.v_cache_buffer[layer_idx][sl, :, lo:hi].copy_(v_ctx.gather(2, ex).reshape(bsz, H, -1, D))
+
+        keep = torch.ones(bsz, H, n, dtype=torch.bool, device=means.device)
+        keep.scatter_(-1, outlier, False)
+        rest_idx = torch.arange(n, device=means.device).expand(bsz, H, -1)[keep].view(bsz, H, -1)
+        lm = means.gather(2, rest_idx.unsqueeze(-1).expand(-1, -1, -1, D))
+        self.register_k_landmark(lm, rest_idx, layer_idx)
+
+        # first fill of the sparse region with the prompt's last query (kv_cache.py:926-970)
+        q = last_query_states.view(-1, H, self.num_key_value_groups, D)
+        att = torch.einsum("bhgd,bhcd->bhgc", q, lm.to(q.device)) / math.sqrt(128)
+        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(self.dtype).max(dim=-2).values
+        sel = rest_idx.to(q.device).gather(-1, att.topk(self.select_sets, dim=-1).indices)
+        self.position_ids[layer_idx][sl].copy_(sel)
+        tok = (sel.unsqueeze(-1) * C_ + torch.arange(C_, device=sel.device)).view(bsz, H, -1)
+        ex = tok.unsqueeze(-1).expand(-1, -1, -1, D)
+        self.v_cache_buffer[layer_idx][sl, :, self.sparse_start:self.sparse_end].copy_(new_v_cache.gather(-2, ex))
+        self.k_cache_buffer[layer_idx][sl, :, self.sparse_start:self.sparse_end].copy_(key_states_roped.gather(-2, ex))
+
+        if layer_idx == self.num_layers - 1:
+            assert self.sparse_budget < incoming
+            self.prefilled_batch += bsz
+            if self.prefilled_batch == self.batch_size:
+                self.kv_offset += incoming
+                assert not bool(torch.any(self.position_ids == -1)), "the cache for offloading is not built correctly"
+
+    def H2D(self):
+        """Move factors and landmarks to the GPU (kv_cache.py:1178-1225)."""
+        for name in ("SV", "U", "k_landmark", "k_landmark_idx"):
+            t = getattr(self, name)
+            if t is not None and not t.is_cuda:
+                setattr(self, name, t.to(self.device))
+        self._geom = None
+        torch.cuda.synchronize(self.device)
+
+    def load_state(self, *, prompt_len: int, U, SV, k_landmark, k_landmark_idx, position_ids=None):
+        """Install externally built decode state (synthetic benches, tests): tensors laid out as
+        SURVEY.md section 8 a1.  V store and K/V buffers are filled by the caller through the public
+        attributes.  Replaces get_svd/prefill_kv_cache + H2D."""
+        self._set_layout(prompt_len)
+        self.U, self.SV, self.k_landmark, self.k_landmark_idx = U, SV, k_landmark, k_landmark_idx
+        if position_ids is not None:
+            self.position_ids.copy_(position_ids)
+        self.kv_offset = prompt_len
+        self.prefilled_batch = self.batch_size
+        self.H2D()
+
+    # ------------------------------------------------------------------------------------------
+    # decode step
+    # ------------------------------------------------------------------------------------------
+    def update_kv_cache(self, new_k_cache, new_v_cache, layer_idx):
+        """Append the new token's post-RoPE K and V rows (kv_cache.py:1227-1271)."""
+        incoming = new_k_cache.shape[-2]
+        if incoming != 1:
+            raise ValueError("decode appends one token per step")
+        g = self._geometry()
+        pos = self.sparse_end + self.gen_offset
+        if pos >= self.buf_len:
+            raise RuntimeError(f"generation buffer full ({self.buf_len - self.sparse_end} tokens)")
+        check(lib.skv_append_kv(C.byref(g), new_k_cache.contiguous().data_ptr(), new_v_cache.contiguous().data_ptr(),
+                                self.k_cache_buffer[layer_idx].data_ptr(), self.v_cache_buffer[layer_idx].data_ptr(),
+                                pos, _cs()), "append_kv")
+        if layer_idx == self.num_layers - 1:
+            self.kv_offset += incoming
+            self.gen_offset += incoming
+
+    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None):
+        """Score landmarks, pick the top chunks and update the chunk table (kv_cache.py:983-1057).
+        Returns position_ids[layer] (chunk id resident in every sparse slot), updated in place."""
+        self.incoming_q_len = query_states.shape[-2]
+        if self.incoming_q_len != 1:
+            raise ValueError("decode scores one query token per step")
+        g = self._geometry()
+        q = query_states.contiguous()
+        check(lib.skv_select_chunks(C.byref(g), q.data_ptr(), self.k_landmark[layer_idx].data_ptr(),
+                                    self.k_landmark_idx[layer_idx].data_ptr(), self.position_ids[layer_idx].data_ptr(),
+                                    self.offsets.data_ptr(), self.cnts.data_ptr(),
+                                    selected_out.data_ptr() if selected_out is not None else 0,
+                                    score_out.data_ptr() if score_out is not None else 0,
+                                    self._sel_ws.data_ptr(), _cs()), "select_chunks")
+        return self.position_ids[layer_idx]
+
+    def _view_len(self, layer_idx):
+        gen = self.gen_offset if layer_idx == self.num_layers - 1 else self.gen_offset + self.incoming_q_len
+        return self.sparse_end + gen
+
+    def get_value_cache(self, layer_idx, position_ids):
+        """Compact the hit chunks, fetch the missed ones from pinned host memory (kv_cache.py:1059-1106)."""
+        g = self._geometry()
+        st = _cs()
+        vb = self.v_cache_buffer[layer_idx]
+        check(lib.skv_compact_hits(C.byref(g), 0, vb.data_ptr(), self.offsets.data_ptr(), self.cnts.data_ptr(), st),
+              "compact_hits(V)")
+        vh = self.v_cache_cpu[layer_idx]
+        check(lib.skv_fetch_misses(C.byref(g), vh.data_ptr(), vh.stride(1), vb.data_ptr(), self.offsets.data_ptr(),
+                                   self.cnts.data_ptr(), st), "fetch_misses")
+        return vb[:, :, :self._view_len(layer_idx)]
+
+    def get_key_cache(self, layer_idx, position_ids, rope_func, cos_sin_cache):
+        """Compact the hit chunks, rebuild + RoPE the missed ones from U.SV (kv_cache.py:1108-1176).
+        rope_func is accepted for signature compatibility and unused, as in the reference."""
+        g = self._geometry(cos_sin_cache)
+        st = _cs()
+        kb = self.k_cache_buffer[layer_idx]
+        check(lib.skv_compact_hits(C.byref(g), kb.data_ptr(), 0, self.offsets.data_ptr(), self.cnts.data_ptr(), st),
+              "compact_hits(K)")
+        check(lib.skv_rebuild_keys(C.byref(g), self.U[layer_idx].data_ptr(), self.SV[layer_idx].data_ptr(),
+                                   cos_sin_cache.data_ptr(), self.position_ids[layer_idx].data_ptr(),
+                                   self.cnts.data_ptr(), kb.data_ptr(), self.rebuild_impl, st), "rebuild_keys")
+        return kb[:, :, :self._view_len(layer_idx)]
+
+    def attention(self, layer_idx, query_states, kv_len=None, out=None):
+        """softmax(q K^T / sqrt(D)) V over rows [0, kv_len) of this layer's buffers (base.py:341)."""
+        g = self._geometry()
+        kv_len = self._view_len(layer_idx) if kv_len is None else kv_len
+        q = query_states.contiguous()
+        B, Hq = q.shape[0], q.shape[1]
+        if out is None:
+            out = torch.empty(B, 1, Hq, self.head_dim, dtype=self.dtype, device=self.device)
+        kb, vb = self.k_cache_buffer[layer_idx], self.v_cache_buffer[layer_idx]
+        check(lib.skv_attention_decode(q.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), B,
+                                       g.kv_heads, g.q_groups, g.head_dim, kv_len, kb.stride(0), kb.stride(1),
+                                       kb.stride(2), 1.0 / math.sqrt(self.head_dim), 0, self._attn_ws.data_ptr(),
+                                       _cs()), "attention_decode")
+        return out
+
+    def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None):
+        """The whole per-layer sparse-KV decode step, with the reference's stream choreography
+        (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
+        query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D]."""
+        self.update_kv_cache(key_states, value_states, layer_idx)
+        pid = self.get_retrieval_position_ids(layer_idx, query_states)
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.get_value_cache(layer_idx, pid)
+        self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
+        cur.wait_stream(self.copy_stream)
+        kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
+        return self.attention(layer_idx, query_states, kv_len, out)
+
+
+class ShadowKVCache(ShadowKVCache_CPU):
+    """Batch-1 variant with V resident on the GPU and no chunk cache (reference models/kv_cache.py:155-506):
+    every step rebuilds all S chunks.  Same kernels; the resident table is cleared before each selection so
+    every chunk is a miss and the V "fetch" reads the device-resident store."""
+
+    def __init__(self, config, batch_size=1, max_length=32 * 1024, device="cuda:0", dtype=torch.bfloat16,
+                 sparse_budget=2048, chunk_size=8, rank=160) -> None:
+        assert batch_size == 1, "ShadowKV class only supports batch_size=1, please use ShadowKV_CPU class for batch_size > 1"
+        super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank)
+        self.outlier_chunk = 48                                            # kv_cache.py:206
+        self.v_cache_cpu = self.v_cache_cpu.to(self.device)                # GPU-resident full V (kv_cache.py:222-230)
+
+    def print_stats(self):
+        print(f"ShadowKV | sparse budget {self.sparse_budget} | chunk size {self.chunk_size} |rank {self.rank} "
+              f"| cached {self.kv_offset} | local_chunk {self.local_chunk} | outlier_chunk {self.outlier_chunk}")
+
+    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None):
+        self.position_ids[layer_idx].fill_(-1)
+        chunk_ids = super().get_retrieval_position_ids(layer_idx, query_states, selected_out, score_out)
+        # token-level ids, as the reference returns for this class (kv_cache.py:440-445)
+        ar = torch.arange(self.chunk_size, device=chunk_ids.device)
+        return (chunk_ids.unsqueeze(-1) * self.chunk_size + ar).view(self.batch_size, self.num_key_value_heads, -1)

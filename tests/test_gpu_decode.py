@@ -1,0 +1,133 @@
+"""The whole per-layer decode step through the reference-shaped cache object, against the oracle, over
+several steps (chunk cache warm) and layers; Llama (neox RoPE, G=4) and GLM (interleaved RoPE, G=8)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import shadowkv_oracle as O
+from shadowkv_b200 import synth
+from tests.tolerances import assert_close_bf16, assert_ulp_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(cuda, model, B, prompt_len, budget, layers, rank=160):
+    from shadowkv_b200.kv_cache import ShadowKVCache_CPU
+    shape = synth.MODELS[model]
+    cs = synth.cos_sin_table(prompt_len + 1024, 128, theta=shape.rope_theta, glm=shape.glm_rope)
+    states = [synth.layer_state(shape, B, prompt_len, seed=1000 + l, rank=rank, sparse_budget=budget, cos_sin=cs)
+              for l in range(layers)]
+    cache = ShadowKVCache_CPU(shape.config(layers), batch_size=B, max_length=prompt_len, device=str(cuda),
+                              sparse_budget=budget, rank=rank)
+    synth.install(cache, states)
+    lay = states[0]["layout"]
+    ora = [O.LayerState(landmarks=s["k_landmark"], landmark_idx=s["k_landmark_idx"], U=s["U"], SV=s["SV"],
+                        v_host=s["v_chunks"], k_buf=s["k_buf"].clone(), v_buf=s["v_buf"].clone(),
+                        resident=s["resident"].clone()) for s in states]
+    geo = O.Geometry(sparse_start=lay.sparse_start, sparse_end=lay.sparse_end)
+    return shape, cache, ora, geo, cs, lay
+
+
+@pytest.mark.parametrize("model,B,prompt_len,budget", [("llama-3.1-8b", 2, 8192, 1024), ("glm-4-9b-1m", 1, 8192, 1024),
+                                                       ("llama-3.1-8b", 1, 32768, 2048)])
+def test_decode_steps_match_oracle(cuda, model, B, prompt_len, budget):
+    layers, steps = 2, 4
+    shape, cache, ora, geo, cs, lay = _build(cuda, model, B, prompt_len, budget, layers)
+    d_cs = cs.to(cuda)
+    H, S = shape.num_key_value_heads, lay.select
+    base = None
+    hit_rates = []
+    for step in range(steps):
+        geo.gen_offset = step
+        for l in range(layers):
+            q, kn, vn = synth.queries(shape, B, seed=50 * step + l, base=base, noise=0.35)
+            if base is None:
+                base = q
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            # --- the calls of base.py:320-341, one by one ------------------------------------------------
+            cache.update_kv_cache(dk, dv, l)
+            sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+            pid = cache.get_retrieval_position_ids(layer_idx=l, query_states=dq, selected_out=sel)
+            cur = torch.cuda.current_stream()
+            cache.copy_stream.wait_stream(cur)
+            with torch.cuda.stream(cache.copy_stream):
+                v_view = cache.get_value_cache(l, pid)
+            k_view = cache.get_key_cache(layer_idx=l, position_ids=pid, rope_func=None, cos_sin_cache=d_cs)
+            torch.cuda.current_stream().wait_stream(cache.copy_stream)
+            from shadowkv_b200.attention import flash_attn_with_kvcache
+            out = flash_attn_with_kvcache(q=dq.transpose(1, 2), k_cache=k_view.transpose(1, 2),
+                                          v_cache=v_view.transpose(1, 2), causal=True)
+            torch.cuda.synchronize()
+            # --- oracle, forced onto the kernel's selection after checking it ---------------------------
+            want, info = O.decode_step(ora[l], geo, q, kn, vn, cs, selected_override=sel.cpu())
+            for b in range(B):
+                for h in range(H):
+                    a, bb = set(sel[b, h].tolist()), set(info["own_selected"][b, h].tolist())
+                    assert len(a) == S
+                    assert len(a ^ bb) <= max(8, S // 16), f"selection differs in {len(a ^ bb)} chunks"
+            np.testing.assert_array_equal(cache.cnts.cpu().numpy(), info["cnts"])
+            np.testing.assert_array_equal(cache.offsets.cpu().numpy().reshape(B * H, S), info["offsets"])
+            assert torch.equal(cache.position_ids[l].cpu(), ora[l].resident)
+            L_att = lay.sparse_end + step + 1
+            assert k_view.shape[2] == L_att and v_view.shape[2] == L_att
+            assert torch.equal(cache.v_cache_buffer[l].cpu()[:, :, :L_att], ora[l].v_buf[:, :, :L_att]), "V buffer bytes"
+            assert_ulp_bf16(cache.k_cache_buffer[l].cpu()[:, :, :L_att], ora[l].k_buf[:, :, :L_att], ulps=2,
+                            frac_exact=0.95, what="K buffer")
+            assert_close_bf16(out, want, what=f"attention step {step} layer {l}")
+            hit_rates.append(float(info["cnts"].mean()) / S)
+            # keep the oracle's K bit-identical to the kernel's so 1-ulp rebuild differences do not pile up
+            ora[l].k_buf.copy_(cache.k_cache_buffer[l].cpu())
+        cache_gen = cache.gen_offset
+        assert cache_gen == step + 1
+    assert max(hit_rates[layers:]) > 0.2, "correlated queries should give cache hits"
+
+
+def test_decode_layer_fused_equals_stepwise(cuda):
+    """decode_layer (stream-overlapped, one call) gives the same bytes as the method-by-method sequence."""
+    shape, c1, _, _, cs, lay = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2)
+    _, c2, _, _, _, _ = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2)
+    d_cs = cs.to(cuda)
+    from shadowkv_b200.attention import flash_attn_with_kvcache
+    base = None
+    for step in range(3):
+        for l in range(2):
+            q, kn, vn = synth.queries(shape, 2, seed=7 * step + l, base=base, noise=0.3)
+            base = q if base is None else base
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            o1 = c1.decode_layer(l, dq, dk, dv, d_cs)
+            c2.update_kv_cache(dk, dv, l)
+            pid = c2.get_retrieval_position_ids(l, dq)
+            vv = c2.get_value_cache(l, pid)
+            kk = c2.get_key_cache(l, pid, None, d_cs)
+            o2 = flash_attn_with_kvcache(dq.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), causal=True)
+            torch.cuda.synchronize()
+            assert torch.equal(c1.position_ids[l], c2.position_ids[l])
+            assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l])
+            assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l])
+            assert_close_bf16(o1, o2, max_abs=4e-3, what="fused vs stepwise")
+
+
+def test_uncached_variant_token_ids(cuda):
+    """ShadowKVCache (batch 1, no chunk cache; reference kv_cache.py:421-470) returns token-level ids and
+    rebuilds every chunk each step."""
+    from shadowkv_b200.kv_cache import ShadowKVCache
+    shape = synth.MODELS["llama-3.1-8b"]
+    prompt_len, budget = 8192, 1024
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    st = synth.layer_state(shape, 1, prompt_len, seed=3, sparse_budget=budget, cos_sin=cs)
+    cache = ShadowKVCache(shape.config(1), batch_size=1, max_length=prompt_len, device=str(cuda), sparse_budget=budget)
+    synth.install(cache, [st])
+    q, kn, vn = synth.queries(shape, 1, seed=1)
+    out = cache.decode_layer(0, q.to(cuda), kn.to(cuda), vn.to(cuda), cs.to(cuda))
+    torch.cuda.synchronize()
+    assert int(cache.cnts.sum()) == 0
+    lay = st["layout"]
+    ora = O.LayerState(landmarks=st["k_landmark"], landmark_idx=st["k_landmark_idx"], U=st["U"], SV=st["SV"],
+                       v_host=st["v_chunks"], k_buf=st["k_buf"].clone(), v_buf=st["v_buf"].clone(),
+                       resident=torch.full_like(st["resident"], -1))
+    geo = O.Geometry(sparse_start=lay.sparse_start, sparse_end=lay.sparse_end)
+    want, info = O.decode_step(ora, geo, q, kn, vn, cs, selected_override=cache.position_ids[0].cpu())
+    assert_close_bf16(out, want, what="uncached variant")
+    tok = cache.get_retrieval_position_ids(0, q.to(cuda))
+    assert tok.shape == (1, 8, budget)
+    assert torch.equal(tok.view(1, 8, -1, 8)[..., 0] // 8, cache.position_ids[0])

@@ -1,0 +1,118 @@
+"""Landmark scoring + chunk selection against the oracle.
+
+Scores are bf16-rounded fp32 dot products: a different fp32 summation order can move a value to the
+neighbouring bf16, so D / Softmax are compared to 1 bf16 ulp (and must be mostly bit-identical), and the
+selection is checked bit-exactly against the top-S rule applied to the kernel's OWN scores (ties: lowest
+landmark index), plus near-tie agreement with the oracle's scores."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import shadowkv_oracle as O
+from shadowkv_b200 import synth
+from tests.tolerances import assert_ulp_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("G,N", [(4, 4044), (8, 2048), (1, 1000), (16, 520), (4, 15560)])
+def test_batch_gemm_softmax(cuda, G, N):
+    from shadowkv_b200 import shadowkv
+    B, H = 2, 3
+    g = torch.Generator().manual_seed(N + G)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16)
+    gemm_o = torch.zeros(B, H, G, N, dtype=torch.bfloat16, device=cuda)
+    soft_o = torch.zeros_like(gemm_o)
+    T = (N + 255) // 256
+    norm = torch.zeros(B * H, G, T, device=cuda)
+    ssum = torch.zeros(B * H, G, T, device=cuda)
+    shadowkv.batch_gemm_softmax(q.to(cuda), lm.to(cuda), gemm_o, norm, ssum, soft_o, B * H, G, N, 128,
+                                1 / math.sqrt(128), 0)
+    torch.cuda.synchronize()
+    want_d, want_s = O.landmark_scores(q, lm)
+    assert_ulp_bf16(gemm_o, want_d, ulps=1, frac_exact=0.97, what="D")
+    assert_ulp_bf16(soft_o, want_s, ulps=2, frac_exact=0.90, what="Softmax")
+    assert float((soft_o.float().sum(-1) - 1).abs().max()) < 2e-2
+
+
+def _select(cuda, shape, N, S, seed, glm=False):
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    B = 2
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S]] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    d_res = resident.to(cuda)
+    off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+    sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+    score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.to(cuda).data_ptr(), lm.to(cuda).data_ptr(),
+                                          idx.to(cuda).data_ptr(), d_res.data_ptr(), off.data_ptr(), cnt.data_ptr(),
+                                          sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "select")
+    torch.cuda.synchronize()
+    return q, lm, idx, resident, d_res.cpu(), off.cpu().view(B * H, S), cnt.cpu(), sel.cpu(), score.cpu()
+
+
+@pytest.mark.parametrize("model,N,S", [("llama-3.1-8b", 4044, 256), ("glm-4-9b-1m", 2040, 128),
+                                       ("llama-3.1-8b", 15560, 256), ("yi-9b-200k", 3000, 512),
+                                       ("llama-3.1-8b", 1024, 1024)])
+def test_select_chunks(cuda, model, N, S):
+    shape = synth.MODELS[model]
+    q, lm, idx, resident, new_res, off, cnt, sel, score = _select(cuda, shape, N, S, seed=N + S)
+    B, H = sel.shape[:2]
+    _, soft = O.landmark_scores(q, lm)
+    want_sel, want_top, want_score = O.select_chunks(soft, idx, S)
+    assert_ulp_bf16(score, want_score, ulps=2, frac_exact=0.90, what="max-over-groups softmax")
+    pos_of = [{int(c): i for i, c in enumerate(idx.view(B * H, N)[r].tolist())} for r in range(B * H)]
+    for r in range(B * H):
+        b, h = divmod(r, H)
+        got_top = torch.tensor([pos_of[r][int(c)] for c in sel[b, h].tolist()])
+        # 1. bit-exact rule on the kernel's own scores: top-S, ties to the lowest index, emitted ascending
+        own = score[b, h].float()
+        rule = torch.sort(own, descending=True, stable=True).indices[:S].sort().values
+        assert torch.equal(got_top, rule), f"row {r}: selection is not top-S/lowest-index of the kernel's scores"
+        # 2. against the oracle's scores: differences only among near-ties of the S-th value
+        a, bset = set(got_top.tolist()), set(want_top[b, h].tolist())
+        kth = float(torch.sort(want_score[b, h].float(), descending=True).values[S - 1])
+        assert len(a ^ bset) <= max(8, S // 16), f"row {r}: {len(a ^ bset)} chunks differ"
+        for i in a ^ bset:
+            assert abs(float(want_score[b, h, i]) - kth) <= kth * 2 ** -6
+        # 3. chunk-table update is bit-exact given the kernel's selection
+        nk, no, nc = O.reorder_keys_and_compute_offsets(resident.view(B * H, S)[r:r + 1].numpy(),
+                                                        sel.view(B * H, S)[r:r + 1].numpy())
+        np.testing.assert_array_equal(new_res.view(B * H, S)[r].numpy(), nk[0])
+        np.testing.assert_array_equal(off[r].numpy(), no[0])
+        assert int(cnt[r]) == int(nc[0])
+
+
+def test_select_massive_ties(cuda):
+    """All landmarks identical -> every score ties; the rule must pick the S lowest indices."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    B, H, G, N, S = 1, 2, 4, 3000, 256
+    q = torch.randn(B, H * G, 1, 128).to(torch.bfloat16)
+    lm = torch.ones(B, H, N, 128, dtype=torch.bfloat16) * 0.01
+    idx = torch.arange(N).expand(B, H, N).contiguous() * 3
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=4000, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    res = torch.full((B, H, S), -1, dtype=torch.int64, device=cuda)
+    off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.to(cuda).data_ptr(), lm.to(cuda).data_ptr(),
+                                          idx.to(cuda).data_ptr(), res.data_ptr(), off.data_ptr(), cnt.data_ptr(), 0, 0,
+                                          ws.data_ptr(), torch.cuda.current_stream().cuda_stream), "select")
+    torch.cuda.synchronize()
+    assert (cnt.cpu() == 0).all()
+    assert torch.equal(res.cpu(), (torch.arange(S) * 3).expand(B, H, S))

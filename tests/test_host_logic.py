@@ -1,0 +1,37 @@
+"""Host-side geometry against the numbers the survey derived from the reference."""
+from shadowkv_b200 import synth
+
+
+def test_layout_cfg2_llama_122k():
+    lay = synth.layout(124928, 2048, 8)
+    assert lay.all_chunks == 15616
+    assert lay.chunks == 15608
+    assert lay.n_landmarks == 15560
+    assert lay.prefill_local == 64
+    assert (lay.sparse_start, lay.sparse_end, lay.buf_len) == (448, 2496, 2592)
+    assert lay.select == 256
+
+
+def test_layout_other_configs():
+    assert synth.layout(524288).n_landmarks == 65480          # cfg3
+    assert synth.layout(131072).n_landmarks == 16328          # cfg4
+    assert synth.layout(204800).n_landmarks == 25544          # cfg5
+    # budgets 1024 / 4096 of test/e2e.py:35-116
+    assert synth.layout(61440, 1024).outlier_chunk == 24
+    assert synth.layout(249856, 4096).select == 512
+
+
+def test_cos_sin_tables():
+    t = synth.cos_sin_table(64, 128)
+    assert t.shape == (64, 128)
+    assert float(t[0, :64].float().min()) == 1.0 and float(t[0, 64:].float().abs().max()) == 0.0
+    g = synth.cos_sin_table(64, 128, glm=True)
+    assert g.shape == (64, 64)
+
+
+def test_model_shapes():
+    m = synth.MODELS["llama-3.1-8b"]
+    cfg = m.config()
+    assert cfg.num_attention_heads // cfg.num_key_value_heads == 4
+    assert cfg.hidden_size // cfg.num_attention_heads == 128
+    assert synth.MODELS["glm-4-9b-1m"].glm_rope
