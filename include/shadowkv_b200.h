@@ -191,6 +191,15 @@ int skv_select_chunks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *l
                       const int64_t *landmark_idx, int64_t *resident, int32_t *offsets, int32_t *cnts,
                       int64_t *selected_out, skv_bf16 *score_out, void *workspace, skv_stream_t stream);
 
+/* The two launches of skv_select_chunks, individually (same arguments, same workspace): the scoring pass
+ * alone (HBM-bound stream over the landmarks; this is the kernel bench.py reports the roofline for) and the
+ * per-(b,h) selection + chunk-table update that consumes its scores. */
+int skv_score_landmarks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *landmarks, void *workspace,
+                        skv_stream_t stream);
+int skv_select_from_scores(const skv_geom *geom, const int64_t *landmark_idx, int64_t *resident, int32_t *offsets,
+                           int32_t *cnts, int64_t *selected_out, skv_bf16 *score_out, void *workspace,
+                           skv_stream_t stream);
+
 /* (a6)+(a7) hit compaction for K and V in one cluster-staged launch (no temp buffer):
  * for i < cnts[bh]: slot i <- slot offsets[bh*S+i] in both buffers.  Either buffer may be NULL. */
 int skv_compact_hits(const skv_geom *geom, skv_bf16 *k_buf, skv_bf16 *v_buf, const int32_t *offsets,
@@ -209,9 +218,11 @@ int skv_rebuild_keys(const skv_geom *geom, const skv_bf16 *U, const skv_bf16 *SV
                      const int64_t *resident, const int32_t *cnts, skv_bf16 *k_buf, int impl,
                      skv_stream_t stream);
 
-/* (a2) append the new token's K and V rows at buffer row `pos` of every (b,h). k_new/v_new [B,H,D]. */
+/* (a2) append the new token's K and V rows at buffer row `pos` of every (b,h). k_new/v_new [B,H,D].
+ * pos_dev (optional, device int32): when non-NULL the row is pos + *pos_dev, read on the device, so the
+ * same launch can be replayed from a CUDA graph while the generation offset advances. */
 int skv_append_kv(const skv_geom *geom, const skv_bf16 *k_new, const skv_bf16 *v_new, skv_bf16 *k_buf,
-                  skv_bf16 *v_buf, int pos, skv_stream_t stream);
+                  skv_bf16 *v_buf, int pos, const int32_t *pos_dev, skv_stream_t stream);
 
 /* Bytes of device scratch skv_attention_decode needs (split partials + arrival counters). */
 int64_t skv_attention_workspace_bytes(int batch, int kv_heads, int q_groups, int head_dim, int max_splits);
@@ -219,11 +230,13 @@ int64_t skv_attention_workspace_bytes(int batch, int kv_heads, int q_groups, int
 /* (a8) replacement for flash_attn_with_kvcache(q, k_cache, v_cache, causal=True) with one query token
  * (reference models/base.py:341): out[b, h*G+g, :] = softmax(q K^T / sqrt(D)) V over rows [0, kv_len).
  * k/v element strides: (batch, head, row); rows are D contiguous elements.  workspace must be zeroed
- * once at allocation (the kernel leaves its counters at zero).  num_splits <= 0 picks a split count. */
+ * once at allocation (the kernel leaves its counters at zero).  num_splits <= 0 picks a split count.
+ * kv_len_dev (optional, device int32): when non-NULL the attended length is min(kv_len, *kv_len_dev) read on
+ * the device and kv_len only sizes the grid (CUDA-graph replay with a growing cache). */
 int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch,
                          int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b,
                          int64_t stride_h, int64_t stride_row, float scale, int num_splits, void *workspace,
-                         skv_stream_t stream);
+                         const int32_t *kv_len_dev, skv_stream_t stream);
 
 #ifdef __cplusplus
 }

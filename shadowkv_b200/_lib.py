@@ -42,11 +42,13 @@ _SIGS = {
     "skv_batch_gather_gemm": [_p] * 6 + [_i] * 9 + [_p, _p],
     "skv_batch_gemm_softmax": [_p] * 6 + [_i] * 4 + [_f, _f, _p],
     "skv_select_chunks": [C.POINTER(Geom)] + [_p] * 10,
+    "skv_score_landmarks": [C.POINTER(Geom)] + [_p] * 4,
+    "skv_select_from_scores": [C.POINTER(Geom)] + [_p] * 8,
     "skv_compact_hits": [C.POINTER(Geom)] + [_p] * 5,
     "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p],
     "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 6 + [_i, _p],
-    "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p],
-    "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p],
+    "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
+    "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
 }
 # every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
 EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",

@@ -43,6 +43,6 @@ def flash_attn_with_kvcache(q, k_cache, v_cache, causal=True, softmax_scale=None
     scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(D)
     check(lib.skv_attention_decode(qc.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), B, H, G, D,
                                    Lp, k_cache.stride(0), k_cache.stride(2), k_cache.stride(1), float(scale),
-                                   int(num_splits), _workspace(q.device, B, H, G).data_ptr(),
+                                   int(num_splits), _workspace(q.device, B, H, G).data_ptr(), 0,
                                    torch.cuda.current_stream().cuda_stream), "attention_decode")
     return out

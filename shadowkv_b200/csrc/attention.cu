@@ -19,6 +19,7 @@ struct AttnParams {
   float *part_o;         // [rows, max_splits, GT, 128]
   float *part_ml;        // [rows, max_splits, GT, 2]
   int *counters;         // [rows]
+  const int32_t *kv_len_dev;   // optional device-side length
   int B, H, G, ngz, kv_len, keys_per_split, num_splits;
   int64_t sb, sh, sr;
   float scale_log2;      // scale * log2(e)
@@ -51,8 +52,9 @@ __global__ void __launch_bounds__(kAttnThreads)
     }
   }
 
+  const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
   const int k_begin = split * p.keys_per_split;
-  const int k_end = min(p.kv_len, k_begin + p.keys_per_split);
+  const int k_end = min(kv_len, k_begin + p.keys_per_split);
   const int4 *kbase = reinterpret_cast<const int4 *>(p.k + size_t(b) * p.sb + size_t(h) * p.sh);
   const int4 *vbase = reinterpret_cast<const int4 *>(p.v + size_t(b) * p.sb + size_t(h) * p.sh);
   const size_t row_i4 = size_t(p.sr) / 8;          // int4 per row stride
@@ -244,9 +246,12 @@ __global__ void __launch_bounds__(kAttnThreads)
 
 // (a2) append: one row of K and V per (b,h)
 __global__ void append_kv_kernel(const int4 *__restrict__ k_new, const int4 *__restrict__ v_new, int4 *__restrict__ k_buf,
-                                 int4 *__restrict__ v_buf, int BH, int64_t buf_rows, int pos) {
+                                 int4 *__restrict__ v_buf, int BH, int64_t buf_rows, int pos,
+                                 const int32_t *__restrict__ pos_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;      // BH * 16 int4
   if (i >= BH * 16) return;
+  if (pos_dev) pos += *pos_dev;
+  if (pos >= buf_rows) return;                              // generation region full: drop (host checks too)
   const int bh = i >> 4, c = i & 15;
   const size_t dst = (size_t(bh) * buf_rows + pos) * 16 + c;
   k_buf[dst] = k_new[i];
@@ -267,13 +272,14 @@ int64_t skv_attention_workspace_bytes(int batch, int kv_heads, int q_groups, int
 
 int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch,
                          int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b, int64_t stride_h,
-                         int64_t stride_row, float scale, int num_splits, void *workspace, skv_stream_t stream) {
+                         int64_t stride_row, float scale, int num_splits, void *workspace,
+                         const int32_t *kv_len_dev, skv_stream_t stream) {
   if (!q || !k || !v || !out || !workspace) { set_error("attention_decode: null pointer"); return SKV_ERR_ARGUMENT; }
   if (head_dim != kHeadDim || q_groups < 1 || kv_len < 1 || (stride_row % 8) || (stride_h % 8) || (stride_b % 8)) {
     set_error("attention_decode: need head_dim=128 and 16-byte aligned strides"); return SKV_ERR_UNSUPPORTED;
   }
   AttnParams p{};
-  p.q = q; p.k = k; p.v = v; p.out = out;
+  p.q = q; p.k = k; p.v = v; p.out = out; p.kv_len_dev = kv_len_dev;
   p.B = batch; p.H = kv_heads; p.G = q_groups; p.ngz = (q_groups + kAttnGT - 1) / kAttnGT; p.kv_len = kv_len;
   p.sb = stride_b; p.sh = stride_h; p.sr = stride_row;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -301,13 +307,13 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
 }
 
 int skv_append_kv(const skv_geom *g, const skv_bf16 *k_new, const skv_bf16 *v_new, skv_bf16 *k_buf, skv_bf16 *v_buf,
-                  int pos, skv_stream_t stream) {
+                  int pos, const int32_t *pos_dev, skv_stream_t stream) {
   if (!g || !k_new || !v_new || !k_buf || !v_buf) { set_error("append_kv: null pointer"); return SKV_ERR_ARGUMENT; }
   if (g->head_dim != kHeadDim || pos < 0 || pos >= g->buf_len) { set_error("append_kv: pos %d outside buffer", pos); return SKV_ERR_ARGUMENT; }
   const int BH = g->batch * g->kv_heads;
   append_kv_kernel<<<(BH * 16 + 127) / 128, 128, 0, as_stream(stream)>>>(
       reinterpret_cast<const int4 *>(k_new), reinterpret_cast<const int4 *>(v_new), reinterpret_cast<int4 *>(k_buf),
-      reinterpret_cast<int4 *>(v_buf), BH, g->buf_len, pos);
+      reinterpret_cast<int4 *>(v_buf), BH, g->buf_len, pos, pos_dev);
   return launch_status("append_kv_kernel");
 }
 

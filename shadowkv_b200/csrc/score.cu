@@ -378,23 +378,36 @@ int64_t skv_select_workspace_bytes(const skv_geom *g) {
   return align_up(BH * g->q_groups * g->n_landmarks * 2, 256) + 2 * align_up(BH * g->q_groups * T * 4, 256);
 }
 
-int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, const int64_t *landmark_idx,
-                      int64_t *resident, int32_t *offsets, int32_t *cnts, int64_t *selected_out,
-                      skv_bf16 *score_out, void *workspace, skv_stream_t stream) {
-  if (!g || !q || !landmarks || !landmark_idx || !resident || !offsets || !cnts || !workspace) {
-    set_error("select_chunks: null pointer"); return SKV_ERR_ARGUMENT;
-  }
+static int check_select_geom(const skv_geom *g, const char *who) {
   if (g->head_dim != kHeadDim || g->q_groups < 1 || g->q_groups > 16 || !valid_map_size(g->select) ||
       g->n_landmarks < g->select || g->n_landmarks > 100000) {
-    set_error("select_chunks: unsupported geometry (D=%d G=%d S=%d N=%d)", g->head_dim, g->q_groups, g->select,
+    set_error("%s: unsupported geometry (D=%d G=%d S=%d N=%d)", who, g->head_dim, g->q_groups, g->select,
               g->n_landmarks);
     return SKV_ERR_UNSUPPORTED;
   }
+  return SKV_OK;
+}
+
+int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, void *workspace,
+                        skv_stream_t stream) {
+  if (!g || !q || !landmarks || !workspace) { set_error("score_landmarks: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (int rc = check_select_geom(g, "score_landmarks")) return rc;
+  SelectWorkspace w = carve(g, workspace);
+  // scale = 1/sqrt(128), the constant the reference hard-codes (kv_cache.py:1017)
+  return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
+                           g->n_landmarks, w.T, 0.08838834764831845f, as_stream(stream));
+}
+
+int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64_t *resident, int32_t *offsets,
+                           int32_t *cnts, int64_t *selected_out, skv_bf16 *score_out, void *workspace,
+                           skv_stream_t stream) {
+  if (!g || !landmark_idx || !resident || !offsets || !cnts || !workspace) {
+    set_error("select_from_scores: null pointer"); return SKV_ERR_ARGUMENT;
+  }
+  if (int rc = check_select_geom(g, "select_from_scores")) return rc;
   cudaStream_t st = as_stream(stream);
   const int BH = g->batch * g->kv_heads, G = g->q_groups, N = g->n_landmarks;
   SelectWorkspace w = carve(g, workspace);
-  int rc = launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, BH, G, N, w.T, 0.08838834764831845f, st);
-  if (rc) return rc;
   const int smem = int(align_up(int64_t(N) * 2, 16));
 #define SKV_SEL(SV)                                                                                              \
   case SV: {                                                                                                     \
@@ -409,6 +422,13 @@ int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *land
   }
 #undef SKV_SEL
   return launch_status("select_kernel");
+}
+
+int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, const int64_t *landmark_idx,
+                      int64_t *resident, int32_t *offsets, int32_t *cnts, int64_t *selected_out,
+                      skv_bf16 *score_out, void *workspace, skv_stream_t stream) {
+  if (int rc = skv_score_landmarks(g, q, landmarks, workspace, stream)) return rc;
+  return skv_select_from_scores(g, landmark_idx, resident, offsets, cnts, selected_out, score_out, workspace, stream);
 }
 
 int skv_batch_gemm_softmax(const skv_bf16 *A, const skv_bf16 *B, skv_bf16 *D, float *Norm, float *Sum,

@@ -96,6 +96,10 @@ class ShadowKVCache_CPU:
         self._attn_ws = None
         self.rebuild_impl = 0      # 0: tcgen05 (product); 1: SIMT cross-check (tests only)
         self.rope_glm = False
+        # device-side copies of the generation counters, so a captured CUDA graph of the step can be replayed
+        # while the cache grows (decode_layer(..., device_counters=True) + advance_device_counters())
+        self.gen_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.kv_len_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------------------------------
     def print_stats(self):
@@ -262,21 +266,39 @@ class ShadowKVCache_CPU:
     # ------------------------------------------------------------------------------------------
     # decode step
     # ------------------------------------------------------------------------------------------
-    def update_kv_cache(self, new_k_cache, new_v_cache, layer_idx):
+    def update_kv_cache(self, new_k_cache, new_v_cache, layer_idx, device_counters=False):
         """Append the new token's post-RoPE K and V rows (kv_cache.py:1227-1271)."""
         incoming = new_k_cache.shape[-2]
         if incoming != 1:
             raise ValueError("decode appends one token per step")
         g = self._geometry()
-        pos = self.sparse_end + self.gen_offset
+        pos = self.sparse_end + (0 if device_counters else self.gen_offset)
         if pos >= self.buf_len:
             raise RuntimeError(f"generation buffer full ({self.buf_len - self.sparse_end} tokens)")
         check(lib.skv_append_kv(C.byref(g), new_k_cache.contiguous().data_ptr(), new_v_cache.contiguous().data_ptr(),
                                 self.k_cache_buffer[layer_idx].data_ptr(), self.v_cache_buffer[layer_idx].data_ptr(),
-                                pos, _cs()), "append_kv")
-        if layer_idx == self.num_layers - 1:
+                                pos, self.gen_dev.data_ptr() if device_counters else 0, _cs()), "append_kv")
+        if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += incoming
             self.gen_offset += incoming
+
+    # --- device-side counters (CUDA-graph replay) ---------------------------------------------------------
+    def reset_device_counters(self):
+        """Copy the host-side generation offset into the device counters (call before capture / replay)."""
+        self.gen_dev.fill_(self.gen_offset)
+        self.kv_len_dev.fill_(self.sparse_end + self.gen_offset + 1)
+
+    def advance_device_counters(self):
+        """gen += 1 on the device; part of the captured step."""
+        self.gen_dev.add_(1)
+        self.kv_len_dev.add_(1)
+
+    def note_replayed_steps(self, n: int):
+        """Host-side bookkeeping after `n` graph replays (kv_cache.py:1269-1271 done in bulk)."""
+        self.gen_offset += n
+        self.kv_offset += n
+        if self.sparse_end + self.gen_offset > self.buf_len:
+            raise RuntimeError("generation buffer overrun during graph replay")
 
     def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None):
         """Score landmarks, pick the top chunks and update the chunk table (kv_cache.py:983-1057).
@@ -323,10 +345,13 @@ class ShadowKVCache_CPU:
                                    self.cnts.data_ptr(), kb.data_ptr(), self.rebuild_impl, st), "rebuild_keys")
         return kb[:, :, :self._view_len(layer_idx)]
 
-    def attention(self, layer_idx, query_states, kv_len=None, out=None):
+    def attention(self, layer_idx, query_states, kv_len=None, out=None, device_counters=False):
         """softmax(q K^T / sqrt(D)) V over rows [0, kv_len) of this layer's buffers (base.py:341)."""
         g = self._geometry()
-        kv_len = self._view_len(layer_idx) if kv_len is None else kv_len
+        if device_counters:
+            kv_len = self.buf_len                    # sizes the grid; the kernel reads the real length
+        elif kv_len is None:
+            kv_len = self._view_len(layer_idx)
         q = query_states.contiguous()
         B, Hq = q.shape[0], q.shape[1]
         if out is None:
@@ -335,14 +360,19 @@ class ShadowKVCache_CPU:
         check(lib.skv_attention_decode(q.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), B,
                                        g.kv_heads, g.q_groups, g.head_dim, kv_len, kb.stride(0), kb.stride(1),
                                        kb.stride(2), 1.0 / math.sqrt(self.head_dim), 0, self._attn_ws.data_ptr(),
-                                       _cs()), "attention_decode")
+                                       self.kv_len_dev.data_ptr() if device_counters else 0, _cs()),
+              "attention_decode")
         return out
 
-    def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None):
+    def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
+                     device_counters=False):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
-        query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D]."""
-        self.update_kv_cache(key_states, value_states, layer_idx)
+        query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
+        With device_counters=True nothing depends on host-side counters, so the call sequence can be
+        captured in a CUDA graph and replayed (see reset/advance_device_counters)."""
+        self.incoming_q_len = 1
+        self.update_kv_cache(key_states, value_states, layer_idx, device_counters)
         pid = self.get_retrieval_position_ids(layer_idx, query_states)
         cur = torch.cuda.current_stream()
         self.copy_stream.wait_stream(cur)
@@ -351,7 +381,7 @@ class ShadowKVCache_CPU:
         self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
         cur.wait_stream(self.copy_stream)
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
-        return self.attention(layer_idx, query_states, kv_len, out)
+        return self.attention(layer_idx, query_states, kv_len, out, device_counters)
 
 
 class ShadowKVCache(ShadowKVCache_CPU):

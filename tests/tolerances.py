@@ -43,3 +43,34 @@ def assert_ulp_bf16(got, want, *, ulps=1, frac_exact=0.98, abs_floor=3e-5, what=
     exact = float((d == 0).float().mean())
     assert exact >= frac_exact, f"{what}: only {exact:.4f} of elements bit-identical"
     return exact
+
+
+def assert_rope_rows_close(got, want, *, glm=False, ulps_in=1, frac_exact=0.90, what=""):
+    """Post-RoPE key rows [..., 128] against the oracle when the PRE-RoPE value may differ by `ulps_in` bf16
+    ulp (different fp32 summation order in the rank-R contraction).  RoPE mixes the pair (x1, x2) into
+    o1 = x1 c - x2 s, o2 = x2 c + x1 s, so a 1-ulp input difference (<= 2^-7 |x| relative) moves either
+    output by at most 2^-7 (|x1||c| + |x2||s|) <= 2^-7 sqrt(x1^2 + x2^2) = 2^-7 * pair norm (c^2 + s^2 = 1),
+    however small the output itself is after cancellation; the bf16 roundings of the product and of the
+    result add at most another 1.5 * 2^-8 of the pair norm.  Tolerance per element:
+        (ulps_in + 1) * 2^-7 * pair_norm(want) + 1e-6,
+    and at least `frac_exact` of all elements must be bit-identical.  Neox pairs are (d, d+64); GLM pairs are
+    (2j, 2j+1) for d < 64 and dims 64..127 are plain copies (tolerance `ulps_in` ulp of the value)."""
+    g = got.float().cpu()
+    w = want.float().cpu()
+    if glm:
+        rot = w[..., :64].reshape(*w.shape[:-1], 32, 2)
+        norm = rot.pow(2).sum(-1, keepdim=True).sqrt().expand_as(rot).reshape(*w.shape[:-1], 64)
+        norm = torch.cat([norm, w[..., 64:].abs()], dim=-1)
+    else:
+        n = (w[..., :64].pow(2) + w[..., 64:].pow(2)).sqrt()
+        norm = torch.cat([n, n], dim=-1)
+    tol = (ulps_in + 1) * 2.0 ** -7 * norm + 1e-6
+    bad = (g - w).abs() > tol
+    if bool(bad.any()):
+        i = bad.flatten().nonzero()[0].item()
+        raise AssertionError(f"{what}: {int(bad.sum())} of {bad.numel()} elements outside the RoPE pair-norm tolerance "
+                             f"(first: got {g.flatten()[i].item()!r} want {w.flatten()[i].item()!r} "
+                             f"tol {tol.flatten()[i].item():.3g})")
+    exact = float((got.cpu().view(torch.int16) == want.cpu().view(torch.int16)).float().mean())
+    assert exact >= frac_exact, f"{what}: only {exact:.4f} of elements bit-identical"
+    return exact
