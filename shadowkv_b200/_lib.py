@@ -39,7 +39,7 @@ _SIGS = {
     "skv_apply_rotary_pos_emb_push_cache": [_p] * 5 + [_i] * 19 + [_p],
     "skv_apply_rotary_pos_emb_push_cache_opt": [_p] * 5 + [_i] * 19 + [_p],
     "skv_apply_rotary_pos_emb_push_cache_opt_glm": [_p] * 5 + [_i] * 19 + [_p],
-    "skv_batch_gather_gemm": [_p] * 6 + [_i] * 9 + [_p, _p],
+    "skv_batch_gather_gemm": [_p] * 6 + [_i] * 8 + [_p, _p],
     "skv_batch_gemm_softmax": [_p] * 6 + [_i] * 4 + [_f, _f, _p],
     "skv_select_chunks": [C.POINTER(Geom)] + [_p] * 10,
     "skv_score_landmarks": [C.POINTER(Geom)] + [_p] * 4,

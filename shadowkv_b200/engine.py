@@ -1,0 +1,137 @@
+"""Whole-token runner of the sparse-KV decode step: all layers of one decode token captured once in a CUDA
+graph and replayed per token (the loop of reference models/base.py:147-148 + 315-341, minus the dense
+QKV / MLP work that sits between the layers and is outside this path).
+
+Two public entry points:
+
+* ``step_device(q, k, v)``  -- inputs already on the GPU ([layers,B,Hq,1,D] / [layers,B,H,1,D] bf16);
+  returns the device tensor of attention outputs [layers,B,1,Hq,D].
+* ``step_host(q, k, v)``    -- inputs are HOST tensors; they are staged through pinned memory, copied to
+  the device INSIDE the replayed graph, and the attention outputs are copied back to pinned host memory
+  inside the same graph.  This is the call ``bench.py`` times as ``e2e``.
+
+The graph holds, per layer: append -> score -> select -> {V hit compaction + miss fetch on the copy stream
+|| K hit compaction + tcgen05 rebuild} -> split-K attention, i.e. 7 kernels, plus one counter-advance kernel
+per token.  The generation offset lives on the device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the
+same graph is valid for every token.
+"""
+from __future__ import annotations
+
+import torch
+
+from .kv_cache import ShadowKVCache_CPU
+
+KERNELS_PER_LAYER = 8     # append, score, select, compact(V), fetch(V), compact(K), rebuild(K), attention
+
+
+class DecodeStepGraph:
+    def __init__(self, cache: ShadowKVCache_CPU, cos_sin_cache: torch.Tensor, *, host_io: bool = True):
+        self.cache = cache
+        self.cos_sin = cos_sin_cache
+        self.host_io = host_io
+        L, B = cache.num_layers, cache.batch_size
+        Hq, H, D = cache.num_attention_heads, cache.num_key_value_heads, cache.head_dim
+        dev, dt = cache.device, cache.dtype
+        self.q_d = torch.zeros(L, B, Hq, 1, D, dtype=dt, device=dev)
+        self.k_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
+        self.v_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
+        self.out_d = torch.zeros(L, B, 1, Hq, D, dtype=dt, device=dev)
+        self.hits_d = torch.zeros(L, B * H, dtype=torch.int32, device=dev)   # cnts per layer of the last token
+        if host_io:
+            self.q_h = torch.zeros(L, B, Hq, 1, D, dtype=dt).pin_memory()
+            self.k_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
+            self.v_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
+            self.out_h = torch.zeros(L, B, 1, Hq, D, dtype=dt).pin_memory()
+        self.h2d_bytes = (self.q_d.numel() + self.k_d.numel() + self.v_d.numel()) * 2
+        self.d2h_bytes = self.out_d.numel() * 2
+        self.launches_per_step = L * KERNELS_PER_LAYER       # kernels of libshadowkv_b200.so per token
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=dev)
+        self.replays = 0
+        self._presets = {}
+
+    # ----------------------------------------------------------------------------------------------
+    def _body(self):
+        c = self.cache
+        if self.host_io:
+            self.q_d.copy_(self.q_h, non_blocking=True)
+            self.k_d.copy_(self.k_h, non_blocking=True)
+            self.v_d.copy_(self.v_h, non_blocking=True)
+        for l in range(c.num_layers):
+            c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
+                           device_counters=True)
+            self.hits_d[l].copy_(c.cnts)
+        c.advance_device_counters()
+        if self.host_io:
+            self.out_h.copy_(self.out_d, non_blocking=True)
+
+    def capture(self, warmup: int = 1):
+        """Warm up eagerly (allocates scratch, builds tensor maps, sets kernel attributes), then capture.
+        The warm-up tokens are real decode steps: they advance the cache like any other token."""
+        c = self.cache
+        c.reset_device_counters()
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self._body()
+                c.note_replayed_steps(1)
+        self.stream.synchronize()
+        self.rewind_async(c.gen_offset)          # builds the preset for "here" before capture; no-op otherwise
+        self._presets.setdefault(0, torch.tensor([0, c.sparse_end + 1], dtype=torch.int32, device=c.device))
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._body()
+        # capture does not execute: the cache state is unchanged by it
+        return self
+
+    # ----------------------------------------------------------------------------------------------
+    def replay(self):
+        """Enqueue one token on the runner's stream (no host synchronisation)."""
+        c = self.cache
+        if c.sparse_end + c.gen_offset + 1 > c.buf_len:
+            raise RuntimeError(f"generation buffer full ({c.buf_len - c.sparse_end} tokens)")
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        c.note_replayed_steps(1)
+        self.replays += 1
+
+    def step_device(self, q, k, v):
+        with torch.cuda.stream(self.stream):
+            self.q_d.copy_(q, non_blocking=True)
+            self.k_d.copy_(k, non_blocking=True)
+            self.v_d.copy_(v, non_blocking=True)
+        self.replay()
+        return self.out_d
+
+    def step_host(self, q, k, v):
+        """Host tensors in, pinned host tensor out; synchronises on the result (a user needs it to sample)."""
+        if not self.host_io:
+            raise RuntimeError("runner was built with host_io=False")
+        self.q_h.copy_(q)
+        self.k_h.copy_(k)
+        self.v_h.copy_(v)
+        self.replay()
+        self.stream.synchronize()
+        return self.out_h
+
+    def rewind_async(self, gen_offset: int = 0):
+        """Stream-ordered rewind (no host synchronisation): the counters are reset by a device-to-device copy
+        enqueued behind the tokens already in flight."""
+        c = self.cache
+        key = int(gen_offset)
+        if key not in self._presets:
+            self._presets[key] = torch.tensor([key, c.sparse_end + key + 1], dtype=torch.int32, device=c.device)
+        c.kv_offset -= c.gen_offset - gen_offset
+        c.gen_offset = gen_offset
+        with torch.cuda.stream(self.stream):
+            c._counters_dev.copy_(self._presets[key], non_blocking=True)
+
+    def rewind(self, gen_offset: int = 0):
+        """Reset the generation region (bench loops longer than the buffer's capacity): the sparse region,
+        chunk table and landmarks are left as they are; only the append position goes back."""
+        c = self.cache
+        self.stream.synchronize()
+        c.kv_offset -= c.gen_offset - gen_offset
+        c.gen_offset = gen_offset
+        c.reset_device_counters()
+        torch.cuda.synchronize(c.device)

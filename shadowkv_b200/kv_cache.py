@@ -58,7 +58,7 @@ class ShadowKVCache_CPU:
         self.chunk_size = chunk_size
         self.rank = rank
         self.local_chunk = 4                                             # kv_cache.py:547
-        self.outlier_chunk = int((self.sparse_budget // 1024) * 24)      # kv_cache.py:548
+        self.outlier_chunk = self._outlier_chunks()                      # kv_cache.py:548 (:206 for ShadowKVCache)
         self.select_sets = self.sparse_budget // self.chunk_size
         assert self.select_sets * self.chunk_size == self.sparse_budget, \
             f"({self.select_sets}) * {self.chunk_size} != {self.sparse_budget}"
@@ -69,9 +69,8 @@ class ShadowKVCache_CPU:
 
         L, B, H, D = self.num_layers, batch_size, self.num_key_value_heads, self.head_dim
         # pinned-host chunk-major V store                      kv_cache.py:554-563
-        self.v_cache_cpu = torch.zeros(L, B, H, max_length // chunk_size, D * chunk_size, dtype=dtype,
-                                       device="cpu", pin_memory=True)
-        self.buf_len = self.sparse_budget + 128 + (self.outlier_chunk + self.local_chunk) * chunk_size   # :574
+        self.v_cache_cpu = self._alloc_v_store(L, B, H, max_length // chunk_size, D * chunk_size)
+        self.buf_len = self._buffer_len()
         self.k_cache_buffer = torch.zeros(L, B, H, self.buf_len, D, dtype=dtype, device=self.device)
         self.v_cache_buffer = torch.zeros(L, B, H, self.buf_len, D, dtype=dtype, device=self.device)
 
@@ -98,8 +97,19 @@ class ShadowKVCache_CPU:
         self.rope_glm = False
         # device-side copies of the generation counters, so a captured CUDA graph of the step can be replayed
         # while the cache grows (decode_layer(..., device_counters=True) + advance_device_counters())
-        self.gen_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.kv_len_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._counters_dev = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.gen_dev = self._counters_dev[0:1]
+        self.kv_len_dev = self._counters_dev[1:2]
+
+    # --- sizing hooks (the batch-1 GPU-resident variant overrides them) ---------------------------
+    def _outlier_chunks(self) -> int:
+        return int((self.sparse_budget // 1024) * 24)
+
+    def _buffer_len(self) -> int:
+        return self.sparse_budget + 128 + (self.outlier_chunk + self.local_chunk) * self.chunk_size   # kv_cache.py:574
+
+    def _alloc_v_store(self, *shape):
+        return torch.zeros(*shape, dtype=self.dtype, device="cpu", pin_memory=True)
 
     # ------------------------------------------------------------------------------------------
     def print_stats(self):
@@ -275,7 +285,8 @@ class ShadowKVCache_CPU:
         pos = self.sparse_end + (0 if device_counters else self.gen_offset)
         if pos >= self.buf_len:
             raise RuntimeError(f"generation buffer full ({self.buf_len - self.sparse_end} tokens)")
-        check(lib.skv_append_kv(C.byref(g), new_k_cache.contiguous().data_ptr(), new_v_cache.contiguous().data_ptr(),
+        kc, vc = new_k_cache.contiguous(), new_v_cache.contiguous()     # named: temporaries must outlive the launch
+        check(lib.skv_append_kv(C.byref(g), kc.data_ptr(), vc.data_ptr(),
                                 self.k_cache_buffer[layer_idx].data_ptr(), self.v_cache_buffer[layer_idx].data_ptr(),
                                 pos, self.gen_dev.data_ptr() if device_counters else 0, _cs()), "append_kv")
         if layer_idx == self.num_layers - 1 and not device_counters:
@@ -285,13 +296,12 @@ class ShadowKVCache_CPU:
     # --- device-side counters (CUDA-graph replay) ---------------------------------------------------------
     def reset_device_counters(self):
         """Copy the host-side generation offset into the device counters (call before capture / replay)."""
-        self.gen_dev.fill_(self.gen_offset)
-        self.kv_len_dev.fill_(self.sparse_end + self.gen_offset + 1)
+        self._counters_dev.copy_(torch.tensor([self.gen_offset, self.sparse_end + self.gen_offset + 1],
+                                              dtype=torch.int32), non_blocking=False)
 
     def advance_device_counters(self):
         """gen += 1 on the device; part of the captured step."""
-        self.gen_dev.add_(1)
-        self.kv_len_dev.add_(1)
+        self._counters_dev.add_(1)
 
     def note_replayed_steps(self, n: int):
         """Host-side bookkeeping after `n` graph replays (kv_cache.py:1269-1271 done in bulk)."""
@@ -393,8 +403,15 @@ class ShadowKVCache(ShadowKVCache_CPU):
                  sparse_budget=2048, chunk_size=8, rank=160) -> None:
         assert batch_size == 1, "ShadowKV class only supports batch_size=1, please use ShadowKV_CPU class for batch_size > 1"
         super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank)
-        self.outlier_chunk = 48                                            # kv_cache.py:206
-        self.v_cache_cpu = self.v_cache_cpu.to(self.device)                # GPU-resident full V (kv_cache.py:222-230)
+
+    def _outlier_chunks(self) -> int:
+        return 48                                                          # kv_cache.py:206
+
+    def _buffer_len(self) -> int:
+        return self.sparse_budget + 4096                                   # kv_cache.py:233-251
+
+    def _alloc_v_store(self, *shape):
+        return torch.zeros(*shape, dtype=self.dtype, device=self.device)   # GPU-resident full V (kv_cache.py:222-230)
 
     def print_stats(self):
         print(f"ShadowKV | sparse budget {self.sparse_budget} | chunk size {self.chunk_size} |rank {self.rank} "

@@ -48,10 +48,11 @@ def cos_sin_table(rows: int, head_dim: int = 128, theta: float = 500000.0, glm: 
     return torch.cat([ang.cos(), ang.sin()], dim=-1).to(BF16).contiguous()
 
 
-def layout(prompt_len: int, sparse_budget: int = 2048, chunk: int = 8):
-    """Region boundaries as the reference computes them (models/kv_cache.py:547-548, 819-894)."""
+def layout(prompt_len: int, sparse_budget: int = 2048, chunk: int = 8, uncached: bool = False):
+    """Region boundaries as the reference computes them (models/kv_cache.py:547-548, 819-894).
+    uncached=True: the batch-1 GPU-resident class (48 outlier chunks, buffer budget+4096; kv_cache.py:206,233)."""
     local_chunk = 4
-    outlier_chunk = (sparse_budget // 1024) * 24
+    outlier_chunk = 48 if uncached else (sparse_budget // 1024) * 24
     chunks = prompt_len // chunk - local_chunk
     chunks -= chunks % 8
     prefill_local = prompt_len - chunks * chunk
@@ -59,7 +60,8 @@ def layout(prompt_len: int, sparse_budget: int = 2048, chunk: int = 8):
     return SimpleNamespace(chunks=chunks, n_landmarks=chunks - outlier_chunk, prefill_local=prefill_local,
                            outlier_chunk=outlier_chunk, sparse_start=sparse_start,
                            sparse_end=sparse_start + sparse_budget,
-                           buf_len=sparse_budget + 128 + (outlier_chunk + local_chunk) * chunk,
+                           buf_len=sparse_budget + 4096 if uncached else
+                           sparse_budget + 128 + (outlier_chunk + local_chunk) * chunk,
                            select=sparse_budget // chunk, all_chunks=prompt_len // chunk)
 
 
@@ -78,13 +80,13 @@ def _rope_float(x, cs):
 
 
 def layer_state(shape: ModelShape, batch: int, prompt_len: int, *, seed: int, rank: int = 160,
-                sparse_budget: int = 2048, chunk: int = 8, device="cpu", cos_sin=None):
+                sparse_budget: int = 2048, chunk: int = 8, device="cpu", cos_sin=None, uncached: bool = False):
     """One layer of decode state.  Returns a dict of tensors:
     U [B,L,R], SV [B,H,D,R], k_landmark [B,H,N,D], k_landmark_idx [B,H,N] (ascending, `outlier_chunk` random
     chunks removed), v_chunks [B,H,L/C,C*D], k_buf / v_buf [B,H,Lbuf,D] (local + outlier rows random, sparse
     region filled consistently with `resident`: V rows are the store's chunks; K rows are RoPE(U.SV) of
     the resident chunks when `cos_sin` is given, else random), resident [B,H,S] distinct chunk ids."""
-    lay = layout(prompt_len, sparse_budget, chunk)
+    lay = layout(prompt_len, sparse_budget, chunk, uncached)
     H, D = shape.num_key_value_heads, shape.hidden_size // shape.num_attention_heads
     g = torch.Generator(device=device).manual_seed(seed)
 
@@ -137,8 +139,9 @@ def queries(shape: ModelShape, batch: int, *, seed: int, device="cpu", base=None
     return q.to(BF16), k.to(BF16), v.to(BF16)
 
 
-def install(cache, layer_states, cos_sin=None):
-    """Load per-layer synthetic states into a ShadowKVCache_CPU (stacking along the layer dim)."""
+def install(cache, layer_states, cos_sin=None, skip_v_store: bool = False):
+    """Load per-layer synthetic states into a ShadowKVCache_CPU (stacking along the layer dim).
+    skip_v_store: the caller already copied every layer's `v_chunks` into cache.v_cache_cpu."""
     dev = cache.device
     L = len(layer_states)
     lay = layer_states[0]["layout"]
@@ -148,8 +151,9 @@ def install(cache, layer_states, cos_sin=None):
         return torch.stack([s[name].to(dev) for s in layer_states])
 
     for l, s in enumerate(layer_states):
-        nchunks = s["v_chunks"].shape[2]
-        cache.v_cache_cpu[l][:, :, :nchunks].copy_(s["v_chunks"])
+        if not skip_v_store:
+            nchunks = s["v_chunks"].shape[2]
+            cache.v_cache_cpu[l][:, :, :nchunks].copy_(s["v_chunks"])
         cache.k_cache_buffer[l].copy_(s["k_buf"])
         cache.v_cache_buffer[l].copy_(s["v_buf"])
     cache.load_state(prompt_len=prompt_len, U=stack("U"), SV=stack("SV"), k_landmark=stack("k_landmark"),

@@ -114,7 +114,7 @@ def test_uncached_variant_token_ids(cuda):
     shape = synth.MODELS["llama-3.1-8b"]
     prompt_len, budget = 8192, 1024
     cs = synth.cos_sin_table(prompt_len + 1024)
-    st = synth.layer_state(shape, 1, prompt_len, seed=3, sparse_budget=budget, cos_sin=cs)
+    st = synth.layer_state(shape, 1, prompt_len, seed=3, sparse_budget=budget, cos_sin=cs, uncached=True)
     cache = ShadowKVCache(shape.config(1), batch_size=1, max_length=prompt_len, device=str(cuda), sparse_budget=budget)
     synth.install(cache, [st])
     q, kn, vn = synth.queries(shape, 1, seed=1)

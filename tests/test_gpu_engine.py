@@ -1,0 +1,91 @@
+"""DecodeStepGraph (all layers of a token in one CUDA graph, device-side generation counters) against the
+eager method-by-method path on identical state: same chunk table, same K/V buffer bytes, same attention
+output (the split-K boundaries differ, so the output is compared within the bf16 tolerance)."""
+import pytest
+import torch
+
+from shadowkv_b200 import synth
+from tests.tolerances import assert_close_bf16
+
+pytestmark = pytest.mark.gpu
+
+
+def _cache(cuda, shape, B, prompt_len, budget, layers, cs):
+    from shadowkv_b200.kv_cache import ShadowKVCache_CPU
+    states = [synth.layer_state(shape, B, prompt_len, seed=1000 + l, sparse_budget=budget, cos_sin=cs)
+              for l in range(layers)]
+    cache = ShadowKVCache_CPU(shape.config(layers), batch_size=B, max_length=prompt_len, device=str(cuda),
+                              sparse_budget=budget)
+    return synth.install(cache, states)
+
+
+@pytest.mark.parametrize("host_io", [False, True])
+def test_graph_replay_equals_eager(cuda, host_io):
+    from shadowkv_b200.engine import DecodeStepGraph
+    shape = synth.MODELS["llama-3.1-8b"]
+    B, prompt_len, budget, layers, tokens = 2, 8192, 1024, 3, 5
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    d_cs = cs.to(cuda)
+    c1 = _cache(cuda, shape, B, prompt_len, budget, layers, cs)
+    c2 = _cache(cuda, shape, B, prompt_len, budget, layers, cs)
+    Hq, H, D = shape.num_attention_heads, shape.num_key_value_heads, 128
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(layers, B, Hq, 1, D, generator=g)
+
+    def tok_inputs():
+        q = (0.95 * base + 0.3 * torch.randn(layers, B, Hq, 1, D, generator=g)).to(torch.bfloat16)
+        k = torch.randn(layers, B, H, 1, D, generator=g).to(torch.bfloat16)
+        v = torch.randn(layers, B, H, 1, D, generator=g).to(torch.bfloat16)
+        return q, k, v
+
+    ins = [tok_inputs() for _ in range(tokens)]
+    run = DecodeStepGraph(c2, d_cs, host_io=host_io)
+    # the capture warm-up consumes token 0 (a real decode step)
+    if host_io:
+        run.q_h.copy_(ins[0][0]); run.k_h.copy_(ins[0][1]); run.v_h.copy_(ins[0][2])
+    else:
+        run.q_d.copy_(ins[0][0]); run.k_d.copy_(ins[0][1]); run.v_d.copy_(ins[0][2])
+    run.capture(warmup=1)
+    assert c2.gen_offset == 1
+    for t in range(tokens):
+        q, k, v = ins[t]
+        outs = [c1.decode_layer(l, q[l].to(cuda), k[l].to(cuda), v[l].to(cuda), d_cs) for l in range(layers)]
+        torch.cuda.synchronize()
+        if t > 0:
+            if host_io:
+                got = run.step_host(q, k, v).to(cuda)
+            else:
+                got = run.step_device(q.to(cuda), k.to(cuda), v.to(cuda))
+        else:
+            got = run.out_d
+        torch.cuda.synchronize()
+        assert c1.gen_offset == c2.gen_offset == t + 1
+        assert torch.equal(c1.position_ids, c2.position_ids), f"chunk table differs at token {t}"
+        assert torch.equal(c1.k_cache_buffer, c2.k_cache_buffer), f"K buffers differ at token {t}"
+        assert torch.equal(c1.v_cache_buffer, c2.v_cache_buffer), f"V buffers differ at token {t}"
+        for l in range(layers):
+            assert_close_bf16(got[l], outs[l], max_abs=4e-3, what=f"token {t} layer {l}")
+    assert int(run.hits_d.sum()) > 0
+
+
+def test_rewind_reuses_generation_region(cuda):
+    from shadowkv_b200.engine import DecodeStepGraph
+    shape = synth.MODELS["llama-3.1-8b"]
+    B, prompt_len, budget, layers = 1, 8192, 1024, 1
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    c = _cache(cuda, shape, B, prompt_len, budget, layers, cs)
+    run = DecodeStepGraph(c, cs.to(cuda), host_io=False).capture(warmup=1)
+    cap = c.buf_len - c.sparse_end
+    q = torch.randn(layers, B, 32, 1, 128, device=cuda).to(torch.bfloat16)
+    k = torch.randn(layers, B, 8, 1, 128, device=cuda).to(torch.bfloat16)
+    for _ in range(cap - 1):
+        run.step_device(q, k, k)
+    assert c.gen_offset == cap
+    with pytest.raises(RuntimeError):
+        run.replay()
+    run.rewind_async(0)
+    k2 = torch.full_like(k, 3.0)
+    run.step_device(q, k2, k2)
+    torch.cuda.synchronize()
+    assert c.gen_offset == 1
+    assert torch.equal(c.k_cache_buffer[0][:, :, c.sparse_end], k2[0][:, :, 0])

@@ -99,5 +99,7 @@ def test_batch_gather_gemm_wrapper(cuda):
     for r in range(B * H):
         b, h = divmod(r, H)
         first = (int(cnts[r]) * 8 // 128) * 128
-        assert_ulp_bf16(out[b, h, first:].cpu(), kpre[b, h, first:], ulps=1, frac_exact=0.95, what="pre-RoPE K")
-        assert float(out[b, h, :first].float().abs().max()) == 0.0 if first else True
+        if first < S * 8:
+            assert_ulp_bf16(out[b, h, first:].cpu(), kpre[b, h, first:], ulps=1, frac_exact=0.95, what="pre-RoPE K")
+        if first:
+            assert float(out[b, h, :first].float().abs().max()) == 0.0

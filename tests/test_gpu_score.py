@@ -56,8 +56,9 @@ def _select(cuda, shape, N, S, seed, glm=False):
     cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
     sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
     score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
-    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.to(cuda).data_ptr(), lm.to(cuda).data_ptr(),
-                                          idx.to(cuda).data_ptr(), d_res.data_ptr(), off.data_ptr(), cnt.data_ptr(),
+    d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)     # named: a temporary would be freed before the launch
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(),
+                                          d_idx.data_ptr(), d_res.data_ptr(), off.data_ptr(), cnt.data_ptr(),
                                           sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
                                           torch.cuda.current_stream().cuda_stream), "select")
     torch.cuda.synchronize()
@@ -110,8 +111,9 @@ def test_select_massive_ties(cuda):
     res = torch.full((B, H, S), -1, dtype=torch.int64, device=cuda)
     off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
     cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
-    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.to(cuda).data_ptr(), lm.to(cuda).data_ptr(),
-                                          idx.to(cuda).data_ptr(), res.data_ptr(), off.data_ptr(), cnt.data_ptr(), 0, 0,
+    d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(),
+                                          d_idx.data_ptr(), res.data_ptr(), off.data_ptr(), cnt.data_ptr(), 0, 0,
                                           ws.data_ptr(), torch.cuda.current_stream().cuda_stream), "select")
     torch.cuda.synchronize()
     assert (cnt.cpu() == 0).all()
