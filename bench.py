@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--rank", type=int, default=160)
     ap.add_argument("--noise", type=float, default=0.28,
                     help="per-token query innovation; 0.28 gives ~60%% chunk-cache hits (reference test default)")
+    ap.add_argument("--table-mode", default="inplace", choices=["inplace", "reference"],
+                    help="chunk-table slot policy: in place (no hit compaction) or the reference's slot order")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -209,7 +211,7 @@ def workload_config(args, shape, L, *, hit_rate, n_gpus):
             "scope": "sparse-KV decode step of every layer; dense QKV/o_proj/MLP not included (SURVEY.md 8 f2)",
             "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "ctx": args.ctx, "layers": L,
             "landmarks": lay.n_landmarks, "select_chunks": lay.select, "kv_rows_attended": lay.sparse_end + 1,
-            "chunk_cache_hit_rate": round(hit_rate, 4), "query_noise": args.noise,
+            "chunk_cache_hit_rate": round(hit_rate, 4), "query_noise": args.noise, "table_mode": args.table_mode,
             "l2_policy": "inputs larger than L2: per token the step streams every layer's landmarks, "
                          f"{L} x {lay.n_landmarks * shape.num_key_value_heads * 256 / 1e6:.1f} MB per sequence",
             "parallelism": f"batch-sharded x{n_gpus}, no collective"}
@@ -241,7 +243,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
     t_setup = time.perf_counter()
     cs = synth.cos_sin_table(args.ctx + 1024, theta=shape.rope_theta, glm=shape.glm_rope, device=dev)
     cache = ShadowKVCache_CPU(shape.config(L), batch_size=B, max_length=args.ctx, device=str(dev),
-                              sparse_budget=args.budget, rank=args.rank)
+                              sparse_budget=args.budget, rank=args.rank, table_mode=args.table_mode)
     states = []
     for l in range(L):
         st = synth.layer_state(shape, B, args.ctx, seed=1000 + l + 7919 * rank, rank=args.rank,
@@ -373,26 +375,35 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     from shadowkv_b200._lib import lib, check
     H, G, D, S, N, R = cache.num_key_value_heads, cache.num_key_value_groups, 128, lay.select, lay.n_landmarks, args.rank
     g = cache._geometry(cs)
-    st = torch.cuda.current_stream()
-    sp = st.cuda_stream
     q = torch.randn(L, B, H * G, 1, D, device=dev).to(torch.bfloat16)
     out = torch.empty(B, 1, H * G, D, dtype=torch.bfloat16, device=dev)
 
+    def cur():
+        return torch.cuda.current_stream().cuda_stream
+
     def timed(fn, reps):
+        """`reps` back-to-back launches captured in one CUDA graph (no host launch gaps), replayed between two
+        CUDA events on the launching stream."""
         for i in range(min(reps, L)):
             fn(i % L)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(reps):
+                fn(i % L)
+        graph.replay()
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        for i in range(reps):
-            fn(i % L)
+        graph.replay()
         e1.record(st)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / reps          # us per launch
 
     def score(l):
         check(lib.skv_score_landmarks(C.byref(g), q[l].data_ptr(), cache.k_landmark[l].data_ptr(),
-                                      cache._sel_ws.data_ptr(), sp), "score")
+                                      cache._sel_ws.data_ptr(), None, cur()), "score")
 
     reps = 4 * L
     t_score = timed(score, reps)
@@ -412,7 +423,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     def select(l):
         check(lib.skv_select_from_scores(C.byref(g), cache.k_landmark_idx[l].data_ptr(),
                                          cache.position_ids[l].data_ptr(), cache.offsets.data_ptr(),
-                                         cache.cnts.data_ptr(), 0, 0, cache._sel_ws.data_ptr(), sp), "select")
+                                         cache.cnts.data_ptr(), 0, 0, cache._sel_ws.data_ptr(), cur()), "select")
 
     score(0)
     t_select = timed(select, 2 * L)
@@ -429,31 +440,39 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     # controlled hit rates for the data-movement kernels: offsets/cnts built directly
     for label, hit in (("h0", 0.0), ("h60", 154 / 256), ("h100", 1.0)):
         cnt = int(round(hit * S))
-        offs = torch.empty(B * H, S, dtype=torch.int32, device=dev)
-        # hits: ascending source slots >= i (every other slot, clipped); misses: ascending chunk ids
-        src = torch.sort(torch.randperm(S, device=dev)[:cnt]).values.to(torch.int32) if cnt else None
+        inplace = cache.table_mode == "inplace"
+        offs = torch.zeros(B * H, S, dtype=torch.int32, device=dev)
+        res = torch.zeros(B * H, S, dtype=torch.int64, device=dev)
         for r in range(B * H):
-            if cnt:
-                offs[r, :cnt] = torch.maximum(src, torch.arange(cnt, device=dev, dtype=torch.int32))
-            if cnt < S:
-                offs[r, cnt:] = torch.sort(torch.randperm(lay.chunks, device=dev)[:S - cnt]).values.to(torch.int32)
+            ids = torch.randperm(lay.chunks, device=dev)[:S]
+            if inplace:      # resident[slot] = chunk id; offsets[i] = slot of the i-th miss (ascending slot and id)
+                slots = torch.sort(torch.randperm(S, device=dev)[:S - cnt]).values
+                ids[slots] = torch.sort(ids[slots]).values
+                res[r] = ids
+                offs[r, :S - cnt] = slots.to(torch.int32)
+            else:            # hits: ascending source slots >= i; misses: ascending chunk ids (offset = id)
+                if cnt:
+                    offs[r, :cnt] = torch.sort(torch.randperm(S, device=dev)[:cnt]).values.to(torch.int32)
+                if cnt < S:
+                    offs[r, cnt:] = torch.sort(ids[cnt:]).values.to(torch.int32)
+                res[r] = offs[r].to(torch.int64)
         cache.offsets.copy_(offs.view(-1))
         cache.cnts.fill_(cnt)
-        res = offs.to(torch.int64).view(B, H, S).clone()
+        res = res.view(B, H, S)
         miss = S - cnt
 
         def fetch(l):
             vh = cache.v_cache_cpu[l]
             check(lib.skv_fetch_misses(C.byref(g), vh.data_ptr(), vh.stride(1), cache.v_cache_buffer[l].data_ptr(),
-                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), sp), "fetch")
+                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), res.data_ptr(), cur()), "fetch")
 
         def compact(l):
             check(lib.skv_compact_hits(C.byref(g), cache.k_cache_buffer[l].data_ptr(), cache.v_cache_buffer[l].data_ptr(),
-                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), sp), "compact")
+                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), cur()), "compact")
 
         def rebuild(l):
             check(lib.skv_rebuild_keys(C.byref(g), cache.U[l].data_ptr(), cache.SV[l].data_ptr(), cs.data_ptr(),
-                                       res.data_ptr(), cache.cnts.data_ptr(), cache.k_cache_buffer[l].data_ptr(), 0, sp),
+                                       res.data_ptr(), cache.cnts.data_ptr(), cache.offsets.data_ptr(), cache.k_cache_buffer[l].data_ptr(), 0, cur()),
                   "rebuild")
 
         row = {}
@@ -470,7 +489,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
             row["rebuild_GBps"] = (rd + wr) / t * 1e-3
             row["rebuild_TFLOPs"] = fl / t * 1e-6
             row["rebuild_frac_tensor"] = fl / t * 1e-6 / peaks["bf16"]
-        if cnt:
+        if cnt and not inplace:
             t = timed(compact, 2 * L)
             row["compact_kv_us"] = t
             row["compact_GBps"] = 2 * 2 * B * H * cnt * 2048 / t * 1e-3
@@ -482,6 +501,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     dbuf = torch.empty(n, dtype=torch.uint8, device=dev)
     dbuf.copy_(hbuf, non_blocking=True)
     torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for _ in range(4):

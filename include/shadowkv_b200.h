@@ -174,8 +174,20 @@ typedef struct skv_geom {
   int32_t sparse_start; /* first row of the sparse region      */
   int32_t rope_glm;     /* 0: neox [cos64|sin64]; 1: GLM [cos32|sin32] */
   int32_t cos_sin_rows; /* rows of the cos_sin table           */
-  int32_t reserved;
+  int32_t table_mode;   /* 0: reference slot order (hits compacted to the front, needs skv_compact_hits);
+                         * 1: in-place table (hits keep their slots; offsets[i] = slot of the i-th miss) */
 } skv_geom;
+
+/* Optional fused append (a2) for the scoring launch: the new token's K and V rows [B,H,D] are written at
+ * buffer row pos (+ *pos_dev when pos_dev != NULL) of every (b,h) by the first CTA of each row, which saves
+ * the separate skv_append_kv launch on the critical path. */
+typedef struct skv_append {
+  const skv_bf16 *k_new, *v_new;
+  skv_bf16 *k_buf, *v_buf;
+  const int32_t *pos_dev;
+  int32_t pos;
+  int32_t reserved;
+} skv_append;
 
 /* Bytes of device scratch skv_select_chunks needs for `geom` (scores + partials). */
 int64_t skv_select_workspace_bytes(const skv_geom *geom);
@@ -186,16 +198,17 @@ int64_t skv_select_workspace_bytes(const skv_geom *geom);
  * skv_reorder_keys_and_compute_offsets.  q [B, H*G, D] bf16 (post-RoPE); landmarks [B,H,N,D];
  * landmark_idx [B,H,N] int64; resident [B,H,S] int64 in/out; offsets [B*H*S], cnts [B*H] out.
  * selected_out (optional, may be NULL) receives the S selected chunk ids per (b,h) in ascending
- * landmark order; score_out (optional) the bf16 max-over-groups softmax [B,H,N]. */
+ * landmark order; score_out (optional) the bf16 max-over-groups softmax [B,H,N]; append (optional) fuses (a2). */
 int skv_select_chunks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *landmarks,
                       const int64_t *landmark_idx, int64_t *resident, int32_t *offsets, int32_t *cnts,
-                      int64_t *selected_out, skv_bf16 *score_out, void *workspace, skv_stream_t stream);
+                      int64_t *selected_out, skv_bf16 *score_out, void *workspace, const skv_append *append,
+                      skv_stream_t stream);
 
 /* The two launches of skv_select_chunks, individually (same arguments, same workspace): the scoring pass
  * alone (HBM-bound stream over the landmarks; this is the kernel bench.py reports the roofline for) and the
  * per-(b,h) selection + chunk-table update that consumes its scores. */
 int skv_score_landmarks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *landmarks, void *workspace,
-                        skv_stream_t stream);
+                        const skv_append *append, skv_stream_t stream);
 int skv_select_from_scores(const skv_geom *geom, const int64_t *landmark_idx, int64_t *resident, int32_t *offsets,
                            int32_t *cnts, int64_t *selected_out, skv_bf16 *score_out, void *workspace,
                            skv_stream_t stream);
@@ -206,17 +219,20 @@ int skv_compact_hits(const skv_geom *geom, skv_bf16 *k_buf, skv_bf16 *v_buf, con
                      const int32_t *cnts, skv_stream_t stream);
 
 /* (a6) miss fetch: for i >= cnts[bh]: V slot i <- v_host[bh, offsets[bh*S+i]] (pinned host memory,
- * read over PCIe by the SMs).  host_stride = elements between consecutive (b,h) blocks of v_host. */
+ * read over PCIe by the SMs).  host_stride = elements between consecutive (b,h) blocks of v_host.
+ * geom->table_mode == 1: for i < S - cnts[bh]: slot = offsets[bh*S+i]; V slot <- v_host[bh, resident[bh*S+slot]]
+ * (resident is required in that mode, ignored otherwise). */
 int skv_fetch_misses(const skv_geom *geom, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
-                     const int32_t *offsets, const int32_t *cnts, skv_stream_t stream);
+                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, skv_stream_t stream);
 
 /* (a7) K rebuild for the missed chunks with RoPE in the epilogue (TMA-fed tcgen05, fp32 accumulate in
  * TMEM, bf16 round, bf16 RoPE at token position id*C+r), written straight into the sparse region of
  * k_buf.  U [B,L,R], SV [B,H,D,R], cos_sin [rows, D] or [rows, D/2] (GLM), resident [B,H,S] int64.
+ * offsets: only read when geom->table_mode == 1 (slot of the i-th miss); may be NULL otherwise.
  * impl: 0 = tcgen05 (product path), 1 = SIMT cross-check used by the tests. */
 int skv_rebuild_keys(const skv_geom *geom, const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin,
-                     const int64_t *resident, const int32_t *cnts, skv_bf16 *k_buf, int impl,
-                     skv_stream_t stream);
+                     const int64_t *resident, const int32_t *cnts, const int32_t *offsets, skv_bf16 *k_buf,
+                     int impl, skv_stream_t stream);
 
 /* (a2) append the new token's K and V rows at buffer row `pos` of every (b,h). k_new/v_new [B,H,D].
  * pos_dev (optional, device int32): when non-NULL the row is pos + *pos_dev, read on the device, so the

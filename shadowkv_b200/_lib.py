@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libshadowkv_b200.so")
+# SKV_LIB selects another build of the same library (the phase-timeline build of `make trace`, for tuning)
+LIB_PATH = os.environ.get("SKV_LIB") or os.path.join(_HERE, "lib", "libshadowkv_b200.so")
 
 
 class SkvError(RuntimeError):
@@ -16,7 +17,13 @@ class Geom(C.Structure):
     """struct skv_geom (include/shadowkv_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "kv_heads", "q_groups", "head_dim", "chunk", "select", "n_landmarks", "rank", "seq_len",
-        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "reserved")]
+        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode")]
+
+
+class Append(C.Structure):
+    """struct skv_append (include/shadowkv_b200.h)."""
+    _fields_ = [("k_new", C.c_void_p), ("v_new", C.c_void_p), ("k_buf", C.c_void_p), ("v_buf", C.c_void_p),
+                ("pos_dev", C.c_void_p), ("pos", C.c_int32), ("reserved", C.c_int32)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -41,12 +48,12 @@ _SIGS = {
     "skv_apply_rotary_pos_emb_push_cache_opt_glm": [_p] * 5 + [_i] * 19 + [_p],
     "skv_batch_gather_gemm": [_p] * 6 + [_i] * 8 + [_p, _p],
     "skv_batch_gemm_softmax": [_p] * 6 + [_i] * 4 + [_f, _f, _p],
-    "skv_select_chunks": [C.POINTER(Geom)] + [_p] * 10,
-    "skv_score_landmarks": [C.POINTER(Geom)] + [_p] * 4,
+    "skv_select_chunks": [C.POINTER(Geom)] + [_p] * 9 + [C.POINTER(Append), _p],
+    "skv_score_landmarks": [C.POINTER(Geom)] + [_p] * 3 + [C.POINTER(Append), _p],
     "skv_select_from_scores": [C.POINTER(Geom)] + [_p] * 8,
     "skv_compact_hits": [C.POINTER(Geom)] + [_p] * 5,
-    "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p],
-    "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 6 + [_i, _p],
+    "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p],
+    "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 7 + [_i, _p],
     "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
 }

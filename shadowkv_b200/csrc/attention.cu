@@ -7,10 +7,14 @@
 
 namespace skv {
 
-constexpr int kAttnThreads = 128;            // 4 warps
+constexpr int kAttnMinWarps = 8;              // 256 threads: the combine maps 128 dims x 2 head pairs onto them
+constexpr int kAttnMaxWarps = 12;             // block size is chosen per launch (see plan_splits)
 constexpr int kAttnGT = 4;                   // query heads per CTA
 constexpr int kAttnGroupKeys = 16;           // keys per warp iteration
 constexpr int kAttnMaxSplits = 64;
+
+// barrier over the first 256 threads only (the extra key-streaming warps have left by then)
+__device__ __forceinline__ void bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct AttnParams {
   const skv_bf16 *q;     // [B, H*G, 128]
@@ -25,18 +29,22 @@ struct AttnParams {
   float scale_log2;      // scale * log2(e)
 };
 
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnMaxWarps * 32, 1)
     attention_decode_kernel(AttnParams p) {
-  __shared__ __align__(16) float s_p[kAttnThreads / 32][kAttnGroupKeys][kAttnGT];
-  __shared__ float s_o[kAttnThreads / 32][kAttnGT][kHeadDim];
-  __shared__ float s_ml[kAttnThreads / 32][kAttnGT][2];
+  __shared__ __align__(16) float s_p[kAttnMaxWarps][kAttnGroupKeys][kAttnGT];
+  __shared__ float s_o[kAttnMaxWarps][kAttnGT][kHeadDim];
+  __shared__ float s_ml[kAttnMaxWarps][kAttnGT][2];
+  __shared__ float s_f[kAttnMaxSplits][kAttnGT];
+  __shared__ float s_L[kAttnGT];
   __shared__ int s_last;
 
   const int split = blockIdx.x;
   const int h = blockIdx.y / p.ngz, gz = blockIdx.y % p.ngz, b = blockIdx.z;
   const int g0 = gz * kAttnGT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 15, hw = lane >> 4;
+  const int nwarps = blockDim.x >> 5;
   const int row_id = (b * p.H + h) * p.ngz + gz;
+  SKV_STAMP(row_id == 0 ? split : 999, 0);
 
   float qf[kAttnGT][8];
 #pragma unroll
@@ -53,6 +61,7 @@ __global__ void __launch_bounds__(kAttnThreads)
   }
 
   const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
+  SKV_STAMP(row_id == 0 ? split : 999, 1);
   const int k_begin = split * p.keys_per_split;
   const int k_end = min(kv_len, k_begin + p.keys_per_split);
   const int4 *kbase = reinterpret_cast<const int4 *>(p.k + size_t(b) * p.sb + size_t(h) * p.sh);
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(kAttnThreads)
   }
 
 #pragma unroll 1
-  for (int kg = k_begin + warp * kAttnGroupKeys; kg < k_end; kg += (kAttnThreads / 32) * kAttnGroupKeys) {
+  for (int kg = k_begin + warp * kAttnGroupKeys; kg < k_end; kg += nwarps * kAttnGroupKeys) {
     int4 kl[8], vl[8];
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -178,7 +187,8 @@ __global__ void __launch_bounds__(kAttnThreads)
     }
   }
 
-  // ---- merge inside the warp (two key parities), then across the 4 warps ---------------------------
+  SKV_STAMP(row_id == 0 ? split : 999, 2);
+  // ---- merge inside the warp (two key parities), then across the warps of the CTA ---------------------
 #pragma unroll
   for (int g = 0; g < kAttnGT; ++g) {
     l_run[g] = warp_sum(l_run[g]);
@@ -196,52 +206,95 @@ __global__ void __launch_bounds__(kAttnThreads)
     for (int g = 0; g < kAttnGT; ++g) { s_ml[warp][g][0] = m_run[g]; s_ml[warp][g][1] = l_run[g]; }
   }
   __syncthreads();
-  const int d = threadIdx.x;                      // 128 threads = 128 dims
+  if (threadIdx.x >= 256) return;                 // warps beyond 8 only stream keys; none of them can be thread 0
+  const int d = threadIdx.x & (kHeadDim - 1);     // 256 threads = 128 dims x 2 head pairs
+  const int gh = threadIdx.x >> 7;
   float *po = p.part_o + (size_t(row_id) * kAttnMaxSplits + split) * kAttnGT * kHeadDim;
   float *pml = p.part_ml + (size_t(row_id) * kAttnMaxSplits + split) * kAttnGT * 2;
 #pragma unroll
-  for (int g = 0; g < kAttnGT; ++g) {
+  for (int gg = 0; gg < kAttnGT / 2; ++gg) {
+    const int g = gh * (kAttnGT / 2) + gg;
     float m = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kAttnThreads / 32; ++w) m = fmaxf(m, s_ml[w][g][0]);
+    for (int w = 0; w < nwarps; ++w) m = fmaxf(m, s_ml[w][g][0]);
     float l = 0.f, o = 0.f;
-#pragma unroll
-    for (int w = 0; w < kAttnThreads / 32; ++w) {
+#pragma unroll 4
+    for (int w = 0; w < nwarps; ++w) {
       const float mw = s_ml[w][g][0];
       const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - m);
       l += s_ml[w][g][1] * f;
       o += s_o[w][g][d] * f;
     }
-    po[g * kHeadDim + d] = o;
-    if (d == 0) { pml[g * 2] = m; pml[g * 2 + 1] = l; }
+    if (p.num_splits == 1) {                       // single split: finish here, no workspace round trip
+      if (g0 + g < p.G)
+        p.out[(size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + d] = f32_to_bf16_bits(o / l);
+    } else {
+      __stcg(po + g * kHeadDim + d, o);
+      if (d == 0) { __stcg(pml + g * 2, m); __stcg(pml + g * 2 + 1, l); }
+    }
   }
+  if (p.num_splits == 1) return;
+  SKV_STAMP(row_id == 0 ? split : 999, 3);
   // ---- last-arriving CTA of this (b, head group) merges the splits ---------------------------------
   __threadfence();
-  __syncthreads();
+  bar256();
   if (threadIdx.x == 0) {
     const int prev = atomicAdd(&p.counters[row_id], 1);
     s_last = (prev == p.num_splits - 1);
     if (s_last) p.counters[row_id] = 0;           // ready for the next launch
   }
-  __syncthreads();
+  bar256();
+  SKV_STAMP(row_id == 0 ? split : 999, 4);
   if (!s_last) return;
   __threadfence();
+  SKV_STAMP(row_id == 0 ? split : 999, 5);
   const float *ro = p.part_o + size_t(row_id) * kAttnMaxSplits * kAttnGT * kHeadDim;
   const float *rml = p.part_ml + size_t(row_id) * kAttnMaxSplits * kAttnGT * 2;
+  // weights of every (split, head): one warp per head, lanes over the splits (<= 64)
+  if (warp < kAttnGT) {
+    const int g = warp;
+    float ms[2], ls[2], m = -INFINITY;
 #pragma unroll
-  for (int g = 0; g < kAttnGT; ++g) {
-    if (g0 + g >= p.G) break;
-    float m = -INFINITY;
-    for (int s = 0; s < p.num_splits; ++s) m = fmaxf(m, __ldcg(rml + (s * kAttnGT + g) * 2));
-    float l = 0.f, o = 0.f;
-    for (int s = 0; s < p.num_splits; ++s) {
-      const float ms = __ldcg(rml + (s * kAttnGT + g) * 2);
-      const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - m);
-      l += __ldcg(rml + (s * kAttnGT + g) * 2 + 1) * f;
-      o += __ldcg(ro + (size_t(s) * kAttnGT + g) * kHeadDim + d) * f;
+    for (int k = 0; k < 2; ++k) {
+      const int sidx = lane + 32 * k;
+      const bool on = sidx < p.num_splits;
+      ms[k] = on ? __ldcg(rml + (sidx * kAttnGT + g) * 2) : -INFINITY;
+      ls[k] = on ? __ldcg(rml + (sidx * kAttnGT + g) * 2 + 1) : 0.f;
+      m = fmaxf(m, ms[k]);
     }
-    p.out[(size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + d] = f32_to_bf16_bits(o / l);
+    m = warp_max(m);
+    float lsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float f = (ms[k] == -INFINITY) ? 0.f : exp2f(ms[k] - m);
+      lsum += ls[k] * f;
+      if (lane + 32 * k < kAttnMaxSplits) s_f[lane + 32 * k][g] = f;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) s_L[g] = lsum;
   }
+  bar256();
+  SKV_STAMP(row_id == 0 ? split : 999, 6);
+#pragma unroll
+  for (int gg = 0; gg < kAttnGT / 2; ++gg) {
+    const int g = gh * (kAttnGT / 2) + gg;
+    if (g0 + g >= p.G) break;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    const float *col = ro + size_t(g) * kHeadDim + d;
+    const int ns = p.num_splits;
+    int sidx = 0;
+    for (; sidx + 4 <= ns; sidx += 4) {            // four independent loads in flight
+      const float v0 = __ldcg(col + size_t(sidx) * kAttnGT * kHeadDim);
+      const float v1 = __ldcg(col + size_t(sidx + 1) * kAttnGT * kHeadDim);
+      const float v2 = __ldcg(col + size_t(sidx + 2) * kAttnGT * kHeadDim);
+      const float v3 = __ldcg(col + size_t(sidx + 3) * kAttnGT * kHeadDim);
+      o0 = fmaf(v0, s_f[sidx][g], o0); o1 = fmaf(v1, s_f[sidx + 1][g], o1);
+      o2 = fmaf(v2, s_f[sidx + 2][g], o2); o3 = fmaf(v3, s_f[sidx + 3][g], o3);
+    }
+    for (; sidx < ns; ++sidx) o0 = fmaf(__ldcg(col + size_t(sidx) * kAttnGT * kHeadDim), s_f[sidx][g], o0);
+    const float o = (o0 + o1) + (o2 + o3);
+    p.out[(size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + d] = f32_to_bf16_bits(o / s_L[g]);
+  }
+  SKV_STAMP(row_id == 0 ? split : 999, 7);
 }
 
 // (a2) append: one row of K and V per (b,h)
@@ -261,6 +314,8 @@ __global__ void append_kv_kernel(const int4 *__restrict__ k_new, const int4 *__r
 }  // namespace skv
 
 using namespace skv;
+
+SKV_TRACE_READER(attention)
 
 extern "C" {
 
@@ -284,25 +339,38 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
   p.sb = stride_b; p.sh = stride_h; p.sr = stride_row;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int64_t rows = int64_t(batch) * kv_heads * p.ngz;
-  const int step = (kAttnThreads / 32) * kAttnGroupKeys;     // 64 keys per CTA iteration
-  int kps;
+  // Split planning: one CTA per SM (register footprint), so the launch costs ceil(rows*ns/148) waves of
+  // (bytes streamed per SM + per-iteration latency + a fixed prologue), plus the merge of the partials.  Pick the split count that minimises
+  // it, then size the CTA (8..12 warps, 16 keys per warp per iteration) so that a split is ONE iteration
+  // per warp when the cache is short (batch 1: 8 rows x 18 splits x 9 warps = 144 CTAs, a single wave).
+  int ns = 1, kps = kv_len;
   if (num_splits > 0) {
-    kps = ((kv_len + num_splits - 1) / num_splits + step - 1) / step * step;
+    ns = num_splits > kAttnMaxSplits ? kAttnMaxSplits : num_splits;
   } else {
-    const int64_t target = 2 * kNumSMs;
-    int64_t want = (int64_t(kv_len) * rows + target - 1) / target;
-    kps = int((want + step - 1) / step * step);
+    double best = 1e30;
+    for (int c = 1; c <= kAttnMaxSplits; ++c) {
+      const int keys = ((kv_len + c - 1) / c + kAttnGroupKeys - 1) / kAttnGroupKeys * kAttnGroupKeys;
+      const int64_t waves = (rows * c + kNumSMs - 1) / kNumSMs;
+      const int iters = (keys + kAttnMaxWarps * kAttnGroupKeys - 1) / (kAttnMaxWarps * kAttnGroupKeys);
+      const double cost = double(waves) * (keys * 0.08 + iters * 8.0 + 6.0) + (c > 1 ? 4.0 + 0.25 * c : 0.0);
+      if (cost < best - 1e-9) { best = cost; ns = c; }
+    }
   }
-  if (kps < step) kps = step;
-  int ns = (kv_len + kps - 1) / kps;
-  while (ns > kAttnMaxSplits) { kps += step; ns = (kv_len + kps - 1) / kps; }
+  kps = ((kv_len + ns - 1) / ns + kAttnGroupKeys - 1) / kAttnGroupKeys * kAttnGroupKeys;
+  ns = (kv_len + kps - 1) / kps;
+  int warps = (kps / kAttnGroupKeys);
+  if (warps > kAttnMaxWarps) {                       // several iterations per warp: balance them
+    const int iters = (warps + kAttnMaxWarps - 1) / kAttnMaxWarps;
+    warps = (warps + iters - 1) / iters;
+  }
+  if (warps < kAttnMinWarps) warps = kAttnMinWarps;
   p.keys_per_split = kps; p.num_splits = ns;
   unsigned char *w = static_cast<unsigned char *>(workspace);
   p.part_o = reinterpret_cast<float *>(w);
   p.part_ml = p.part_o + rows * kAttnMaxSplits * kAttnGT * kHeadDim;
   p.counters = reinterpret_cast<int *>(p.part_ml + rows * kAttnMaxSplits * kAttnGT * 2);
   dim3 grid(ns, kv_heads * p.ngz, batch);
-  attention_decode_kernel<<<grid, kAttnThreads, 0, as_stream(stream)>>>(p);
+  attention_decode_kernel<<<grid, warps * 32, 0, as_stream(stream)>>>(p);
   return launch_status("attention_decode_kernel");
 }
 

@@ -21,7 +21,7 @@ struct ChunkTableSmem {
 // All threads of the block must call this (it synchronises); threads with tid >= S carry no element.
 // old_id / new_id: this thread's resident id and selected id (int32-truncated), valid for tid < S.
 // Outputs through pointers to global memory for this (b,h) row.
-template <int S>
+template <int S, bool kInPlace = false>
 __device__ __forceinline__ void chunk_table_update(int tid, int old_id, int new_id, ChunkTableSmem sm,
                                                    int64_t *__restrict__ g_resident,
                                                    int32_t *__restrict__ g_offsets,
@@ -32,9 +32,12 @@ __device__ __forceinline__ void chunk_table_update(int tid, int old_id, int new_
     sm.slot_of[tid] = INT_MAX;
   }
   __syncthreads();
+  // The ids usually arrive ascending already (the landmark index of the reference is an ascending list,
+  // kv_cache.py:909-915, and the selection is emitted in landmark order): one vote skips the sort.
+  const int in_order = __syncthreads_and(!active || tid == 0 || sm.sorted_new[tid - 1] <= new_id);
   // bitonic sort, ascending
 #pragma unroll 1
-  for (int k = 2; k <= S; k <<= 1) {
+  for (int k = 2; k <= (in_order ? 0 : S); k <<= 1) {
 #pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
       if (active) {
@@ -72,13 +75,29 @@ __device__ __forceinline__ void chunk_table_update(int tid, int old_id, int new_
   const int miss = (active && sm.slot_of[tid] == INT_MAX) ? 1 : 0;
   int nmiss;
   const int mpos = block_excl_scan(miss, sm.warp_tot, nmiss);
-  if (keep) {
-    g_resident[hpos] = static_cast<int64_t>(old_id);
-    g_offsets[hpos] = tid;
-  }
-  if (miss) {
-    g_resident[cnt + mpos] = static_cast<int64_t>(my_sorted);
-    g_offsets[cnt + mpos] = my_sorted;
+  if (!kInPlace) {
+    if (keep) {
+      g_resident[hpos] = static_cast<int64_t>(old_id);
+      g_offsets[hpos] = tid;
+    }
+    if (miss) {
+      g_resident[cnt + mpos] = static_cast<int64_t>(my_sorted);
+      g_offsets[cnt + mpos] = my_sorted;
+    }
+  } else {
+    // In-place table (B200 path): hits stay in their slots, so neither K nor V moves for them; the i-th
+    // missed chunk (ascending id) takes the i-th freed slot (ascending slot).  offsets[i] = that slot.
+    const int freed = (active && !keep) ? 1 : 0;
+    int nfree;
+    const int fpos = block_excl_scan(freed, sm.warp_tot, nfree);
+    __syncthreads();                       // slot_of is dead from here on: reuse it as the free-slot list
+    if (freed) sm.slot_of[fpos] = tid;
+    __syncthreads();
+    if (miss) {
+      const int slot = sm.slot_of[mpos];
+      g_resident[slot] = static_cast<int64_t>(my_sorted);
+      g_offsets[mpos] = slot;
+    }
   }
   if (tid == 0) *g_cnt = cnt;
 }

@@ -21,6 +21,25 @@ constexpr int kNumSMs = 148;
 
 void set_error(const char *fmt, ...);
 
+// Optional phase timeline for kernel tuning (build with `make TRACE=1`): thread 0 of a CTA stamps clock64()
+// into a per-translation-unit table, read back through skv_debug_read_trace_<unit>().  Compiled out of the
+// product library.
+#ifdef SKV_TRACE
+static __device__ long long g_skv_trace[8192];
+#define SKV_STAMP(cta, slot)                                                             \
+  do {                                                                                   \
+    if (threadIdx.x == 0 && (cta) < 256) g_skv_trace[(cta) * 32 + (slot)] = clock64();   \
+  } while (0)
+#define SKV_TRACE_READER(unit)                                                           \
+  extern "C" int skv_debug_read_trace_##unit(long long *host_out, int n) {               \
+    cudaDeviceSynchronize();                                                             \
+    return (int)cudaMemcpyFromSymbol(host_out, skv::g_skv_trace, sizeof(long long) * (n < 8192 ? n : 8192)); \
+  }
+#else
+#define SKV_STAMP(cta, slot) do { } while (0)
+#define SKV_TRACE_READER(unit)
+#endif
+
 inline cudaStream_t as_stream(skv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Collect the launch status without synchronising.
@@ -79,6 +98,11 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;

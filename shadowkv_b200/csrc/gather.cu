@@ -153,22 +153,35 @@ template <typename IdT>
 __global__ void __launch_bounds__(256)
     fetch_chunks_kernel(const skv_bf16 *__restrict__ src, int64_t src_stride_bh, skv_bf16 *__restrict__ dst,
                         int64_t dst_stride_bh, int64_t dst_base_off, const IdT *__restrict__ ids,
-                        const int32_t *__restrict__ cnts, int S) {
+                        const int32_t *__restrict__ cnts, const int64_t *__restrict__ resident, int S) {
   const int bh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cnt = cnts ? cnts[bh] : 0;
-  const int i = (blockIdx.x * 8 + warp) * 2;          // two slots per warp
-  if (i + 1 < cnt || i >= S) return;
+  const int i = (blockIdx.x * 8 + warp) * 2;          // two slots (or two entries of the miss list) per warp
   const int4 *sbase = reinterpret_cast<const int4 *>(src + size_t(bh) * src_stride_bh);
   int4 *dbase = reinterpret_cast<int4 *>(dst + size_t(bh) * dst_stride_bh + dst_base_off);
   const IdT *id = ids + size_t(bh) * S;
   int4 v[2][4];
   bool on[2];
+  int slot[2];
+  if (resident) {                                     // in-place table: ids[] lists the slots of the S-cnt misses
+    if (i >= S - cnt) return;
+  } else if (i + 1 < cnt || i >= S) {
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    on[u] = (i + u) >= cnt && (i + u) < S;
+    long long chunk = 0;
+    if (resident) {
+      on[u] = (i + u) < S - cnt;
+      if (on[u]) { slot[u] = static_cast<int>(id[i + u]); chunk = resident[size_t(bh) * S + slot[u]]; }
+    } else {
+      on[u] = (i + u) >= cnt && (i + u) < S;
+      slot[u] = i + u;
+      if (on[u]) chunk = static_cast<long long>(id[i + u]);
+    }
     if (on[u]) {
-      const int4 *p = sbase + size_t(id[i + u]) * (kChunkBytes / 16) + lane;
+      const int4 *p = sbase + size_t(chunk) * (kChunkBytes / 16) + lane;
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[u][k] = ld_stream(p + k * 32);
     }
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     if (on[u]) {
-      int4 *p = dbase + size_t(i + u) * (kChunkBytes / 16) + lane;
+      int4 *p = dbase + size_t(slot[u]) * (kChunkBytes / 16) + lane;
 #pragma unroll
       for (int k = 0; k < 4; ++k) p[k * 32] = v[u][k];
     }
@@ -185,9 +198,9 @@ __global__ void __launch_bounds__(256)
 
 template <typename IdT>
 static int launch_fetch(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, int64_t dst_stride, int64_t dst_off,
-                        const IdT *ids, const int32_t *cnts, int BH, int S, cudaStream_t st) {
+                        const IdT *ids, const int32_t *cnts, const int64_t *resident, int BH, int S, cudaStream_t st) {
   dim3 grid((S + 15) / 16, BH);
-  fetch_chunks_kernel<IdT><<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, dst_off, ids, cnts, S);
+  fetch_chunks_kernel<IdT><<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, dst_off, ids, cnts, resident, S);
   return launch_status("fetch_chunks_kernel");
 }
 
@@ -220,7 +233,7 @@ int skv_gather_copy(const skv_bf16 *values, skv_bf16 *v_cache_buffer, const int6
                     int heads, int cpu_v_length, int gpu_v_length, int map_size, skv_stream_t stream) {
   if (!values || !v_cache_buffer || !position_ids) { set_error("gather_copy: null pointer"); return SKV_ERR_ARGUMENT; }
   if (!valid_map_size(map_size)) { set_error("gather_copy: map_size %d unsupported", map_size); return SKV_ERR_UNSUPPORTED; }
-  return launch_fetch<int64_t>(values, cpu_v_length, v_cache_buffer, gpu_v_length, 0, position_ids, nullptr,
+  return launch_fetch<int64_t>(values, cpu_v_length, v_cache_buffer, gpu_v_length, 0, position_ids, nullptr, nullptr,
                                batch_size * heads, map_size, as_stream(stream));
 }
 
@@ -245,7 +258,7 @@ int skv_gather_copy_with_offsets(const skv_bf16 *values, skv_bf16 *v_cache_buffe
   int rc = launch_compact(v_cache_buffer, nullptr, offsets, cnts, batch_size * heads, map_size, gpu_v_stride,
                           gpu_v_offset, st);
   if (rc) return rc;
-  return launch_fetch<int32_t>(values, cpu_v_length, v_cache_buffer, gpu_v_stride, gpu_v_offset, offsets, cnts,
+  return launch_fetch<int32_t>(values, cpu_v_length, v_cache_buffer, gpu_v_stride, gpu_v_offset, offsets, cnts, nullptr,
                                batch_size * heads, map_size, st);
 }
 
@@ -260,14 +273,17 @@ int skv_compact_hits(const skv_geom *g, skv_bf16 *k_buf, skv_bf16 *v_buf, const 
 }
 
 int skv_fetch_misses(const skv_geom *g, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
-                     const int32_t *offsets, const int32_t *cnts, skv_stream_t stream) {
-  if (!g || !v_host || !v_buf || !offsets || !cnts) { set_error("fetch_misses: null pointer"); return SKV_ERR_ARGUMENT; }
+                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, skv_stream_t stream) {
+  if (!g || !v_host || !v_buf || !offsets || !cnts || (g->table_mode && !resident)) {
+    set_error("fetch_misses: null pointer"); return SKV_ERR_ARGUMENT;
+  }
   if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select)) {
     set_error("fetch_misses: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
   }
   return launch_fetch<int32_t>(v_host, host_stride, v_buf, int64_t(g->buf_len) * g->head_dim,
-                               int64_t(g->sparse_start) * g->head_dim, offsets, cnts, g->batch * g->kv_heads,
-                               g->select, as_stream(stream));
+                               int64_t(g->sparse_start) * g->head_dim, offsets, cnts,
+                               g->table_mode ? resident : nullptr, g->batch * g->kv_heads, g->select,
+                               as_stream(stream));
 }
 
 }  // extern "C"

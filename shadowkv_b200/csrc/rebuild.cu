@@ -115,6 +115,7 @@ struct RebuildParams {
   const int64_t *resident;   // [BH, S] chunk ids (after reorder)
   const int32_t *ids32;      // alternative int32 ids (drop-in batch_gather_gemm); one of the two is set
   const int32_t *cnts;       // [BH]
+  const int32_t *miss_slots; // in-place table: [BH, S] slot of the i-th miss (i < S - cnt); null = slots cnt..S-1
   const __nv_bfloat16 *cos_sin;
   __nv_bfloat16 *out;        // K buffer (fused) or scratch [BH, S*8, 128] (drop-in)
   int64_t out_stride_bh;     // elements
@@ -133,20 +134,32 @@ __global__ void __launch_bounds__(128, 1)
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kMaxSlabs * (kSlabBytesA + kSlabBytesB));
   uint64_t *mma_bar = full_bar + kMaxSlabs;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 1);
-  int *s_ids = reinterpret_cast<int *>(tmem_slot + 2);        // [16]
+  int *s_ids = reinterpret_cast<int *>(tmem_slot + 2);        // [16] chunk id per tile row group (-1: skip)
+  int *s_slots = s_ids + kTileChunks;                         // [16] destination slot
 
   const int tile = blockIdx.x, bh = blockIdx.y, b = bh / p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cnt = p.cnts ? p.cnts[bh] : 0;
   const int first_slot = tile * kTileChunks;
-  if (first_slot + kTileChunks <= cnt) return;                // tile entirely cache hits (uniform per CTA)
+  if (p.miss_slots) {
+    if (first_slot >= p.S - cnt) return;                      // tiles run over the miss list in this mode
+  } else if (first_slot + kTileChunks <= cnt) {
+    return;                                                   // tile entirely cache hits (uniform per CTA)
+  }
 
   if (threadIdx.x < kTileChunks) {
-    const int slot = first_slot + threadIdx.x;
+    int slot = first_slot + threadIdx.x;
     int id = -1;
-    if (slot < p.S && (p.tile_skip || slot >= cnt))
+    if (p.miss_slots) {
+      if (slot < p.S - cnt) {
+        slot = p.miss_slots[size_t(bh) * p.S + slot];
+        id = static_cast<int>(p.resident[size_t(bh) * p.S + slot]);
+      }
+    } else if (slot < p.S && (p.tile_skip || slot >= cnt)) {
       id = p.resident ? static_cast<int>(p.resident[size_t(bh) * p.S + slot]) : p.ids32[size_t(bh) * p.S + slot];
+    }
     s_ids[threadIdx.x] = id;
+    s_slots[threadIdx.x] = slot;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_slabs; ++s) mbarrier_init(&full_bar[s], 1);
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(128, 1)
   const int row = threadIdx.x;                     // warp w owns TMEM lanes 32w..32w+31
   const int j = row >> 3, r = row & 7;
   const int id = s_ids[j];
-  const int slot = first_slot + j;
+  const int slot = s_slots[j];
   const bool write = id >= 0;
   const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
   __nv_bfloat16 *orow = p.out + size_t(bh) * p.out_stride_bh + (p.out_row0 + size_t(slot) * kChunkTokens + r) * kHeadDim;
@@ -287,9 +300,15 @@ __global__ void __launch_bounds__(128)
     rebuild_simt_kernel(const __nv_bfloat16 *__restrict__ U, const __nv_bfloat16 *__restrict__ SV, RebuildParams p) {
   __shared__ float s_u[kChunkTokens][256];
   __shared__ __nv_bfloat16 s_k[kChunkTokens][kHeadDim];
-  const int slot = blockIdx.x, bh = blockIdx.y, b = bh / p.H, d = threadIdx.x;
+  const int bh = blockIdx.y, b = bh / p.H, d = threadIdx.x;
   const int cnt = p.cnts ? p.cnts[bh] : 0;
-  if (p.tile_skip ? (slot / kTileChunks + 1) * kTileChunks <= cnt : slot < cnt) return;
+  int slot = blockIdx.x;
+  if (p.miss_slots) {
+    if (slot >= p.S - cnt) return;
+    slot = p.miss_slots[size_t(bh) * p.S + slot];
+  } else if (p.tile_skip ? (slot / kTileChunks + 1) * kTileChunks <= cnt : slot < cnt) {
+    return;
+  }
   const int id = p.resident ? static_cast<int>(p.resident[size_t(bh) * p.S + slot]) : p.ids32[size_t(bh) * p.S + slot];
   const __nv_bfloat16 *u = U + (size_t(b) * p.L + size_t(id) * kChunkTokens) * p.R;
   for (int i = threadIdx.x; i < kChunkTokens * p.R; i += 128) s_u[i / p.R][i % p.R] = __bfloat162float(u[i]);
@@ -386,7 +405,7 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
   if (rc) return rc;
   rc = make_map(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim);
   if (rc) return rc;
-  const int smem = kMaxSlabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 16 * 4 + 64;
+  const int smem = kMaxSlabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   dim3 grid((p.S + kTileChunks - 1) / kTileChunks, BH);
@@ -401,13 +420,16 @@ using namespace skv;
 extern "C" {
 
 int skv_rebuild_keys(const skv_geom *g, const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin,
-                     const int64_t *resident, const int32_t *cnts, skv_bf16 *k_buf, int impl, skv_stream_t stream) {
-  if (!g || !U || !SV || !cos_sin || !resident || !cnts || !k_buf) { set_error("rebuild_keys: null pointer"); return SKV_ERR_ARGUMENT; }
+                     const int64_t *resident, const int32_t *cnts, const int32_t *offsets, skv_bf16 *k_buf, int impl,
+                     skv_stream_t stream) {
+  if (!g || !U || !SV || !cos_sin || !resident || !cnts || !k_buf || (g->table_mode && !offsets)) {
+    set_error("rebuild_keys: null pointer"); return SKV_ERR_ARGUMENT;
+  }
   if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select)) {
     set_error("rebuild_keys: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
   }
   RebuildParams p{};
-  p.resident = resident; p.cnts = cnts;
+  p.resident = resident; p.cnts = cnts; p.miss_slots = g->table_mode ? offsets : nullptr;
   p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(cos_sin);
   p.out = reinterpret_cast<__nv_bfloat16 *>(k_buf);
   p.out_stride_bh = int64_t(g->buf_len) * g->head_dim;

@@ -9,8 +9,12 @@
 //                       (map.cuh:754-796) -- replaces 3 CUTLASS launches + torch.max + torch.topk + gather +
 //                       reorder of the reference with two launches.
 //  softmax_apply_kernel: only for the drop-in batch_gemm_softmax entry point (materialises Softmax).
+#include <cooperative_groups.h>
+
 #include "chunk_table.cuh"
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace skv {
 
@@ -25,8 +29,19 @@ __global__ void __launch_bounds__(kScoreThreads)
                        skv_bf16 *__restrict__ scores,           // [BH, G, N]
                        float *__restrict__ part_max,            // [BH, G, T]
                        float *__restrict__ part_sum,            // [BH, G, T]
-                       int G, int N, int T, float alpha) {
+                       int G, int N, int ldn, int T, float alpha,       // ldn: row stride of `scores` (>= N)
+                       skv_append ap, int64_t buf_rows) {
   constexpr int kTileRows = kRowsPerWarp * (kScoreThreads / 32);
+  // fused append (a2): the first CTA of every (b,h) writes the new token's K and V rows
+  if (ap.k_new && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x < 32) {
+    const int64_t pos = ap.pos + (ap.pos_dev ? *ap.pos_dev : 0);
+    if (pos < buf_rows) {
+      const int c = threadIdx.x & 15;
+      const int4 *src = reinterpret_cast<const int4 *>(threadIdx.x < 16 ? ap.k_new : ap.v_new) + size_t(blockIdx.y) * 16 + c;
+      int4 *dst = reinterpret_cast<int4 *>(threadIdx.x < 16 ? ap.k_buf : ap.v_buf) + (size_t(blockIdx.y) * buf_rows + pos) * 16 + c;
+      *dst = *src;
+    }
+  }
   __shared__ float s_tile[GT][kTileRows];
   const int tile = blockIdx.x, bh = blockIdx.y, g0 = blockIdx.z * GT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(kScoreThreads)
       const uint16_t bits = f32_to_bf16_bits(fin[k] * alpha);
       float sv = -INFINITY;
       if (row < N && g0 + g < G) {
-        scores[(size_t(bh) * G + g0 + g) * N + row] = bits;
+        scores[(size_t(bh) * G + g0 + g) * ldn + row] = bits;
         sv = bf16_bits_to_f32(bits);
       }
       s_tile[g][lrow] = sv;
@@ -179,14 +194,21 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
-// select_kernel
+// select_kernel: one cluster of 8 CTAs per (b,h).  Every CTA owns a contiguous eighth of the landmarks:
+// it turns the bf16 scores of the G heads into the bf16 softmax value, keeps the max over the heads as a
+// 16-bit key in shared memory, and builds warp-private 256-bin histograms (no shared-memory atomics; a
+// softmax row has only a handful of distinct exponents, so a shared histogram serialises on 3-4 bins).
+// The 8 partial histograms are summed through distributed shared memory, so every CTA finds the same
+// two-level radix threshold; the selected landmarks are then emitted in ascending index order straight
+// into CTA 0's shared memory, and CTA 0 runs the chunk-table update.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSelThreads = 1024;
+constexpr int kSelCluster = 8;
 
-// histogram of `bin` (0..255; 0xFFFF = no element) with one atomic per distinct value per warp
-__device__ __forceinline__ void hist_add(int *hist, unsigned bin) {
+// warp-private histogram: after __match_any_sync the leaders of distinct bins touch distinct words
+__device__ __forceinline__ void hist_add_private(int *hist, unsigned bin) {
   const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin != 0xFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+  if (bin != 0xFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) hist[bin] += __popc(peers);
+  __syncwarp();
 }
 
 // Warp 0: find the highest bin b with (count of bins above b) < want <= (count of bins >= b).
@@ -209,143 +231,308 @@ __device__ __forceinline__ void find_threshold_bin(const int *hist, int want, in
   }
 }
 
-template <int S>
-__global__ void __launch_bounds__(kSelThreads)
-    select_kernel(const skv_bf16 *__restrict__ scores,        // [BH, G, N] bf16 scaled dot products
+// Final (max, 1/sum) with both partial arrays fetched in one round trip (<= 8 x 32 tiles per lane in
+// registers; longer rows fall back to reduce_partials).
+__device__ __forceinline__ void reduce_partials_fast(const float *pm, const float *ps, int T, int lane, float &m_out,
+                                                     float &inv_out) {
+  if (T > 256) { reduce_partials(pm, ps, T, lane, m_out, inv_out); return; }
+  float vm[8], vs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = lane + 32 * i;
+    vm[i] = t < T ? pm[t] : -INFINITY;
+    vs[i] = t < T ? ps[t] : 0.f;
+  }
+  float m = vm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, vm[i]);
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += vs[i] * ((vm[i] == -INFINITY) ? 0.f : expf(vm[i] - m));
+  sum = warp_sum(sum);
+  m_out = m;
+  inv_out = 1.0f / sum;
+}
+
+// exclusive block scan of two ints at once; returns the exclusive prefixes, `tot_*` the block sums
+template <int kWarps>
+__device__ __forceinline__ void block_excl_scan2(int a, int b, int *wa, int *wb, int &pa, int &pb, int &tot_a,
+                                                 int &tot_b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ia = warp_incl_scan(a), ib = warp_incl_scan(b);
+  __syncthreads();                        // wa / wb may still be read from a previous round
+  if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+  __syncthreads();
+  if (warp == 0) {
+    const int xa = lane < kWarps ? wa[lane] : 0, xb = lane < kWarps ? wb[lane] : 0;
+    const int sa = warp_incl_scan(xa), sb = warp_incl_scan(xb);
+    if (lane < kWarps) { wa[lane] = sa - xa; wb[lane] = sb - xb; }
+    if (lane == 31) { wa[kWarps] = sa; wb[kWarps] = sb; }
+  }
+  __syncthreads();
+  pa = wa[warp] + ia - a;
+  pb = wb[warp] + ib - b;
+  tot_a = wa[kWarps];
+  tot_b = wb[kWarps];
+}
+
+template <int S, bool kInPlace>
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? S : 256)
+    select_kernel(const skv_bf16 *__restrict__ scores,        // [BH, G, ldn] bf16 scaled dot products
                   const float *__restrict__ part_max, const float *__restrict__ part_sum,   // [BH, G, T]
                   const int64_t *__restrict__ landmark_idx,   // [BH, N]
                   int64_t *__restrict__ resident,             // [BH, S] in/out
                   int32_t *__restrict__ offsets, int32_t *__restrict__ cnts,
                   int64_t *__restrict__ selected_out,         // [BH, S] or null
                   skv_bf16 *__restrict__ score_out,           // [BH, N] or null
-                  int G, int N, int T) {
+                  int G, int N, int ldn, int T, int per) {
+  constexpr int kThreads = S > 256 ? S : 256;
+  constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char sel_smem[];
-  uint16_t *keys = reinterpret_cast<uint16_t *>(sel_smem);                   // [N rounded to 8]
+  int *whist1 = reinterpret_cast<int *>(sel_smem);                                 // [kWarps][256] level 1
+  int *whist2 = whist1 + kWarps * 256;                                             // [kWarps][256] level 2
+  uint16_t *keys = reinterpret_cast<uint16_t *>(sel_smem + 2 * kWarps * 256 * 4);  // [per rounded to 8]
   __shared__ float s_m[16], s_inv[16];
-  __shared__ int s_hist[256];
+  __shared__ int s_parts1[kSelCluster][256];    // level-1 histograms of all 8 CTAs (each CTA stores into every CTA)
+  __shared__ int s_parts2[kSelCluster][256];
+  __shared__ int s_tot[256];
   __shared__ int s_res[4];
-  __shared__ int s_wgt[32], s_weq[32];
-  __shared__ int s_sel[S];
+  __shared__ int s_cnts[kSelCluster][2];        // (greater, equal) counts of all 8 CTAs
+  __shared__ int s_wa[kWarps + 1], s_wb[kWarps + 1];
+  __shared__ int s_new[S];                      // CTA 0: selected chunk ids in ascending landmark order
   __shared__ int s_sorted[S], s_slot[S], s_warp[33];
 
-  const int bh = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = blockIdx.x;                  // the cluster spans blockIdx.x
+  const int bh = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_begin = min(N, rank * per), n_end = min(N, n_begin + per);
+  const int count = n_end - n_begin;            // only the last slice can be ragged (N % 8 != 0)
+  SKV_STAMP(bh == 0 ? rank : 999, 0);
 
-  // 1. final softmax statistics per head
-  for (int g = warp; g < G; g += kSelThreads / 32) {
+  // early, independent global loads: landmark ids of this thread's first 8 landmarks, its resident id
+  const int64_t *lidx = landmark_idx + size_t(bh) * N + n_begin;
+  int ids0[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ids0[e] = (tid * 8 + e < count) ? static_cast<int>(lidx[tid * 8 + e]) : 0;   // map.cuh:776
+  int old_id = 0;
+  if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
+
+  // 0. final softmax statistics per head (every CTA redundantly: G x T floats)
+  for (int g = warp; g < G; g += kWarps) {
     float m, inv;
-    reduce_partials(part_max + (size_t(bh) * G + g) * T, part_sum + (size_t(bh) * G + g) * T, T, lane, m, inv);
+    reduce_partials_fast(part_max + (size_t(bh) * G + g) * T, part_sum + (size_t(bh) * G + g) * T, T, lane, m, inv);
     if (lane == 0) { s_m[g] = m; s_inv[g] = inv; }
   }
-  if (tid < 256) s_hist[tid] = 0;
+  for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
   __syncthreads();
+  SKV_STAMP(bh == 0 ? rank : 999, 1);
 
-  // 2. p = bf16(exp(s - max) * inv); key = max over heads (bf16 bits are monotone for p >= 0);
-  //    first-level histogram on the high byte
-  const skv_bf16 *sc = scores + size_t(bh) * G * N;
-  const int n_iter = (N + kSelThreads - 1) / kSelThreads;
-  for (int i = 0; i < n_iter; ++i) {
-    const int n = i * kSelThreads + tid;
-    unsigned bin = 0xFFFFu;
-    if (n < N) {
-      uint16_t best = 0;
+  // 1. p = bf16(exp(s - max) * inv); key = max over heads (bf16 bits are monotone for p >= 0);
+  //    first-level histogram on the high byte.  8 consecutive landmarks per thread: 16-byte loads.
+  const skv_bf16 *sc = scores + size_t(bh) * G * ldn;
+  int *my_h1 = whist1 + warp * 256, *my_h2 = whist2 + warp * 256;
+  for (int base = 0; base < count; base += kThreads * 8) {
+    const int off = base + tid * 8;
+    const bool on = off < count;
+    uint16_t best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (on) {
+      const int n = n_begin + off;
+#pragma unroll 4
       for (int g = 0; g < G; ++g) {
-        const float p = expf(bf16_bits_to_f32(sc[size_t(g) * N + n]) - s_m[g]) * s_inv[g];
-        const uint16_t b = f32_to_bf16_bits(p);
-        best = b > best ? b : best;
+        const int4 w = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n);
+        const uint32_t u[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+        const float m = s_m[g], inv = s_inv[g];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint16_t b0 = f32_to_bf16_bits(expf(bf16_lo(u[e]) - m) * inv);
+          const uint16_t b1 = f32_to_bf16_bits(expf(bf16_hi(u[e]) - m) * inv);
+          best[2 * e] = b0 > best[2 * e] ? b0 : best[2 * e];
+          best[2 * e + 1] = b1 > best[2 * e + 1] ? b1 : best[2 * e + 1];
+        }
       }
-      keys[n] = best;
-      if (score_out) score_out[size_t(bh) * N + n] = best;
-      bin = best >> 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (off + e >= count) best[e] = 0;                    // ragged tail: never selected (p > 0 for real keys)
+      const int4 packed = make_int4(int(best[0] | (uint32_t(best[1]) << 16)), int(best[2] | (uint32_t(best[3]) << 16)),
+                                    int(best[4] | (uint32_t(best[5]) << 16)), int(best[6] | (uint32_t(best[7]) << 16)));
+      *reinterpret_cast<int4 *>(keys + off) = packed;
+      if (score_out) {
+        if (ldn == N) {
+          *reinterpret_cast<int4 *>(score_out + size_t(bh) * N + n) = packed;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (off + e < count) score_out[size_t(bh) * N + n + e] = best[e];
+        }
+      }
     }
-    hist_add(s_hist, bin);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hist_add_private(my_h1, (on && off + e < count) ? unsigned(best[e] >> 8) : 0xFFFFu);
+  }
+  SKV_STAMP(bh == 0 ? rank : 999, 2);
+  __syncthreads();
+  if (tid < 256) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += whist1[w * 256 + tid];
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts1[rank][tid], r)[0] = t;   // push to every CTA
+  }
+  cluster.sync();
+  SKV_STAMP(bh == 0 ? rank : 999, 3);
+  if (tid < 256) {
+    int t = 0;
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) t += s_parts1[r][tid];
+    s_tot[tid] = t;
   }
   __syncthreads();
-  if (warp == 0) find_threshold_bin(s_hist, S, s_res);
+  if (warp == 0) find_threshold_bin(s_tot, S, s_res);
   __syncthreads();
   const int b1 = s_res[0], above1 = s_res[1];
-  if (tid < 256) s_hist[tid] = 0;
-  __syncthreads();
-  for (int i = 0; i < n_iter; ++i) {
-    const int n = i * kSelThreads + tid;
-    unsigned bin = 0xFFFFu;
-    if (n < N) {
-      const uint16_t k = keys[n];
-      if ((k >> 8) == b1) bin = k & 0xFF;
+  SKV_STAMP(bh == 0 ? rank : 999, 4);
+
+  // 2. second level: low byte of the keys inside the threshold bin
+  for (int base = 0; base < count; base += kThreads * 8) {
+    const int off = base + tid * 8;
+    const bool on = off < count;
+    uint32_t kw[4] = {0, 0, 0, 0};
+    if (on) {
+      const int4 w = *reinterpret_cast<const int4 *>(keys + off);
+      kw[0] = w.x; kw[1] = w.y; kw[2] = w.z; kw[3] = w.w;
     }
-    hist_add(s_hist, bin);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+      hist_add_private(my_h2, (on && off + e < count && int(k >> 8) == b1) ? (k & 0xFFu) : 0xFFFFu);
+    }
+  }
+  SKV_STAMP(bh == 0 ? rank : 999, 5);
+  __syncthreads();
+  if (tid < 256) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += whist2[w * 256 + tid];
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts2[rank][tid], r)[0] = t;
+  }
+  cluster.sync();
+  SKV_STAMP(bh == 0 ? rank : 999, 6);
+  if (tid < 256) {
+    int t = 0;
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) t += s_parts2[r][tid];
+    s_tot[tid] = t;
   }
   __syncthreads();
-  if (warp == 0) find_threshold_bin(s_hist, S - above1, s_res + 2);
+  if (warp == 0) find_threshold_bin(s_tot, S - above1, s_res + 2);
   __syncthreads();
   const unsigned thr = (unsigned(b1) << 8) | unsigned(s_res[2]);
   const int need_eq = S - (above1 + s_res[3]);      // how many keys equal to thr are taken (>= 1)
+  SKV_STAMP(bh == 0 ? rank : 999, 7);
 
-  // 3. ordered emission (ascending landmark index).  Warp w owns a contiguous range.
-  const int per_warp = (((N + 31) / 32 + 31) / 32) * 32;      // multiple of 32
-  const int w_begin = warp * per_warp, w_end = min(N, w_begin + per_warp);
-  int wgt = 0, weq = 0;
-  for (int n0 = w_begin; n0 < w_end; n0 += 32) {
-    const int n = n0 + lane;
-    const unsigned k = n < w_end ? keys[n] : 0u;
-    const bool valid = n < w_end;
-    wgt += __popc(__ballot_sync(0xffffffffu, valid && k > thr));
-    weq += __popc(__ballot_sync(0xffffffffu, valid && k == thr));
-  }
-  if (lane == 0) { s_wgt[warp] = wgt; s_weq[warp] = weq; }
-  __syncthreads();
-  if (warp == 0) {
-    const int g_incl = warp_incl_scan(s_wgt[lane]);
-    const int e_incl = warp_incl_scan(s_weq[lane]);
-    __syncwarp();
-    s_wgt[lane] = g_incl - s_wgt[lane];
-    s_weq[lane] = e_incl - s_weq[lane];
-  }
-  __syncthreads();
+  // 3. (greater, equal) counts of this CTA's slice, pushed to every CTA of the cluster
   {
-    int eq_seen = s_weq[warp];
-    int pos = s_wgt[warp] + min(eq_seen, need_eq);
-    for (int n0 = w_begin; n0 < w_end; n0 += 32) {
-      const int n = n0 + lane;
-      const bool valid = n < w_end;
-      const unsigned k = valid ? keys[n] : 0u;
-      const unsigned eqm = __ballot_sync(0xffffffffu, valid && k == thr);
-      const int my_eq_rank = eq_seen + __popc(eqm & ((1u << lane) - 1u));
-      const bool take = valid && (k > thr || (k == thr && my_eq_rank < need_eq));
-      const unsigned tm = __ballot_sync(0xffffffffu, take);
-      if (take) s_sel[pos + __popc(tm & ((1u << lane) - 1u))] = n;
-      pos += __popc(tm);
-      eq_seen += __popc(eqm);
+    int gt = 0, eq = 0;
+    for (int base = 0; base < count; base += kThreads * 8) {
+      const int off = base + tid * 8;
+      if (off < count) {
+        const int4 w = *reinterpret_cast<const int4 *>(keys + off);
+        const uint32_t kw[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;     // padded tail keys are 0 < thr
+          gt += k > thr; eq += k == thr;
+        }
+      }
+    }
+    gt = warp_sum_int(gt); eq = warp_sum_int(eq);
+    if (lane == 0) { s_wa[warp] = gt; s_wb[warp] = eq; }
+    __syncthreads();
+    if (warp == 0) {
+      int a = lane < kWarps ? s_wa[lane] : 0, e = lane < kWarps ? s_wb[lane] : 0;
+      a = warp_sum_int(a); e = warp_sum_int(e);
+      if (lane < kSelCluster) {
+        int *dst = cluster.map_shared_rank(&s_cnts[rank][0], lane);
+        dst[0] = a; dst[1] = e;
+      }
     }
   }
-  __syncthreads();
+  SKV_STAMP(bh == 0 ? rank : 999, 8);
+  cluster.sync();
+  SKV_STAMP(bh == 0 ? rank : 999, 9);
+  int gt_before = 0, eq_before = 0;
+  for (int r = 0; r < rank; ++r) { gt_before += s_cnts[r][0]; eq_before += s_cnts[r][1]; }
+  SKV_STAMP(bh == 0 ? rank : 999, 10);
 
-  // 4. chunk ids of the selection, then the chunk-table update
-  int new_id = 0, old_id = 0;
-  if (tid < S) {
-    const int64_t cid = landmark_idx[size_t(bh) * N + s_sel[tid]];
-    if (selected_out) selected_out[size_t(bh) * S + tid] = cid;
-    new_id = static_cast<int>(cid);
-    old_id = static_cast<int>(resident[size_t(bh) * S + tid]);
+  // 4. ordered emission (ascending landmark index): thread t owns 8 consecutive landmarks per round, so the
+  //    position of a taken key = (#greater before it) + min(#equal before it, need_eq), by a block scan.
+  {
+    int *dst = cluster.map_shared_rank(s_new, 0);
+    for (int base = 0; base < count; base += kThreads * 8) {
+      const int off = base + tid * 8;
+      const bool on = off < count;
+      uint32_t kw[4] = {0, 0, 0, 0};
+      if (on) {
+        const int4 w = *reinterpret_cast<const int4 *>(keys + off);
+        kw[0] = w.x; kw[1] = w.y; kw[2] = w.z; kw[3] = w.w;
+      }
+      int gt = 0, eq = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+        gt += k > thr; eq += k == thr;
+      }
+      int pg, pe, tg, te;
+      block_excl_scan2<kWarps>(gt, eq, s_wa, s_wb, pg, pe, tg, te);
+      int gt_seen = gt_before + pg, eq_seen = eq_before + pe;
+      if (gt | eq) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+          const bool take = k > thr || (k == thr && eq_seen < need_eq);
+          if (take) dst[gt_seen + min(eq_seen, need_eq)] = base == 0 ? ids0[e] : static_cast<int>(lidx[off + e]);
+          gt_seen += k > thr; eq_seen += k == thr;
+        }
+      }
+      gt_before += tg; eq_before += te;
+    }
   }
+  SKV_STAMP(bh == 0 ? rank : 999, 11);
+  cluster.sync();
+  SKV_STAMP(bh == 0 ? rank : 999, 12);
+  if (rank != 0) return;
+
+  // 5. chunk-table update (CTA 0)
+  int new_id = 0;
+  if (tid < S) {
+    new_id = s_new[tid];
+    if (selected_out) selected_out[size_t(bh) * S + tid] = static_cast<int64_t>(new_id);
+  }
+  SKV_STAMP(bh == 0 ? rank : 999, 13);
   ChunkTableSmem sm{s_sorted, s_slot, s_warp};
-  chunk_table_update<S>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S, cnts + bh);
+  chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
+                                  cnts + bh);
+  SKV_STAMP(bh == 0 ? rank : 999, 14);
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct SelectWorkspace {
-  skv_bf16 *scores;
+  skv_bf16 *scores;      // [BH, G, ldn], ldn = N rounded up to 8 so every row is 16-byte aligned
   float *pmax, *psum;
-  int T;
+  int T, ldn;
 };
 
 static SelectWorkspace carve(const skv_geom *g, void *ws) {
   SelectWorkspace w;
   const int64_t BH = int64_t(g->batch) * g->kv_heads;
   w.T = (g->n_landmarks + 127) / 128;
+  w.ldn = (g->n_landmarks + 7) / 8 * 8;
   unsigned char *p = static_cast<unsigned char *>(ws);
   w.scores = reinterpret_cast<skv_bf16 *>(p);
-  p += align_up(BH * g->q_groups * g->n_landmarks * 2, 256);
+  p += align_up(BH * g->q_groups * w.ldn * 2, 256);
   w.pmax = reinterpret_cast<float *>(p);
   p += align_up(BH * g->q_groups * w.T * 4, 256);
   w.psum = reinterpret_cast<float *>(p);
@@ -354,13 +541,16 @@ static SelectWorkspace carve(const skv_geom *g, void *ws) {
 
 template <int kRowsPerWarp>
 static int launch_scores(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH,
-                         int G, int N, int T, float alpha, cudaStream_t st) {
+                         int G, int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append = nullptr,
+                         int64_t buf_rows = 0) {
+  skv_append ap{};
+  if (append) ap = *append;
   if (G <= 4) {
     dim3 grid(T, BH, 1);
-    score_tiles_kernel<4, kRowsPerWarp><<<grid, kScoreThreads, 0, st>>>(q, lm, scores, pmax, psum, G, N, T, alpha);
+    score_tiles_kernel<4, kRowsPerWarp><<<grid, kScoreThreads, 0, st>>>(q, lm, scores, pmax, psum, G, N, ldn, T, alpha, ap, buf_rows);
   } else {
     dim3 grid(T, BH, (G + 7) / 8);
-    score_tiles_kernel<8, kRowsPerWarp><<<grid, kScoreThreads, 0, st>>>(q, lm, scores, pmax, psum, G, N, T, alpha);
+    score_tiles_kernel<8, kRowsPerWarp><<<grid, kScoreThreads, 0, st>>>(q, lm, scores, pmax, psum, G, N, ldn, T, alpha, ap, buf_rows);
   }
   return launch_status("score_tiles_kernel");
 }
@@ -369,18 +559,21 @@ static int launch_scores(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores
 
 using namespace skv;
 
+SKV_TRACE_READER(score)
+
 extern "C" {
 
 int64_t skv_select_workspace_bytes(const skv_geom *g) {
   if (!g) return 0;
   const int64_t BH = int64_t(g->batch) * g->kv_heads;
   const int64_t T = (g->n_landmarks + 127) / 128;
-  return align_up(BH * g->q_groups * g->n_landmarks * 2, 256) + 2 * align_up(BH * g->q_groups * T * 4, 256);
+  const int64_t ldn = (g->n_landmarks + 7) / 8 * 8;
+  return align_up(BH * g->q_groups * ldn * 2, 256) + 2 * align_up(BH * g->q_groups * T * 4, 256);
 }
 
 static int check_select_geom(const skv_geom *g, const char *who) {
   if (g->head_dim != kHeadDim || g->q_groups < 1 || g->q_groups > 16 || !valid_map_size(g->select) ||
-      g->n_landmarks < g->select || g->n_landmarks > 100000) {
+      g->n_landmarks < g->select || g->n_landmarks > 720000) {
     set_error("%s: unsupported geometry (D=%d G=%d S=%d N=%d)", who, g->head_dim, g->q_groups, g->select,
               g->n_landmarks);
     return SKV_ERR_UNSUPPORTED;
@@ -389,13 +582,18 @@ static int check_select_geom(const skv_geom *g, const char *who) {
 }
 
 int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, void *workspace,
-                        skv_stream_t stream) {
+                        const skv_append *append, skv_stream_t stream) {
   if (!g || !q || !landmarks || !workspace) { set_error("score_landmarks: null pointer"); return SKV_ERR_ARGUMENT; }
   if (int rc = check_select_geom(g, "score_landmarks")) return rc;
+  if (append && (!append->k_new || !append->v_new || !append->k_buf || !append->v_buf || append->pos < 0 ||
+                 append->pos >= g->buf_len)) {
+    set_error("score_landmarks: bad fused append (pos %d, buffer %d rows)", append->pos, g->buf_len);
+    return SKV_ERR_ARGUMENT;
+  }
   SelectWorkspace w = carve(g, workspace);
   // scale = 1/sqrt(128), the constant the reference hard-codes (kv_cache.py:1017)
   return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
-                           g->n_landmarks, w.T, 0.08838834764831845f, as_stream(stream));
+                           g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append, g->buf_len);
 }
 
 int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64_t *resident, int32_t *offsets,
@@ -408,26 +606,34 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   cudaStream_t st = as_stream(stream);
   const int BH = g->batch * g->kv_heads, G = g->q_groups, N = g->n_landmarks;
   SelectWorkspace w = carve(g, workspace);
-  const int smem = int(align_up(int64_t(N) * 2, 16));
+  const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
+#define SKV_SEL_LAUNCH(SV, IP)                                                                                    \
+  {                                                                                                              \
+    static int cur = 0;                                                                                          \
+    if (smem > cur) { cudaFuncSetAttribute(select_kernel<SV, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cur = smem; } \
+    select_kernel<SV, IP><<<dim3(kSelCluster, BH), kThreads, smem, st>>>(w.scores, w.pmax, w.psum, landmark_idx, \
+                                                                          resident, offsets, cnts, selected_out,   \
+                                                                          score_out, G, N, w.ldn, w.T, per);       \
+  }
 #define SKV_SEL(SV)                                                                                              \
   case SV: {                                                                                                     \
-    static int cur = 0;                                                                                          \
-    if (smem > cur) { cudaFuncSetAttribute(select_kernel<SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cur = smem; } \
-    select_kernel<SV><<<BH, kSelThreads, smem, st>>>(w.scores, w.pmax, w.psum, landmark_idx, resident, offsets,  \
-                                                     cnts, selected_out, score_out, G, N, w.T);                  \
+    constexpr int kThreads = SV > 256 ? SV : 256;                                                                \
+    const int smem = 2 * (kThreads / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                           \
+    if (g->table_mode) SKV_SEL_LAUNCH(SV, true) else SKV_SEL_LAUNCH(SV, false)                                   \
   } break;
   switch (g->select) {
     SKV_SEL(128) SKV_SEL(256) SKV_SEL(512) SKV_SEL(1024)
     default: return SKV_ERR_UNSUPPORTED;
   }
+#undef SKV_SEL_LAUNCH
 #undef SKV_SEL
   return launch_status("select_kernel");
 }
 
 int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, const int64_t *landmark_idx,
                       int64_t *resident, int32_t *offsets, int32_t *cnts, int64_t *selected_out,
-                      skv_bf16 *score_out, void *workspace, skv_stream_t stream) {
-  if (int rc = skv_score_landmarks(g, q, landmarks, workspace, stream)) return rc;
+                      skv_bf16 *score_out, void *workspace, const skv_append *append, skv_stream_t stream) {
+  if (int rc = skv_score_landmarks(g, q, landmarks, workspace, append, stream)) return rc;
   return skv_select_from_scores(g, landmark_idx, resident, offsets, cnts, selected_out, score_out, workspace, stream);
 }
 
@@ -441,7 +647,7 @@ int skv_batch_gemm_softmax(const skv_bf16 *A, const skv_bf16 *B, skv_bf16 *D, fl
   }
   cudaStream_t st = as_stream(stream);
   const int T = (n + 255) / 256;     // the reference's partial layout [batch, m, ceil(n/256)] (kv_cache.py:778-780)
-  int rc = launch_scores<32>(A, B, D, Norm, Sum, batch_count, m, n, T, alpha, st);
+  int rc = launch_scores<32>(A, B, D, Norm, Sum, batch_count, m, n, n, T, alpha, st);
   if (rc) return rc;
   dim3 grid((n + 2047) / 2048, batch_count);
   softmax_apply_kernel<<<grid, 256, 0, st>>>(D, Norm, Sum, Softmax, m, n, T);

@@ -10,9 +10,9 @@ Two public entry points:
   the device INSIDE the replayed graph, and the attention outputs are copied back to pinned host memory
   inside the same graph.  This is the call ``bench.py`` times as ``e2e``.
 
-The graph holds, per layer: append -> score -> select -> {V hit compaction + miss fetch on the copy stream
-|| K hit compaction + tcgen05 rebuild} -> split-K attention, i.e. 7 kernels, plus one counter-advance kernel
-per token.  The generation offset lives on the device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the
+The graph holds, per layer: score (+ fused append) -> select -> {V miss fetch on the copy stream || tcgen05 K
+rebuild} -> split-K attention, i.e. 5 kernels (7 with table_mode="reference": two hit compactions more), plus
+one counter-advance kernel per token.  The generation offset lives on the device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the
 same graph is valid for every token.
 """
 from __future__ import annotations
@@ -21,7 +21,6 @@ import torch
 
 from .kv_cache import ShadowKVCache_CPU
 
-KERNELS_PER_LAYER = 8     # append, score, select, compact(V), fetch(V), compact(K), rebuild(K), attention
 
 
 class DecodeStepGraph:
@@ -44,7 +43,9 @@ class DecodeStepGraph:
             self.out_h = torch.zeros(L, B, 1, Hq, D, dtype=dt).pin_memory()
         self.h2d_bytes = (self.q_d.numel() + self.k_d.numel() + self.v_d.numel()) * 2
         self.d2h_bytes = self.out_d.numel() * 2
-        self.launches_per_step = L * KERNELS_PER_LAYER       # kernels of libshadowkv_b200.so per token
+        # kernels of libshadowkv_b200.so per token: score(+append), select, fetch(V), rebuild(K), attention
+        # (+ the two hit compactions when the table keeps the reference's slot order)
+        self.launches_per_step = L * (5 if cache.table_mode == "inplace" else 7)
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0

@@ -40,9 +40,15 @@ class ShadowKVCache_CPU:
     K factors and landmarks on the GPU after ``H2D``.  Reference: models/kv_cache.py:509-1319."""
 
     def __init__(self, config, batch_size: int = 1, max_length: int = 32 * 1024, device: str = "cuda:0",
-                 dtype=torch.bfloat16, sparse_budget: int = 2048, chunk_size: int = 8, rank: int = 160) -> None:
+                 dtype=torch.bfloat16, sparse_budget: int = 2048, chunk_size: int = 8, rank: int = 160,
+                 table_mode: str = "inplace") -> None:
+        """table_mode: "inplace" (default; chunk-cache hits keep their slots, no compaction traffic) or
+        "reference" (slot order of reference map.cuh:754-796: hits compacted to the front)."""
         if dtype != torch.bfloat16:
             raise ValueError("the sm_100a kernels compute in bf16 only")
+        if table_mode not in ("inplace", "reference"):
+            raise ValueError("table_mode must be 'inplace' or 'reference'")
+        self.table_mode = table_mode
         self.config = config
         self.batch_size = batch_size
         self.max_length = max_length
@@ -156,6 +162,7 @@ class ShadowKVCache_CPU:
             g.rank = self.U.shape[-1]
             g.seq_len = self.U.shape[-2]
             g.buf_len, g.sparse_start = self.buf_len, self.sparse_start
+            g.table_mode = 1 if self.table_mode == "inplace" else 0
             self._geom = g
             self._sel_ws = torch.empty(lib.skv_select_workspace_bytes(C.byref(g)), dtype=torch.uint8,
                                        device=self.device)
@@ -310,9 +317,10 @@ class ShadowKVCache_CPU:
         if self.sparse_end + self.gen_offset > self.buf_len:
             raise RuntimeError("generation buffer overrun during graph replay")
 
-    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None):
+    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None, append=None):
         """Score landmarks, pick the top chunks and update the chunk table (kv_cache.py:983-1057).
-        Returns position_ids[layer] (chunk id resident in every sparse slot), updated in place."""
+        Returns position_ids[layer] (chunk id resident in every sparse slot), updated in place.
+        append: optional _lib.Append -- fuses update_kv_cache's row copy into the scoring launch."""
         self.incoming_q_len = query_states.shape[-2]
         if self.incoming_q_len != 1:
             raise ValueError("decode scores one query token per step")
@@ -323,7 +331,8 @@ class ShadowKVCache_CPU:
                                     self.offsets.data_ptr(), self.cnts.data_ptr(),
                                     selected_out.data_ptr() if selected_out is not None else 0,
                                     score_out.data_ptr() if score_out is not None else 0,
-                                    self._sel_ws.data_ptr(), _cs()), "select_chunks")
+                                    self._sel_ws.data_ptr(), C.byref(append) if append is not None else None, _cs()),
+              "select_chunks")
         return self.position_ids[layer_idx]
 
     def _view_len(self, layer_idx):
@@ -335,11 +344,12 @@ class ShadowKVCache_CPU:
         g = self._geometry()
         st = _cs()
         vb = self.v_cache_buffer[layer_idx]
-        check(lib.skv_compact_hits(C.byref(g), 0, vb.data_ptr(), self.offsets.data_ptr(), self.cnts.data_ptr(), st),
-              "compact_hits(V)")
+        if not g.table_mode:
+            check(lib.skv_compact_hits(C.byref(g), 0, vb.data_ptr(), self.offsets.data_ptr(), self.cnts.data_ptr(), st),
+                  "compact_hits(V)")
         vh = self.v_cache_cpu[layer_idx]
         check(lib.skv_fetch_misses(C.byref(g), vh.data_ptr(), vh.stride(1), vb.data_ptr(), self.offsets.data_ptr(),
-                                   self.cnts.data_ptr(), st), "fetch_misses")
+                                   self.cnts.data_ptr(), self.position_ids[layer_idx].data_ptr(), st), "fetch_misses")
         return vb[:, :, :self._view_len(layer_idx)]
 
     def get_key_cache(self, layer_idx, position_ids, rope_func, cos_sin_cache):
@@ -348,11 +358,13 @@ class ShadowKVCache_CPU:
         g = self._geometry(cos_sin_cache)
         st = _cs()
         kb = self.k_cache_buffer[layer_idx]
-        check(lib.skv_compact_hits(C.byref(g), kb.data_ptr(), 0, self.offsets.data_ptr(), self.cnts.data_ptr(), st),
-              "compact_hits(K)")
+        if not g.table_mode:
+            check(lib.skv_compact_hits(C.byref(g), kb.data_ptr(), 0, self.offsets.data_ptr(), self.cnts.data_ptr(), st),
+                  "compact_hits(K)")
         check(lib.skv_rebuild_keys(C.byref(g), self.U[layer_idx].data_ptr(), self.SV[layer_idx].data_ptr(),
                                    cos_sin_cache.data_ptr(), self.position_ids[layer_idx].data_ptr(),
-                                   self.cnts.data_ptr(), kb.data_ptr(), self.rebuild_impl, st), "rebuild_keys")
+                                   self.cnts.data_ptr(), self.offsets.data_ptr(), kb.data_ptr(), self.rebuild_impl, st),
+              "rebuild_keys")
         return kb[:, :, :self._view_len(layer_idx)]
 
     def attention(self, layer_idx, query_states, kv_len=None, out=None, device_counters=False):
@@ -382,8 +394,19 @@ class ShadowKVCache_CPU:
         With device_counters=True nothing depends on host-side counters, so the call sequence can be
         captured in a CUDA graph and replayed (see reset/advance_device_counters)."""
         self.incoming_q_len = 1
-        self.update_kv_cache(key_states, value_states, layer_idx, device_counters)
-        pid = self.get_retrieval_position_ids(layer_idx, query_states)
+        g = self._geometry(cos_sin_cache)
+        # (a2) fused into the scoring launch: same rows, same position as update_kv_cache
+        kc, vc = key_states.contiguous(), value_states.contiguous()
+        pos = self.sparse_end + (0 if device_counters else self.gen_offset)
+        if pos >= self.buf_len:
+            raise RuntimeError(f"generation buffer full ({self.buf_len - self.sparse_end} tokens)")
+        ap = _lib.Append(k_new=kc.data_ptr(), v_new=vc.data_ptr(), k_buf=self.k_cache_buffer[layer_idx].data_ptr(),
+                         v_buf=self.v_cache_buffer[layer_idx].data_ptr(),
+                         pos_dev=self.gen_dev.data_ptr() if device_counters else None, pos=pos)
+        pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
+        if layer_idx == self.num_layers - 1 and not device_counters:
+            self.kv_offset += 1
+            self.gen_offset += 1
         cur = torch.cuda.current_stream()
         self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream):
@@ -400,9 +423,9 @@ class ShadowKVCache(ShadowKVCache_CPU):
     every chunk is a miss and the V "fetch" reads the device-resident store."""
 
     def __init__(self, config, batch_size=1, max_length=32 * 1024, device="cuda:0", dtype=torch.bfloat16,
-                 sparse_budget=2048, chunk_size=8, rank=160) -> None:
+                 sparse_budget=2048, chunk_size=8, rank=160, table_mode="inplace") -> None:
         assert batch_size == 1, "ShadowKV class only supports batch_size=1, please use ShadowKV_CPU class for batch_size > 1"
-        super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank)
+        super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank, table_mode)
 
     def _outlier_chunks(self) -> int:
         return 48                                                          # kv_cache.py:206
@@ -417,9 +440,9 @@ class ShadowKVCache(ShadowKVCache_CPU):
         print(f"ShadowKV | sparse budget {self.sparse_budget} | chunk size {self.chunk_size} |rank {self.rank} "
               f"| cached {self.kv_offset} | local_chunk {self.local_chunk} | outlier_chunk {self.outlier_chunk}")
 
-    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None):
+    def get_retrieval_position_ids(self, layer_idx, query_states, selected_out=None, score_out=None, append=None):
         self.position_ids[layer_idx].fill_(-1)
-        chunk_ids = super().get_retrieval_position_ids(layer_idx, query_states, selected_out, score_out)
+        chunk_ids = super().get_retrieval_position_ids(layer_idx, query_states, selected_out, score_out, append)
         # token-level ids, as the reference returns for this class (kv_cache.py:440-445)
         ar = torch.arange(self.chunk_size, device=chunk_ids.device)
         return (chunk_ids.unsqueeze(-1) * self.chunk_size + ar).view(self.batch_size, self.num_key_value_heads, -1)

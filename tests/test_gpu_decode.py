@@ -11,14 +11,14 @@ from tests.tolerances import assert_close_bf16, assert_rope_rows_close
 pytestmark = pytest.mark.gpu
 
 
-def _build(cuda, model, B, prompt_len, budget, layers, rank=160):
+def _build(cuda, model, B, prompt_len, budget, layers, rank=160, table_mode="reference"):
     from shadowkv_b200.kv_cache import ShadowKVCache_CPU
     shape = synth.MODELS[model]
     cs = synth.cos_sin_table(prompt_len + 1024, 128, theta=shape.rope_theta, glm=shape.glm_rope)
     states = [synth.layer_state(shape, B, prompt_len, seed=1000 + l, rank=rank, sparse_budget=budget, cos_sin=cs)
               for l in range(layers)]
     cache = ShadowKVCache_CPU(shape.config(layers), batch_size=B, max_length=prompt_len, device=str(cuda),
-                              sparse_budget=budget, rank=rank)
+                              sparse_budget=budget, rank=rank, table_mode=table_mode)
     synth.install(cache, states)
     lay = states[0]["layout"]
     ora = [O.LayerState(landmarks=s["k_landmark"], landmark_idx=s["k_landmark_idx"], U=s["U"], SV=s["SV"],
@@ -131,3 +131,91 @@ def test_uncached_variant_token_ids(cuda):
     tok = cache.get_retrieval_position_ids(0, q.to(cuda))
     assert tok.shape == (1, 8, budget)
     assert torch.equal(tok.view(1, 8, -1, 8)[..., 0] // 8, cache.position_ids[0])
+
+
+@pytest.mark.parametrize("model,B,prompt_len,budget", [("llama-3.1-8b", 2, 8192, 1024), ("glm-4-9b-1m", 1, 8192, 1024),
+                                                       ("llama-3.1-8b", 1, 32768, 2048)])
+def test_inplace_table_matches_oracle_modulo_slot_order(cuda, model, B, prompt_len, budget):
+    """table_mode="inplace" (the default product path): chunk-cache hits keep their slots and the i-th missed
+    chunk (ascending id) takes the i-th freed slot.  Against the oracle (reference slot order) that must give:
+    the same resident SET and hit count, untouched hit slots, V bytes per slot == the host store's chunk,
+    K rows per slot == RoPE(U.SV) of the slot's chunk, and the same attention output (attention is invariant
+    under a permutation of the slots)."""
+    layers, steps = 2, 4
+    shape, cache, ora, geo, cs, lay = _build(cuda, model, B, prompt_len, budget, layers, table_mode="inplace")
+    d_cs = cs.to(cuda)
+    H, S, C = shape.num_key_value_heads, lay.select, 8
+    ss = lay.sparse_start
+    base = None
+    for step in range(steps):
+        geo.gen_offset = step
+        for l in range(layers):
+            q, kn, vn = synth.queries(shape, B, seed=50 * step + l, base=base, noise=0.35)
+            if base is None:
+                base = q
+            before = cache.position_ids[l].cpu().clone()
+            k_before = cache.k_cache_buffer[l].cpu().clone()
+            sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+            # same sequence as decode_layer, with the selection captured
+            cache.update_kv_cache(kn.to(cuda), vn.to(cuda), l)
+            pid = cache.get_retrieval_position_ids(l, q.to(cuda), selected_out=sel)
+            cache.get_value_cache(l, pid)
+            cache.get_key_cache(l, pid, None, d_cs)
+            out = cache.attention(l, q.to(cuda))
+            torch.cuda.synchronize()
+            want, info = O.decode_step(ora[l], geo, q, kn, vn, cs, selected_override=sel.cpu())
+            after = cache.position_ids[l].cpu()
+            offs = cache.offsets.cpu().view(B * H, S)
+            cnts = cache.cnts.cpu()
+            np.testing.assert_array_equal(cnts.numpy(), info["cnts"])
+            L_att = lay.sparse_end + step + 1
+            vbuf, kbuf = cache.v_cache_buffer[l].cpu(), cache.k_cache_buffer[l].cpu()
+            krope = O.rebuild_keys(ora[l].U, ora[l].SV, after, cs)                 # [B,H,S*C,D] in OUR slot order
+            for b in range(B):
+                for h in range(H):
+                    r = b * H + h
+                    new_set = set(sel[b, h].tolist())
+                    assert set(after[b, h].tolist()) == new_set == set(ora[l].resident[b, h].tolist())
+                    hit = torch.tensor([int(x) in new_set for x in before[b, h].tolist()])
+                    assert int(hit.sum()) == int(cnts[r])
+                    assert torch.equal(after[b, h][hit], before[b, h][hit]), "a hit moved"
+                    n_miss = S - int(cnts[r])
+                    miss_slots = offs[r, :n_miss].long()
+                    assert torch.equal(miss_slots, (~hit).nonzero().flatten()), "misses must fill the freed slots in order"
+                    assert torch.equal(after[b, h][miss_slots], after[b, h][miss_slots].sort().values), "misses ascend by id"
+                    # V: every slot holds exactly its chunk of the host store
+                    assert torch.equal(vbuf[b, h, ss:ss + S * C].reshape(S, -1), ora[l].v_host[b, h, after[b, h]])
+                    # K: hit slots keep their bytes, missed slots are rebuilt
+                    kk = kbuf[b, h, ss:ss + S * C].reshape(S, C, -1)
+                    assert torch.equal(kk[hit], k_before[b, h, ss:ss + S * C].reshape(S, C, -1)[hit])
+                    assert_rope_rows_close(kk[~hit], krope[b, h].reshape(S, C, -1)[~hit], glm=shape.glm_rope,
+                                           frac_exact=0.90, what="rebuilt K (in-place slots)")
+            # rows outside the sparse region: local / outliers untouched, appended token present
+            assert torch.equal(kbuf[:, :, :ss], ora[l].k_buf[:, :, :ss]) and torch.equal(vbuf[:, :, :ss], ora[l].v_buf[:, :, :ss])
+            assert torch.equal(kbuf[:, :, lay.sparse_end:L_att], ora[l].k_buf[:, :, lay.sparse_end:L_att])
+            assert_close_bf16(out, want, what=f"attention step {step} layer {l} (vs reference slot order)")
+            assert_close_bf16(out, O.attention(q, kbuf[:, :, :L_att], vbuf[:, :, :L_att]), max_abs=8e-3,
+                              what="attention over our own buffers")
+
+
+def test_decode_layer_fused_append_equals_update_kv_cache(cuda):
+    """decode_layer fuses the append into the scoring launch; the bytes must equal update_kv_cache's."""
+    shape, c1, _, _, cs, lay = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2, table_mode="inplace")
+    _, c2, _, _, _, _ = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2, table_mode="inplace")
+    d_cs = cs.to(cuda)
+    for step in range(3):
+        for l in range(2):
+            q, kn, vn = synth.queries(shape, 2, seed=11 * step + l)
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            o1 = c1.decode_layer(l, dq, dk, dv, d_cs)
+            c2.update_kv_cache(dk, dv, l)
+            pid = c2.get_retrieval_position_ids(l, dq)
+            c2.get_value_cache(l, pid)
+            c2.get_key_cache(l, pid, None, d_cs)
+            o2 = c2.attention(l, dq)
+            torch.cuda.synchronize()
+            assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l])
+            assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l])
+            assert torch.equal(c1.position_ids[l], c2.position_ids[l])
+            assert torch.equal(o1, o2)
+        assert c1.gen_offset == c2.gen_offset == step + 1

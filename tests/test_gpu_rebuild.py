@@ -40,7 +40,7 @@ def test_rebuild_keys(cuda, impl, glm, R, S):
     geom = _lib.Geom(batch=B, kv_heads=H, q_groups=4, head_dim=128, chunk=8, select=S, n_landmarks=L // 8, rank=R,
                      seq_len=L, buf_len=Lbuf, sparse_start=ss, rope_glm=int(glm))
     d = [t.to(cuda) for t in (U, SV, cs, ids, cnts, kbuf)]
-    _lib.check(_lib.lib.skv_rebuild_keys(C.byref(geom), *[t.data_ptr() for t in d], impl,
+    _lib.check(_lib.lib.skv_rebuild_keys(C.byref(geom), *[t.data_ptr() for t in d[:5]], 0, d[5].data_ptr(), impl,
                                          torch.cuda.current_stream().cuda_stream), "rebuild")
     torch.cuda.synchronize()
     got = d[5].cpu()
@@ -65,7 +65,7 @@ def test_tcgen05_equals_simt(cuda):
     for impl in (0, 1):
         kbuf = torch.zeros(B, H, 2592, 128, dtype=torch.bfloat16, device=cuda)
         d = [t.to(cuda) for t in (U, SV, cs, ids, cnts)]
-        _lib.check(_lib.lib.skv_rebuild_keys(C.byref(geom), *[t.data_ptr() for t in d], kbuf.data_ptr(), impl,
+        _lib.check(_lib.lib.skv_rebuild_keys(C.byref(geom), *[t.data_ptr() for t in d], 0, kbuf.data_ptr(), impl,
                                              torch.cuda.current_stream().cuda_stream), "rebuild")
         torch.cuda.synchronize()
         outs.append(kbuf.cpu())

@@ -59,7 +59,7 @@ def _select(cuda, shape, N, S, seed, glm=False):
     d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)     # named: a temporary would be freed before the launch
     _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(),
                                           d_idx.data_ptr(), d_res.data_ptr(), off.data_ptr(), cnt.data_ptr(),
-                                          sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                          sel.data_ptr(), score.data_ptr(), ws.data_ptr(), None,
                                           torch.cuda.current_stream().cuda_stream), "select")
     torch.cuda.synchronize()
     return q, lm, idx, resident, d_res.cpu(), off.cpu().view(B * H, S), cnt.cpu(), sel.cpu(), score.cpu()
@@ -114,7 +114,7 @@ def test_select_massive_ties(cuda):
     d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)
     _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(),
                                           d_idx.data_ptr(), res.data_ptr(), off.data_ptr(), cnt.data_ptr(), 0, 0,
-                                          ws.data_ptr(), torch.cuda.current_stream().cuda_stream), "select")
+                                          ws.data_ptr(), None, torch.cuda.current_stream().cuda_stream), "select")
     torch.cuda.synchronize()
     assert (cnt.cpu() == 0).all()
     assert torch.equal(res.cpu(), (torch.arange(S) * 3).expand(B, H, S))
