@@ -46,19 +46,14 @@ __global__ void __launch_bounds__(kAttnMaxWarps * 32, 1)
   const int row_id = (b * p.H + h) * p.ngz + gz;
   SKV_STAMP(row_id == 0 ? split : 999, 0);
 
-  float qf[kAttnGT][8];
+  // q stays packed (4 registers per head); it is unpacked after the K/V loads of an iteration are in flight,
+  // so the first K/V round trip does not wait behind the q round trip
+  int4 qraw[kAttnGT];
 #pragma unroll
-  for (int g = 0; g < kAttnGT; ++g) {
-    if (g0 + g < p.G) {
-      const int4 w = *reinterpret_cast<const int4 *>(p.q + (size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + sub * 8);
-      const uint32_t u[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { qf[g][2 * e] = bf16_lo(u[e]) * p.scale_log2; qf[g][2 * e + 1] = bf16_hi(u[e]) * p.scale_log2; }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) qf[g][e] = 0.f;
-    }
-  }
+  for (int g = 0; g < kAttnGT; ++g)
+    qraw[g] = (g0 + g < p.G)
+                  ? *reinterpret_cast<const int4 *>(p.q + (size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + sub * 8)
+                  : make_int4(0, 0, 0, 0);
 
   const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
   SKV_STAMP(row_id == 0 ? split : 999, 1);
@@ -85,6 +80,13 @@ __global__ void __launch_bounds__(kAttnMaxWarps * 32, 1)
       const bool ok = key < k_end;
       kl[it] = ok ? ld_stream(kbase + size_t(key) * row_i4 + sub) : make_int4(0, 0, 0, 0);
       vl[it] = ok ? ld_stream(vbase + size_t(key) * row_i4 + sub) : make_int4(0, 0, 0, 0);
+    }
+    float qf[kAttnGT][8];
+#pragma unroll
+    for (int g = 0; g < kAttnGT; ++g) {
+      const uint32_t u[4] = {(uint32_t)qraw[g].x, (uint32_t)qraw[g].y, (uint32_t)qraw[g].z, (uint32_t)qraw[g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { qf[g][2 * e] = bf16_lo(u[e]) * p.scale_log2; qf[g][2 * e + 1] = bf16_hi(u[e]) * p.scale_log2; }
     }
     float v[8][kAttnGT];
 #pragma unroll
@@ -274,25 +276,32 @@ __global__ void __launch_bounds__(kAttnMaxWarps * 32, 1)
   }
   bar256();
   SKV_STAMP(row_id == 0 ? split : 999, 6);
+  {
+    const int g = threadIdx.x >> 6, c2 = threadIdx.x & 63;         // 256 threads = 4 heads x 64 dim pairs
+    if (g0 + g < p.G) {
+      const float *col = ro + size_t(g) * kHeadDim + c2 * 2;
+      const int ns = p.num_splits;
+      float ox = 0.f, oy = 0.f;
+      int sidx = 0;
+      for (; sidx + 8 <= ns; sidx += 8) {                          // eight independent 8-byte loads in flight
+        float2 v[8];
 #pragma unroll
-  for (int gg = 0; gg < kAttnGT / 2; ++gg) {
-    const int g = gh * (kAttnGT / 2) + gg;
-    if (g0 + g >= p.G) break;
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    const float *col = ro + size_t(g) * kHeadDim + d;
-    const int ns = p.num_splits;
-    int sidx = 0;
-    for (; sidx + 4 <= ns; sidx += 4) {            // four independent loads in flight
-      const float v0 = __ldcg(col + size_t(sidx) * kAttnGT * kHeadDim);
-      const float v1 = __ldcg(col + size_t(sidx + 1) * kAttnGT * kHeadDim);
-      const float v2 = __ldcg(col + size_t(sidx + 2) * kAttnGT * kHeadDim);
-      const float v3 = __ldcg(col + size_t(sidx + 3) * kAttnGT * kHeadDim);
-      o0 = fmaf(v0, s_f[sidx][g], o0); o1 = fmaf(v1, s_f[sidx + 1][g], o1);
-      o2 = fmaf(v2, s_f[sidx + 2][g], o2); o3 = fmaf(v3, s_f[sidx + 3][g], o3);
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(reinterpret_cast<const float2 *>(col + size_t(sidx + k) * kAttnGT * kHeadDim));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ox = fmaf(v[k].x, s_f[sidx + k][g], ox); oy = fmaf(v[k].y, s_f[sidx + k][g], oy); }
+      }
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = sidx + k < ns ? __ldcg(reinterpret_cast<const float2 *>(col + size_t(sidx + k) * kAttnGT * kHeadDim))
+                             : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (sidx + k < ns) { ox = fmaf(v[k].x, s_f[sidx + k][g], ox); oy = fmaf(v[k].y, s_f[sidx + k][g], oy); }
+      const float inv = 1.0f / s_L[g];
+      const __nv_bfloat162 o2 = __floats2bfloat162_rn(ox * inv, oy * inv);
+      *reinterpret_cast<__nv_bfloat162 *>(p.out + (size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + c2 * 2) = o2;
     }
-    for (; sidx < ns; ++sidx) o0 = fmaf(__ldcg(col + size_t(sidx) * kAttnGT * kHeadDim), s_f[sidx][g], o0);
-    const float o = (o0 + o1) + (o2 + o3);
-    p.out[(size_t(b) * p.H * p.G + size_t(h) * p.G + g0 + g) * kHeadDim + d] = f32_to_bf16_bits(o / s_L[g]);
   }
   SKV_STAMP(row_id == 0 ? split : 999, 7);
 }

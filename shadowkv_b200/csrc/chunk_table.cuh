@@ -69,12 +69,13 @@ __device__ __forceinline__ void chunk_table_update(int tid, int old_id, int new_
   }
   __syncthreads();
   const int keep = (found >= 0 && sm.slot_of[found] == tid) ? 1 : 0;   // hit, kept at its lowest slot
-  int cnt;
-  const int hpos = block_excl_scan(keep, sm.warp_tot, cnt);
   const int my_sorted = active ? sm.sorted_new[tid] : 0;
   const int miss = (active && sm.slot_of[tid] == INT_MAX) ? 1 : 0;
-  int nmiss;
-  const int mpos = block_excl_scan(miss, sm.warp_tot, nmiss);
+  // one scan for both flags (S <= 1024 fits 16 bits): low half = hits before me, high half = misses before me
+  int packed_total;
+  const int packed = block_excl_scan(keep | (miss << 16), sm.warp_tot, packed_total);
+  const int hpos = packed & 0xFFFF, mpos = packed >> 16;
+  const int cnt = packed_total & 0xFFFF;
   if (!kInPlace) {
     if (keep) {
       g_resident[hpos] = static_cast<int64_t>(old_id);
@@ -88,8 +89,7 @@ __device__ __forceinline__ void chunk_table_update(int tid, int old_id, int new_
     // In-place table (B200 path): hits stay in their slots, so neither K nor V moves for them; the i-th
     // missed chunk (ascending id) takes the i-th freed slot (ascending slot).  offsets[i] = that slot.
     const int freed = (active && !keep) ? 1 : 0;
-    int nfree;
-    const int fpos = block_excl_scan(freed, sm.warp_tot, nfree);
+    const int fpos = tid - hpos;           // freed slots before me = slots before me that are not kept hits
     __syncthreads();                       // slot_of is dead from here on: reuse it as the free-slot list
     if (freed) sm.slot_of[fpos] = tid;
     __syncthreads();

@@ -30,6 +30,10 @@ static __device__ long long g_skv_trace[8192];
   do {                                                                                   \
     if (threadIdx.x == 0 && (cta) < 256) g_skv_trace[(cta) * 32 + (slot)] = clock64();   \
   } while (0)
+#define SKV_STAMP_ANY(cta, slot)                                                         \
+  do {                                                                                   \
+    if ((cta) < 256) g_skv_trace[(cta) * 32 + (slot)] = clock64();                       \
+  } while (0)
 #define SKV_TRACE_READER(unit)                                                           \
   extern "C" int skv_debug_read_trace_##unit(long long *host_out, int n) {               \
     cudaDeviceSynchronize();                                                             \
@@ -37,6 +41,7 @@ static __device__ long long g_skv_trace[8192];
   }
 #else
 #define SKV_STAMP(cta, slot) do { } while (0)
+#define SKV_STAMP_ANY(cta, slot) do { } while (0)
 #define SKV_TRACE_READER(unit)
 #endif
 

@@ -4,104 +4,16 @@
 // per chunk = exactly one 128B-swizzle atom per 64-column slab) and the SV panel are brought in by TMA, the
 // 128x128xR product runs on tcgen05 with the fp32 accumulator in TMEM, and the epilogue rounds to bf16,
 // applies the rotary embedding in bf16 at token position id*8+r and writes straight into the K buffer.
-#include <cuda.h>
-
 #include <map>
 #include <mutex>
 #include <tuple>
 
-#include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace skv {
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers (sm_100a)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbarrier_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarrier_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbarrier_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbarrier_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_addr(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_alloc(uint32_t *smem_slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_slot)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
-               : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = tile row)
-__device__ __forceinline__ void tcgen05_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte-swizzled shared-memory operand descriptor (sm_100 UMMA): start>>4 | LBO=1 (unused for
-// swizzled K-major) | SBO = 1024 B between 8-row groups | version 1 | layout SWIZZLE_128B (2).
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= uint64_t((saddr & 0x3FFFF) >> 4);
-  d |= uint64_t(1) << 16;
-  d |= uint64_t(1024 >> 4) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
 // bf16 x bf16 -> f32, A and B K-major, M=128, N=128
-constexpr uint32_t kIdescBf16M128N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescBf16M128N128 = umma_idesc_bf16_m128(128);
 
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileRows = 128;                 // 16 chunks
@@ -364,19 +276,20 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 row-major [rows, cols] tensor, box {64 cols, box_rows}, 128-byte swizzle, zero OOB fill.
-static int make_map(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  typedef std::tuple<const void *, uint64_t, uint64_t, uint32_t> Key;
+int make_tensor_map_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols) {
+  typedef std::tuple<const void *, uint64_t, uint64_t, uint32_t, uint32_t> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
-  Key key(base, rows, cols, box_rows);
+  Key key(base, rows, cols, box_rows, box_cols);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return SKV_OK; }
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SKV_ERR_DRIVER; }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {kSlabCols, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
@@ -401,9 +314,9 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
     return launch_status("rebuild_simt_kernel");
   }
   CUtensorMap map_u, map_sv;
-  int rc = make_map(&map_u, U, uint64_t(B) * p.L, p.R, kChunkTokens);
+  int rc = make_tensor_map_2d(&map_u, U, uint64_t(B) * p.L, p.R, kChunkTokens, kSlabCols);
   if (rc) return rc;
-  rc = make_map(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim);
+  rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim, kSlabCols);
   if (rc) return rc;
   const int smem = kMaxSlabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
   static bool attr = false;

@@ -18,6 +18,11 @@ namespace cg = cooperative_groups;
 
 namespace skv {
 
+// score_mma.cu: TMA + tcgen05 scoring (product path)
+int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
+                          int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
+                          int64_t buf_rows);
+
 constexpr int kScoreThreads = 256;   // 8 warps
 
 // One warp handles kRowsPerWarp landmarks in groups of 16 (8 x 512 B loads in flight per lane group).
@@ -298,7 +303,6 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   __shared__ int s_parts2[kSelCluster][256];
   __shared__ int s_tot[256];
   __shared__ int s_res[4];
-  __shared__ int s_cnts[kSelCluster][2];        // (greater, equal) counts of all 8 CTAs
   __shared__ int s_wa[kWarps + 1], s_wb[kWarps + 1];
   __shared__ int s_new[S];                      // CTA 0: selected chunk ids in ascending landmark order
   __shared__ int s_sorted[S], s_slot[S], s_warp[33];
@@ -432,38 +436,27 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   const int need_eq = S - (above1 + s_res[3]);      // how many keys equal to thr are taken (>= 1)
   SKV_STAMP(bh == 0 ? rank : 999, 7);
 
-  // 3. (greater, equal) counts of this CTA's slice, pushed to every CTA of the cluster
+  // 3. (greater, equal) counts of the lower-ranked CTAs: every CTA already holds all eight partial
+  //    histograms, so no further exchange is needed
+  int gt_before = 0, eq_before = 0;
   {
-    int gt = 0, eq = 0;
-    for (int base = 0; base < count; base += kThreads * 8) {
-      const int off = base + tid * 8;
-      if (off < count) {
-        const int4 w = *reinterpret_cast<const int4 *>(keys + off);
-        const uint32_t kw[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+    const int b2 = s_res[2];
+    int a = 0, e = 0;
+    if (tid < 256) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;     // padded tail keys are 0 < thr
-          gt += k > thr; eq += k == thr;
+      for (int r = 0; r < kSelCluster; ++r) {
+        if (r < rank) {
+          if (tid > b1) a += s_parts1[r][tid];
+          if (tid > b2) a += s_parts2[r][tid];
+          if (tid == b2) e += s_parts2[r][tid];
         }
       }
     }
-    gt = warp_sum_int(gt); eq = warp_sum_int(eq);
-    if (lane == 0) { s_wa[warp] = gt; s_wb[warp] = eq; }
+    a = warp_sum_int(a); e = warp_sum_int(e);
+    if (lane == 0) { s_wa[warp] = a; s_wb[warp] = e; }
     __syncthreads();
-    if (warp == 0) {
-      int a = lane < kWarps ? s_wa[lane] : 0, e = lane < kWarps ? s_wb[lane] : 0;
-      a = warp_sum_int(a); e = warp_sum_int(e);
-      if (lane < kSelCluster) {
-        int *dst = cluster.map_shared_rank(&s_cnts[rank][0], lane);
-        dst[0] = a; dst[1] = e;
-      }
-    }
+    for (int w = 0; w < (kWarps < 8 ? kWarps : 8); ++w) { gt_before += s_wa[w]; eq_before += s_wb[w]; }
   }
-  SKV_STAMP(bh == 0 ? rank : 999, 8);
-  cluster.sync();
-  SKV_STAMP(bh == 0 ? rank : 999, 9);
-  int gt_before = 0, eq_before = 0;
-  for (int r = 0; r < rank; ++r) { gt_before += s_cnts[r][0]; eq_before += s_cnts[r][1]; }
   SKV_STAMP(bh == 0 ? rank : 999, 10);
 
   // 4. ordered emission (ascending landmark index): thread t owns 8 consecutive landmarks per round, so the
@@ -592,6 +585,11 @@ int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
   }
   SelectWorkspace w = carve(g, workspace);
   // scale = 1/sqrt(128), the constant the reference hard-codes (kv_cache.py:1017)
+  static const bool simt = [] { const char *e = getenv("SKV_SCORE_IMPL"); return e && e[0] == '1'; }();
+  if (!simt)   // product path: TMA ring + tcgen05 (score_mma.cu); SKV_SCORE_IMPL=1 selects the SIMT cross-check
+    return launch_scores_tcgen05(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
+                                 g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append,
+                                 g->buf_len);
   return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                            g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append, g->buf_len);
 }

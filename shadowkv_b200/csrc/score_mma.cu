@@ -1,0 +1,230 @@
+// Landmark scoring, product path: a TMA-fed shared-memory ring streams the landmark matrix of one (b,h) once
+// (HBM bound: N*D*2 bytes), the G <= 16 query heads are the N operand of a 128 x 16 x 128 tcgen05 MMA per
+// 128-landmark tile (fp32 accumulators in TMEM, double buffered), and four epilogue warps turn each tile into
+// bf16(alpha * q.k) scores plus the per-tile softmax partials that select_kernel consumes.
+//
+// Replaces the reference's batch_gemm_softmax GEMM + partial-softmax launch (kernels/batch_gemm_softmax.cu:229-293,
+// CUTLASS 2.x Sm80 mma.sync, tile 32x256x32) on this path; same rounding points: fp32 accumulate, * alpha,
+// round to bf16, max / sum-of-exp over the ROUNDED values (epilogue_visitor_with_softmax).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31 = landmark rows of the tile).  Two CTAs fit per SM (3 x 32 KiB ring).
+#include "sm100_ptx.cuh"
+
+namespace skv {
+
+constexpr int kSmTileRows = 128;                 // landmarks per tile = UMMA M
+constexpr int kSmStages = 3;                     // 3 x 32 KiB ring per CTA
+constexpr int kSmSlabBytes = kSmTileRows * 128;  // one 64-column (128 B) swizzle slab of a tile
+constexpr int kSmTileBytes = 2 * kSmSlabBytes;   // 32 KiB
+constexpr int kSmQSlabBytes = 16 * 128;          // B operand: 16 rows (heads, zero padded) x 64 columns
+constexpr int kSmThreads = 192;
+constexpr int kSmAccCols = 16;                   // fp32 accumulator columns per tile (UMMA N)
+
+struct ScoreMmaParams {
+  const skv_bf16 *q;        // [BH, G, 128]
+  skv_bf16 *scores;         // [BH, G, ldn]
+  float *part_max, *part_sum;   // [BH, G, T]
+  int G, N, ldn, T, ctas_per_row;
+  float alpha;
+  skv_append ap;
+  int64_t buf_rows;
+};
+
+__global__ void __launch_bounds__(kSmThreads, 2)
+    score_tcgen05_kernel(const __grid_constant__ CUtensorMap map_lm, ScoreMmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem;                                          // kSmStages x 32 KiB
+  unsigned char *sQ = smem + kSmStages * kSmTileBytes;               // 2 slabs x 2 KiB
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sQ + 2 * kSmQSlabBytes);
+  uint64_t *empty_bar = full_bar + kSmStages;
+  uint64_t *acc_full = empty_bar + kSmStages;                        // [2]
+  uint64_t *acc_empty = acc_full + 2;                                // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  float *s_red = reinterpret_cast<float *>(tmem_slot + 2);           // [2 acc][4 warps][16 heads][2]
+
+  const int bh = blockIdx.y, cx = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_my = (p.T - cx + p.ctas_per_row - 1) / p.ctas_per_row;   // tiles cx, cx + cpr, ... < T
+  const int tr = bh == 0 ? cx : 999;
+  SKV_STAMP(tr, 0);
+
+  // fused append (a2): the first CTA of every (b,h) writes the new token's K and V rows
+  if (p.ap.k_new && cx == 0 && warp == 2) {
+    const int64_t pos = p.ap.pos + (p.ap.pos_dev ? *p.ap.pos_dev : 0);
+    if (pos < p.buf_rows) {
+      const int c = lane & 15;
+      const int4 *src = reinterpret_cast<const int4 *>(lane < 16 ? p.ap.k_new : p.ap.v_new) + size_t(bh) * 16 + c;
+      int4 *dst = reinterpret_cast<int4 *>(lane < 16 ? p.ap.k_buf : p.ap.v_buf) + (size_t(bh) * p.buf_rows + pos) * 16 + c;
+      *dst = *src;
+    }
+  }
+
+  // B operand: the G query rows of this (b,h), zero padded to 16, written in the 128-byte-swizzled K-major
+  // layout the MMA descriptor expects (chunk c of row r lands at chunk c ^ (r & 7) of its 128-byte line)
+  for (int i = threadIdx.x; i < 2 * 16 * 8; i += kSmThreads) {
+    const int slab = i >> 7, r = (i >> 3) & 15, c = i & 7;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (r < p.G) v = *reinterpret_cast<const int4 *>(p.q + (size_t(bh) * p.G + r) * kHeadDim + slab * 64 + c * 8);
+    *reinterpret_cast<int4 *>(sQ + slab * kSmQSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSmStages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the ring is empty: fill it right away, the rest of the CTA is still setting up
+    const uint64_t pol = l2_policy_evict_first();            // landmarks are read once per step
+    for (int i = 0; i < kSmStages && i < n_my; ++i) {
+      const int row0 = bh * p.N + (cx + i * p.ctas_per_row) * kSmTileRows;
+      mbarrier_expect_tx(&full_bar[i], kSmTileBytes);
+      tma_load_2d_hint(sA + i * kSmTileBytes, &map_lm, 0, row0, &full_bar[i], pol);
+      tma_load_2d_hint(sA + i * kSmTileBytes + kSmSlabBytes, &map_lm, 64, row0, &full_bar[i], pol);
+      if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
+    }
+  }
+  if (warp == 1) tcgen05_alloc(tmem_slot, 32);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  SKV_STAMP(tr, 1);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      for (int i = kSmStages; i < n_my; ++i) {               // the first kSmStages tiles were issued during set-up
+        const int stage = i % kSmStages, ph = (i / kSmStages) & 1;
+        const int tile = cx + i * p.ctas_per_row;
+        mbarrier_wait(&empty_bar[stage], ph ^ 1);
+        mbarrier_expect_tx(&full_bar[stage], kSmTileBytes);
+        const int row0 = bh * p.N + tile * kSmTileRows;      // rows past N belong to the next (b,h) or are zero
+        tma_load_2d_hint(sA + stage * kSmTileBytes, &map_lm, 0, row0, &full_bar[stage], pol);
+        tma_load_2d_hint(sA + stage * kSmTileBytes + kSmSlabBytes, &map_lm, 64, row0, &full_bar[stage], pol);
+        if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(kSmAccCols);
+      const uint64_t db0 = umma_desc_k_sw128(smem_addr(sQ)), db1 = umma_desc_k_sw128(smem_addr(sQ + kSmQSlabBytes));
+      for (int i = 0; i < n_my; ++i) {
+        const int stage = i % kSmStages, ph = (i / kSmStages) & 1;
+        const int acc = i & 1, aph = (i >> 1) & 1;
+        mbarrier_wait(&acc_empty[acc], aph ^ 1);
+        mbarrier_wait(&full_bar[stage], ph);
+        if (i < 4) SKV_STAMP_ANY(tr, 6 + i);
+        tcgen05_fence_after();
+        const uint64_t da0 = umma_desc_k_sw128(smem_addr(sA + stage * kSmTileBytes));
+        const uint64_t da1 = umma_desc_k_sw128(smem_addr(sA + stage * kSmTileBytes + kSmSlabBytes));
+        const uint32_t d = tmem_base + acc * kSmAccCols;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tcgen05_mma_bf16(d, da0 + uint64_t(kk * 2), db0 + uint64_t(kk * 2), idesc, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tcgen05_mma_bf16(d, da1 + uint64_t(kk * 2), db1 + uint64_t(kk * 2), idesc, 1);
+        tcgen05_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+        tcgen05_commit(&acc_full[acc]);                      // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: thread = landmark row of the tile =====
+    const int lg = warp & 3;                                 // TMEM lane group this warp may read
+    const int ew = warp - 2;                                 // 0..3
+    for (int i = 0; i < n_my; ++i) {
+      const int acc = i & 1, aph = (i >> 1) & 1;
+      const int tile = cx + i * p.ctas_per_row;
+      mbarrier_wait(&acc_full[acc], aph);
+      if (i < 4 && threadIdx.x == 64) SKV_STAMP_ANY(tr, 10 + i);
+      tcgen05_fence_after();
+      uint32_t r[16];
+      tcgen05_ld16(tmem_base + (uint32_t(lg * 32) << 16) + acc * kSmAccCols, r);
+      tcgen05_wait_ld();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[acc]);       // accumulator may be overwritten
+      const int n = tile * kSmTileRows + lg * 32 + lane;
+      const bool valid = n < p.N;
+      float *red = s_red + (acc * 4 + ew) * 32;
+      // four heads at a time so the shuffle chains of the reductions overlap
+#pragma unroll
+      for (int g0 = 0; g0 < 16; g0 += 4) {
+        if (g0 < p.G) {                                      // warp uniform
+          float x[4], m[4], e[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint16_t bits = f32_to_bf16_bits(__uint_as_float(r[g0 + k]) * p.alpha);
+            const bool on = valid && g0 + k < p.G;
+            if (on) p.scores[(size_t(bh) * p.G + g0 + k) * p.ldn + n] = bits;
+            x[k] = on ? bf16_bits_to_f32(bits) : -INFINITY;
+            m[k] = x[k];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) e[k] = (x[k] == -INFINITY) ? 0.f : expf(x[k] - m[k]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] += __shfl_xor_sync(0xffffffffu, e[k], o);
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { red[(g0 + k) * 2] = m[k]; red[(g0 + k) * 2 + 1] = e[k]; }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps
+      if (ew == 0 && lane < p.G) {
+        const float *rb = s_red + acc * 4 * 32 + lane * 2;
+        float m = fmaxf(fmaxf(rb[0], rb[32]), fmaxf(rb[64], rb[96]));
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float mw = rb[w * 32];
+          sum += (mw == -INFINITY) ? 0.f : rb[w * 32 + 1] * expf(mw - m);
+        }
+        p.part_max[(size_t(bh) * p.G + lane) * p.T + tile] = m;
+        p.part_sum[(size_t(bh) * p.G + lane) * p.T + tile] = sum;
+      }
+      // s_red is double buffered with the accumulator, and tile i+2 cannot reach this point before every
+      // warp passed the barrier of tile i+1, so no second barrier is needed
+    }
+  }
+  if (threadIdx.x == 64) SKV_STAMP_ANY(tr, 14);
+  tcgen05_fence_before();
+  __syncthreads();
+  SKV_STAMP(tr, 15);
+  if (warp == 1) tcgen05_dealloc(tmem_base, 32);
+}
+
+int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
+                          int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
+                          int64_t buf_rows) {
+  CUtensorMap map;
+  int rc = make_tensor_map_2d(&map, lm, uint64_t(BH) * N, kHeadDim, kSmTileRows, 64);
+  if (rc) return rc;
+  ScoreMmaParams p{};
+  p.q = q; p.scores = scores; p.part_max = pmax; p.part_sum = psum;
+  p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
+  if (append) p.ap = *append;
+  // two CTAs per SM; every CTA of a row strides over that row's tiles
+  int cpr = (2 * kNumSMs + BH - 1) / BH;
+  if (cpr > T) cpr = T;
+  if (cpr < 1) cpr = 1;
+  p.ctas_per_row = cpr;
+  const int smem = kSmStages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmStages + 4) * 8 + 8 + 2 * 4 * 32 * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  score_tcgen05_kernel<<<dim3(cpr, BH), kSmThreads, smem, st>>>(map, p);
+  return launch_status("score_tcgen05_kernel");
+}
+
+}  // namespace skv
+
+SKV_TRACE_READER(score_mma)

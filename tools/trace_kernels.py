@@ -54,6 +54,9 @@ def main():
     show("select_kernel (bh 0, ranks 0..7)", read("score", 8, 15),
          ["start", "stats", "keys+h1", "csync1", "thr1", "h2", "csync2", "thr2", "counts", "csync3", "before", "emit",
           "csync4", "ids", "table"])
+    show("score_tcgen05_kernel (bh 0, first CTAs)", read("score_mma", 6, 16),
+         ["start", "setup", "tma0", "tma1", "tma2", "tma3", "full0", "full1", "full2", "full3", "acc0", "acc1", "acc2",
+          "acc3", "epi_end", "end"])
     show("attention_decode_kernel (row 0, splits)", read("attention", 18, 8),
          ["start", "q", "loop", "partials", "fence+atomic", "last:fence", "weights", "end"])
 
