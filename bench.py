@@ -58,6 +58,9 @@ def parse_args():
                     help="per-token query innovation; 0.28 gives ~60%% chunk-cache hits (reference test default)")
     ap.add_argument("--table-mode", default="inplace", choices=["inplace", "reference"],
                     help="chunk-table slot policy: in place (no hit compaction) or the reference's slot order")
+    ap.add_argument("--shard", default="batch", choices=["batch", "heads"],
+                    help="N > 1: shard the batch (weak scaling, no collective) or split the kv heads of the same "
+                         "sequences over the ranks (strong scaling, one all-gather of the attention output per layer)")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -203,18 +206,20 @@ def main():
     return run_ours(args, rank, world, local_rank, n_gpus)
 
 
-def workload_config(args, shape, L, *, hit_rate, n_gpus):
+def workload_config(args, shape, L, *, hit_rate, n_gpus, heads_mode=False):
     from shadowkv_b200 import synth
     lay = synth.layout(args.ctx, args.budget)
     return {"workload": f"{shape.name} random-init decode state, {args.ctx} ctx ('122K', test/e2e.py shape), "
                         f"batch {args.batch}/GPU, sparse budget {args.budget}, rank {args.rank}, chunk 8, {L} layers",
             "scope": "sparse-KV decode step of every layer; dense QKV/o_proj/MLP not included (SURVEY.md 8 f2)",
-            "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "ctx": args.ctx, "layers": L,
+            "batch_per_gpu": args.batch, "global_batch": args.batch * (1 if heads_mode else n_gpus), "ctx": args.ctx,
+            "layers": L,
             "landmarks": lay.n_landmarks, "select_chunks": lay.select, "kv_rows_attended": lay.sparse_end + 1,
             "chunk_cache_hit_rate": round(hit_rate, 4), "query_noise": args.noise, "table_mode": args.table_mode,
             "l2_policy": "inputs larger than L2: per token the step streams every layer's landmarks, "
                          f"{L} x {lay.n_landmarks * shape.num_key_value_heads * 256 / 1e6:.1f} MB per sequence",
-            "parallelism": f"batch-sharded x{n_gpus}, no collective"}
+            "parallelism": (f"kv heads split x{n_gpus}, one all-gather of the attention output per layer" if heads_mode
+                            else f"batch-sharded x{n_gpus}, no collective")}
 
 
 def run_ours(args, rank, world, local_rank, n_gpus):
@@ -232,7 +237,15 @@ def run_ours(args, rank, world, local_rank, n_gpus):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    shape = synth.MODELS[args.model]
+    full_shape = synth.MODELS[args.model]
+    shape = full_shape
+    heads_mode = args.shard == "heads" and world > 1
+    if heads_mode:        # this rank's slice of the kv heads (and their query heads); same sequences on every rank
+        import dataclasses
+        from shadowkv_b200 import parallel
+        cfg = parallel.head_shard_config(full_shape.config(1), world, rank)
+        shape = dataclasses.replace(full_shape, num_key_value_heads=cfg.num_key_value_heads,
+                                    num_attention_heads=cfg.num_attention_heads, hidden_size=cfg.hidden_size)
     L = args.layers or shape.num_hidden_layers
     B = args.batch
     H, Hq, D = shape.num_key_value_heads, shape.num_attention_heads, 128
@@ -280,7 +293,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
             torch.cuda.synchronize()
 
     # ---- value: device-resident inputs ------------------------------------------------------------------------
-    run_d = DecodeStepGraph(cache, cs, host_io=False).capture(warmup=1)
+    run_d = DecodeStepGraph(cache, cs, host_io=False, gather_heads=heads_mode).capture(warmup=1)
     run_d.rewind(0)
     for t in range(args.warmup):
         run_d.step_device(*dev_inputs[t])
@@ -306,7 +319,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
     hit_rate = float(hits.sum().item()) / (args.steps * L * B * H * S)
 
     # ---- e2e: host tensors through the public API -----------------------------------------------------------------
-    run_h = DecodeStepGraph(cache, cs, host_io=True).capture(warmup=0)
+    run_h = DecodeStepGraph(cache, cs, host_io=True, gather_heads=heads_mode).capture(warmup=0)
     run_h.rewind(0)
     for t in range(args.warmup):
         run_h.step_host(*host_inputs[t])
@@ -329,7 +342,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
 
     ms_dev = max_over_ranks(ms_dev)
     ms_e2e = max_over_ranks(ms_e2e)
-    tokens = args.steps * B * n_gpus
+    tokens = args.steps * B * (1 if heads_mode else n_gpus)      # the head split works on the SAME sequences
     value = tokens / (ms_dev * 1e-3)
     e2e = tokens / (ms_e2e * 1e-3)
 
@@ -350,8 +363,9 @@ def run_ours(args, rank, world, local_rank, n_gpus):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, shape, L, hit_rate=hit_rate, n_gpus=n_gpus),
+                "scaling": "strong" if heads_mode else "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": workload_config(args, full_shape, L, hit_rate=hit_rate, n_gpus=n_gpus, heads_mode=heads_mode),
                 "us_per_layer_step": ms_dev / args.steps / L * 1e3,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": run_h.h2d_bytes,
                         "d2h_bytes_per_step": run_h.d2h_bytes, "ms_per_step": ms_e2e / args.steps,

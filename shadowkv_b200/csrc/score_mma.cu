@@ -7,8 +7,10 @@
 // CUTLASS 2.x Sm80 mma.sync, tile 32x256x32) on this path; same rounding points: fp32 accumulate, * alpha,
 // round to bf16, max / sum-of-exp over the ROUNDED values (epilogue_visitor_with_softmax).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31 = landmark rows of the tile).  Two CTAs fit per SM (3 x 32 KiB ring).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 and 6..9 = two
+// epilogue warpgroups that take alternate tiles (warp w reads TMEM lanes 32*(w%4)..+31 = landmark rows of the
+// tile; the per-tile epilogue is a latency chain of shuffles, so two tiles are kept in flight).  Two CTAs fit per
+// SM (3 x 32 KiB ring each).
 #include "sm100_ptx.cuh"
 
 namespace skv {
@@ -18,7 +20,8 @@ constexpr int kSmStages = 3;                     // 3 x 32 KiB ring per CTA
 constexpr int kSmSlabBytes = kSmTileRows * 128;  // one 64-column (128 B) swizzle slab of a tile
 constexpr int kSmTileBytes = 2 * kSmSlabBytes;   // 32 KiB
 constexpr int kSmQSlabBytes = 16 * 128;          // B operand: 16 rows (heads, zero padded) x 64 columns
-constexpr int kSmThreads = 192;
+constexpr int kSmEpiGroups = 2;                 // two epilogue warpgroups take alternate tiles
+constexpr int kSmThreads = 64 + kSmEpiGroups * 128;
 constexpr int kSmAccCols = 16;                   // fp32 accumulator columns per tile (UMMA N)
 
 struct ScoreMmaParams {
@@ -131,12 +134,13 @@ __global__ void __launch_bounds__(kSmThreads, 2)
   } else {
     // ===== epilogue: thread = landmark row of the tile =====
     const int lg = warp & 3;                                 // TMEM lane group this warp may read
-    const int ew = warp - 2;                                 // 0..3
-    for (int i = 0; i < n_my; ++i) {
+    const int grp = (warp - 2) >> 2;                         // epilogue warpgroup 0 / 1 <-> accumulator buffer
+    const int ew = (warp - 2) & 3;                           // 0..3 inside the group
+    for (int i = grp; i < n_my; i += kSmEpiGroups) {
       const int acc = i & 1, aph = (i >> 1) & 1;
       const int tile = cx + i * p.ctas_per_row;
       mbarrier_wait(&acc_full[acc], aph);
-      if (i < 4 && threadIdx.x == 64) SKV_STAMP_ANY(tr, 10 + i);
+      if (i < 4 && (threadIdx.x == 64 || threadIdx.x == 192)) SKV_STAMP_ANY(tr, 10 + i);
       tcgen05_fence_after();
       uint32_t r[16];
       tcgen05_ld16(tmem_base + (uint32_t(lg * 32) << 16) + acc * kSmAccCols, r);
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kSmThreads, 2)
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the four warps of this group
       if (ew == 0 && lane < p.G) {
         const float *rb = s_red + acc * 4 * 32 + lane * 2;
         float m = fmaxf(fmaxf(rb[0], rb[32]), fmaxf(rb[64], rb[96]));
@@ -189,8 +193,9 @@ __global__ void __launch_bounds__(kSmThreads, 2)
         p.part_max[(size_t(bh) * p.G + lane) * p.T + tile] = m;
         p.part_sum[(size_t(bh) * p.G + lane) * p.T + tile] = sum;
       }
-      // s_red is double buffered with the accumulator, and tile i+2 cannot reach this point before every
-      // warp passed the barrier of tile i+1, so no second barrier is needed
+      // s_red[acc] belongs to this group alone; a second barrier keeps the next tile of the group from
+      // overwriting it while warp 0 of the group still combines
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
     }
   }
   if (threadIdx.x == 64) SKV_STAMP_ANY(tr, 14);

@@ -19,13 +19,18 @@ from __future__ import annotations
 
 import torch
 
+from . import parallel
 from .kv_cache import ShadowKVCache_CPU
 
 
 
 class DecodeStepGraph:
-    def __init__(self, cache: ShadowKVCache_CPU, cos_sin_cache: torch.Tensor, *, host_io: bool = True):
+    def __init__(self, cache: ShadowKVCache_CPU, cos_sin_cache: torch.Tensor, *, host_io: bool = True,
+                 gather_heads: bool = False):
+        """gather_heads: kv-head split over the ranks of the default process group (parallel.head_shard_config):
+        the attention output of every layer is all-gathered inside the graph (the one exchange of that mode)."""
         self.cache = cache
+        self.gather = gather_heads
         self.cos_sin = cos_sin_cache
         self.host_io = host_io
         L, B = cache.num_layers, cache.batch_size
@@ -36,13 +41,18 @@ class DecodeStepGraph:
         self.v_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
         self.out_d = torch.zeros(L, B, 1, Hq, D, dtype=dt, device=dev)
         self.hits_d = torch.zeros(L, B * H, dtype=torch.int32, device=dev)   # cnts per layer of the last token
+        self.out_all = None
+        if gather_heads:
+            import torch.distributed as dist
+            self.out_all = torch.zeros(L, dist.get_world_size(), B, 1, Hq, D, dtype=dt, device=dev)
         if host_io:
             self.q_h = torch.zeros(L, B, Hq, 1, D, dtype=dt).pin_memory()
             self.k_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
             self.v_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
-            self.out_h = torch.zeros(L, B, 1, Hq, D, dtype=dt).pin_memory()
+            self.out_h = (torch.zeros_like(self.out_all, device="cpu") if gather_heads
+                          else torch.zeros(L, B, 1, Hq, D, dtype=dt)).pin_memory()
         self.h2d_bytes = (self.q_d.numel() + self.k_d.numel() + self.v_d.numel()) * 2
-        self.d2h_bytes = self.out_d.numel() * 2
+        self.d2h_bytes = (self.out_all if gather_heads else self.out_d).numel() * 2
         # kernels of libshadowkv_b200.so per token: score(+append), select, fetch(V), rebuild(K), attention
         # (+ the two hit compactions when the table keeps the reference's slot order)
         self.launches_per_step = L * (5 if cache.table_mode == "inplace" else 7)
@@ -62,9 +72,11 @@ class DecodeStepGraph:
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
                            device_counters=True)
             self.hits_d[l].copy_(c.cnts)
+            if self.gather:
+                parallel.gather_heads(self.out_d[l], self.out_all[l])
         c.advance_device_counters()
         if self.host_io:
-            self.out_h.copy_(self.out_d, non_blocking=True)
+            self.out_h.copy_(self.out_all if self.gather else self.out_d, non_blocking=True)
 
     def capture(self, warmup: int = 1):
         """Warm up eagerly (allocates scratch, builds tensor maps, sets kernel attributes), then capture.
