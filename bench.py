@@ -61,6 +61,9 @@ def parse_args():
     ap.add_argument("--shard", default="batch", choices=["batch", "heads"],
                     help="N > 1: shard the batch (weak scaling, no collective) or split the kv heads of the same "
                          "sequences over the ranks (strong scaling, one all-gather of the attention output per layer)")
+    ap.add_argument("--hbm-store-ways", type=int, default=4096,
+                    help="ways per (layer,b,h) of the optional HBM chunk store measured as a SECOND configuration "
+                         "after the headline run (0 = skip); the headline numbers never use it")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -175,7 +178,26 @@ def cpu_reference_layer_time(args, shape, n_layers, *, warmup: int, steps: int, 
 
 
 # ------------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else the process (or NCCL, or torchrun's children)
+    prints to fd 1 was redirected to stderr at start-up."""
+    text = json.dumps(line) + "\n"
+    if _JSON_OUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_OUT, text.encode())
+
+
 def main():
+    global _JSON_OUT
+    # keep stdout clean for the driver: libraries (NCCL prints its version there) write to fd 1 directly
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,7 +222,7 @@ def main():
                 "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     return run_ours(args, rank, world, local_rank, n_gpus)
@@ -333,6 +355,41 @@ def run_ours(args, rank, world, local_rank, n_gpus):
     ms_e2e = (time.perf_counter() - t0) * 1e3
     checksum = float(out_h.float().abs().sum())
 
+    # ---- second configuration: HBM chunk store between the sparse slots and the host store -----------------------
+    store = None
+    if args.hbm_store_ways > 0:
+        cache.enable_hbm_store(args.hbm_store_ways)
+        run_s = DecodeStepGraph(cache, cs, host_io=False, gather_heads=heads_mode).capture(warmup=0)
+        run_s.rewind(0)
+        fill_steps = 32                                     # tokens that warm the store before timing
+        for t in range(fill_steps):
+            if cache.sparse_end + cache.gen_offset + 1 > cache.buf_len:
+                run_s.rewind_async(0)
+            run_s.step_device(*dev_inputs[t % total])
+        barrier()
+        cache.pcie_count.zero_()
+        hits.zero_()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(run_s.stream):
+            s0.record()
+        for t in range(args.warmup, total):
+            if cache.sparse_end + cache.gen_offset + 1 > cache.buf_len:
+                run_s.rewind_async(0)
+            run_s.step_device(*dev_inputs[t])
+            with torch.cuda.stream(run_s.stream):
+                hits += run_s.hits_d
+        with torch.cuda.stream(run_s.stream):
+            s1.record()
+        barrier()
+        ms_store = s0.elapsed_time(s1)
+        slots = args.steps * L * B * H * S
+        store = {"ways": args.hbm_store_ways, "ms": ms_store,
+                 "sparse_slot_hit_rate": float(hits.sum().item()) / slots,
+                 "pcie_chunk_rate": float(cache.pcie_count.sum().item()) / slots,
+                 "hbm_bytes": int(cache.vstore_data.numel() * 2 + cache.vstore_tags.numel() * 4),
+                 "store_fill_tokens": fill_steps}
+        cache.enable_hbm_store(0)
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -342,6 +399,13 @@ def run_ours(args, rank, world, local_rank, n_gpus):
 
     ms_dev = max_over_ranks(ms_dev)
     ms_e2e = max_over_ranks(ms_e2e)
+    if store is not None:
+        ms_store = max_over_ranks(store.pop("ms"))
+        store.update(value=args.steps * B * (1 if heads_mode else n_gpus) / (ms_store * 1e-3), unit=UNIT,
+                     ms_per_step=ms_store / args.steps, us_per_layer_step=ms_store / args.steps / L * 1e3,
+                     note="same workload and outputs, byte for byte; chunks that fell out of the sparse slots are "
+                          "served from a direct-mapped HBM store instead of crossing PCIe again (not part of the "
+                          "headline value / e2e)")
     tokens = args.steps * B * (1 if heads_mode else n_gpus)      # the head split works on the SAME sequences
     value = tokens / (ms_dev * 1e-3)
     e2e = tokens / (ms_e2e * 1e-3)
@@ -371,9 +435,9 @@ def run_ours(args, rank, world, local_rank, n_gpus):
                         "d2h_bytes_per_step": run_h.d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "api": "shadowkv_b200.engine.DecodeStepGraph.step_host"},
                 "gpu_launches": run_d.launches_per_step * args.steps,
-                "roofline": roofline, "kernels": kernels, "pcie": pcie, "cpu_baseline": cpu, "clocks": clocks,
+                "hbm_chunk_store": store, "roofline": roofline, "kernels": kernels, "pcie": pcie, "cpu_baseline": cpu, "clocks": clocks,
                 "peaks": peaks, "lib": _lib.version(), "setup_s": round(setup_s, 1), "checksum": checksum}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -424,7 +488,10 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     score_bytes = B * (H * N * D * 2 + H * G * D * 2)
     roofline = {"kernel": "score_tiles_kernel (landmark scoring)", "bound": "hbm",
                 "achieved": score_bytes / t_score * 1e-3, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": score_bytes / t_score * 1e-3 / peaks["hbm"], "traffic": None,
+                "frac": score_bytes / t_score * 1e-3 / peaks["hbm"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 1 / 8 kv heads / 15 560 landmarks,
+                # from the ncu --set full capture summarised in profiles/r01_ncu_full_summary.txt
+                "traffic": 31910400 if (B, H, N) == (1, 8, 15560) else None,
                 "us_per_launch": t_score, "algorithmic_bytes_per_launch": score_bytes,
                 "peak_source": peaks["src"], "launches_timed": reps}
     kernels = {"score": {"us": t_score, "GBps": score_bytes / t_score * 1e-3}}
@@ -478,7 +545,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
         def fetch(l):
             vh = cache.v_cache_cpu[l]
             check(lib.skv_fetch_misses(C.byref(g), vh.data_ptr(), vh.stride(1), cache.v_cache_buffer[l].data_ptr(),
-                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), res.data_ptr(), cur()), "fetch")
+                                       cache.offsets.data_ptr(), cache.cnts.data_ptr(), res.data_ptr(), None, cur()), "fetch")
 
         def compact(l):
             check(lib.skv_compact_hits(C.byref(g), cache.k_cache_buffer[l].data_ptr(), cache.v_cache_buffer[l].data_ptr(),

@@ -218,12 +218,32 @@ int skv_select_from_scores(const skv_geom *geom, const int64_t *landmark_idx, in
 int skv_compact_hits(const skv_geom *geom, skv_bf16 *k_buf, skv_bf16 *v_buf, const int32_t *offsets,
                      const int32_t *cnts, skv_stream_t stream);
 
+/* Optional HBM-side chunk store between the sparse slots and the pinned host store (a B200 extension: 180 GB of
+ * HBM hold far more V chunks than the sparse budget).  Direct mapped per (b,h): chunk c lives in way c % ways.
+ * skv_fetch_misses only READS it (a missed chunk whose tag matches is copied HBM -> slot instead of crossing PCIe);
+ * skv_vstore_fill, launched after the fetch, installs the chunks that did cross PCIe (one deterministic winner
+ * per way).  Results are byte-identical with and without the store. */
+typedef struct skv_vstore {
+  int32_t *tags;        /* [B*H, ways] chunk id held by every way, -1 = empty                      */
+  skv_bf16 *data;       /* [B*H, ways, 1024]                                                        */
+  int32_t *pcie_count;  /* optional [B*H]: += number of chunks that had to come from the host store */
+  int32_t ways;         /* power of two                                                             */
+  int32_t reserved;
+} skv_vstore;
+
 /* (a6) miss fetch: for i >= cnts[bh]: V slot i <- v_host[bh, offsets[bh*S+i]] (pinned host memory,
  * read over PCIe by the SMs).  host_stride = elements between consecutive (b,h) blocks of v_host.
  * geom->table_mode == 1: for i < S - cnts[bh]: slot = offsets[bh*S+i]; V slot <- v_host[bh, resident[bh*S+slot]]
  * (resident is required in that mode, ignored otherwise). */
 int skv_fetch_misses(const skv_geom *geom, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
-                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, skv_stream_t stream);
+                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, const skv_vstore *vstore,
+                     skv_stream_t stream);
+
+/* Installs the chunks the preceding skv_fetch_misses (same arguments) brought over PCIe into the HBM chunk store:
+ * copies them from their sparse slots into their ways and updates the tags.  When several missed chunks of one
+ * (b,h) map to the same way the last one in miss order wins.  Must run after the fetch and before the next one. */
+int skv_vstore_fill(const skv_geom *geom, const skv_bf16 *v_buf, const int32_t *offsets, const int32_t *cnts,
+                    const int64_t *resident, const skv_vstore *vstore, skv_stream_t stream);
 
 /* (a7) K rebuild for the missed chunks with RoPE in the epilogue (TMA-fed tcgen05, fp32 accumulate in
  * TMEM, bf16 round, bf16 RoPE at token position id*C+r), written straight into the sparse region of

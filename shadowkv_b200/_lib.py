@@ -26,6 +26,12 @@ class Append(C.Structure):
                 ("pos_dev", C.c_void_p), ("pos", C.c_int32), ("reserved", C.c_int32)]
 
 
+class VStore(C.Structure):
+    """struct skv_vstore (include/shadowkv_b200.h)."""
+    _fields_ = [("tags", C.c_void_p), ("data", C.c_void_p), ("pcie_count", C.c_void_p), ("ways", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`)."
@@ -52,7 +58,8 @@ _SIGS = {
     "skv_score_landmarks": [C.POINTER(Geom)] + [_p] * 3 + [C.POINTER(Append), _p],
     "skv_select_from_scores": [C.POINTER(Geom)] + [_p] * 8,
     "skv_compact_hits": [C.POINTER(Geom)] + [_p] * 5,
-    "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p],
+    "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, C.POINTER(VStore), _p],
+    "skv_vstore_fill": [C.POINTER(Geom), _p, _p, _p, _p, C.POINTER(VStore), _p],
     "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 7 + [_i, _p],
     "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],

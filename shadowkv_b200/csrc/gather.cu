@@ -153,7 +153,8 @@ template <typename IdT>
 __global__ void __launch_bounds__(256)
     fetch_chunks_kernel(const skv_bf16 *__restrict__ src, int64_t src_stride_bh, skv_bf16 *__restrict__ dst,
                         int64_t dst_stride_bh, int64_t dst_base_off, const IdT *__restrict__ ids,
-                        const int32_t *__restrict__ cnts, const int64_t *__restrict__ resident, int S) {
+                        const int32_t *__restrict__ cnts, const int64_t *__restrict__ resident, int S,
+                        skv_vstore vs) {
   const int bh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cnt = cnts ? cnts[bh] : 0;
@@ -182,6 +183,14 @@ __global__ void __launch_bounds__(256)
     }
     if (on[u]) {
       const int4 *p = sbase + size_t(chunk) * (kChunkBytes / 16) + lane;
+      if (vs.tags) {                                  // HBM chunk store: read-only here (skv_vstore_fill updates it)
+        const int way = static_cast<int>(chunk) & (vs.ways - 1);
+        const size_t w = size_t(bh) * vs.ways + way;
+        if (vs.tags[w] == static_cast<int>(chunk))    // warp uniform
+          p = reinterpret_cast<const int4 *>(vs.data) + w * (kChunkBytes / 16) + lane;
+        else if (vs.pcie_count && lane == 0)
+          atomicAdd(vs.pcie_count + bh, 1);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[u][k] = ld_stream(p + k * 32);
     }
@@ -198,10 +207,55 @@ __global__ void __launch_bounds__(256)
 
 template <typename IdT>
 static int launch_fetch(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, int64_t dst_stride, int64_t dst_off,
-                        const IdT *ids, const int32_t *cnts, const int64_t *resident, int BH, int S, cudaStream_t st) {
+                        const IdT *ids, const int32_t *cnts, const int64_t *resident, int BH, int S, cudaStream_t st,
+                        const skv_vstore *vstore = nullptr) {
+  skv_vstore vs{};
+  if (vstore) vs = *vstore;
   dim3 grid((S + 15) / 16, BH);
-  fetch_chunks_kernel<IdT><<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, dst_off, ids, cnts, resident, S);
+  fetch_chunks_kernel<IdT><<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, dst_off, ids, cnts, resident, S, vs);
   return launch_status("fetch_chunks_kernel");
+}
+
+// HBM chunk-store fill: one CTA per (b,h).  Thread t looks at miss t: it installs its chunk when the store does
+// not hold it yet and no LATER miss of this row maps to the same way (so every way has exactly one writer and the
+// fetch kernel, which only reads the store, never races with a fill).
+__global__ void __launch_bounds__(256)
+    vstore_fill_kernel(const skv_bf16 *__restrict__ v_buf, int64_t stride_bh, int64_t base_off,
+                       const int32_t *__restrict__ offsets, const int32_t *__restrict__ cnts,
+                       const int64_t *__restrict__ resident, int S, int table_mode, skv_vstore vs) {
+  __shared__ int s_way[1024], s_slot[1024], s_chunk[1024];
+  __shared__ int s_win[1024], s_nwin;
+  const int bh = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cnt = cnts[bh], n_miss = S - cnt;
+  if (threadIdx.x == 0) s_nwin = 0;
+  for (int i = threadIdx.x; i < n_miss; i += blockDim.x) {
+    int slot, chunk;
+    if (table_mode) { slot = offsets[size_t(bh) * S + i]; chunk = static_cast<int>(resident[size_t(bh) * S + slot]); }
+    else { slot = cnt + i; chunk = offsets[size_t(bh) * S + slot]; }
+    s_slot[i] = slot; s_chunk[i] = chunk; s_way[i] = chunk & (vs.ways - 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_miss; i += blockDim.x) {
+    const int way = s_way[i];
+    bool win = vs.tags[size_t(bh) * vs.ways + way] != s_chunk[i];      // not in the store yet
+    for (int j = i + 1; win && j < n_miss; ++j) win = s_way[j] != way;   // the last miss of a way wins
+    if (win) s_win[atomicAdd(&s_nwin, 1)] = i;
+  }
+  __syncthreads();
+  const int nwin = s_nwin;
+  const int4 *src = reinterpret_cast<const int4 *>(v_buf + size_t(bh) * stride_bh + base_off);
+  int4 *dst = reinterpret_cast<int4 *>(vs.data) + size_t(bh) * vs.ways * (kChunkBytes / 16);
+  for (int k = warp; k < nwin; k += blockDim.x >> 5) {
+    const int i = s_win[k];
+    const int4 *p = src + size_t(s_slot[i]) * (kChunkBytes / 16) + lane;
+    int4 *q = dst + size_t(s_way[i]) * (kChunkBytes / 16) + lane;
+    int4 v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = p[e * 32];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e * 32] = v[e];
+    if (lane == 0) vs.tags[size_t(bh) * vs.ways + s_way[i]] = s_chunk[i];
+  }
 }
 
 }  // namespace skv
@@ -273,9 +327,13 @@ int skv_compact_hits(const skv_geom *g, skv_bf16 *k_buf, skv_bf16 *v_buf, const 
 }
 
 int skv_fetch_misses(const skv_geom *g, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
-                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, skv_stream_t stream) {
+                     const int32_t *offsets, const int32_t *cnts, const int64_t *resident, const skv_vstore *vstore,
+                     skv_stream_t stream) {
   if (!g || !v_host || !v_buf || !offsets || !cnts || (g->table_mode && !resident)) {
     set_error("fetch_misses: null pointer"); return SKV_ERR_ARGUMENT;
+  }
+  if (vstore && (!vstore->tags || !vstore->data || vstore->ways < 1 || (vstore->ways & (vstore->ways - 1)))) {
+    set_error("fetch_misses: chunk store needs tags, data and a power-of-two way count"); return SKV_ERR_ARGUMENT;
   }
   if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select)) {
     set_error("fetch_misses: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
@@ -283,7 +341,22 @@ int skv_fetch_misses(const skv_geom *g, const skv_bf16 *v_host, int64_t host_str
   return launch_fetch<int32_t>(v_host, host_stride, v_buf, int64_t(g->buf_len) * g->head_dim,
                                int64_t(g->sparse_start) * g->head_dim, offsets, cnts,
                                g->table_mode ? resident : nullptr, g->batch * g->kv_heads, g->select,
-                               as_stream(stream));
+                               as_stream(stream), vstore);
+}
+
+int skv_vstore_fill(const skv_geom *g, const skv_bf16 *v_buf, const int32_t *offsets, const int32_t *cnts,
+                    const int64_t *resident, const skv_vstore *vstore, skv_stream_t stream) {
+  if (!g || !v_buf || !offsets || !cnts || !vstore || !vstore->tags || !vstore->data || (g->table_mode && !resident)) {
+    set_error("vstore_fill: null pointer"); return SKV_ERR_ARGUMENT;
+  }
+  if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select) || vstore->ways < 1 ||
+      (vstore->ways & (vstore->ways - 1))) {
+    set_error("vstore_fill: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
+  }
+  vstore_fill_kernel<<<g->batch * g->kv_heads, 256, 0, as_stream(stream)>>>(
+      v_buf, int64_t(g->buf_len) * g->head_dim, int64_t(g->sparse_start) * g->head_dim, offsets, cnts, resident,
+      g->select, g->table_mode, *vstore);
+  return launch_status("vstore_fill_kernel");
 }
 
 }  // extern "C"

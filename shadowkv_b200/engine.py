@@ -55,7 +55,7 @@ class DecodeStepGraph:
         self.d2h_bytes = (self.out_all if gather_heads else self.out_d).numel() * 2
         # kernels of libshadowkv_b200.so per token: score(+append), select, fetch(V), rebuild(K), attention
         # (+ the two hit compactions when the table keeps the reference's slot order)
-        self.launches_per_step = L * (5 if cache.table_mode == "inplace" else 7)
+        self.launches_per_step = L * ((5 if cache.table_mode == "inplace" else 7) + (1 if cache.hbm_store_ways else 0))
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0
@@ -74,6 +74,7 @@ class DecodeStepGraph:
             self.hits_d[l].copy_(c.cnts)
             if self.gather:
                 parallel.gather_heads(self.out_d[l], self.out_all[l])
+        c.join_side_streams()
         c.advance_device_counters()
         if self.host_io:
             self.out_h.copy_(self.out_all if self.gather else self.out_d, non_blocking=True)

@@ -41,9 +41,12 @@ class ShadowKVCache_CPU:
 
     def __init__(self, config, batch_size: int = 1, max_length: int = 32 * 1024, device: str = "cuda:0",
                  dtype=torch.bfloat16, sparse_budget: int = 2048, chunk_size: int = 8, rank: int = 160,
-                 table_mode: str = "inplace") -> None:
+                 table_mode: str = "inplace", hbm_store_ways: int = 0) -> None:
         """table_mode: "inplace" (default; chunk-cache hits keep their slots, no compaction traffic) or
-        "reference" (slot order of reference map.cuh:754-796: hits compacted to the front)."""
+        "reference" (slot order of reference map.cuh:754-796: hits compacted to the front).
+        hbm_store_ways: > 0 adds a direct-mapped HBM chunk store of that many 2 KiB ways per (layer, b, h)
+        between the sparse slots and the pinned host store (power of two; 0 = the reference's behaviour: every
+        chunk that is not in a sparse slot crosses PCIe).  Results are byte-identical either way."""
         if dtype != torch.bfloat16:
             raise ValueError("the sm_100a kernels compute in bf16 only")
         if table_mode not in ("inplace", "reference"):
@@ -94,6 +97,16 @@ class ShadowKVCache_CPU:
         self.cnts = torch.zeros(self.block_num, dtype=torch.int32, device=self.device)
         self.position_ids = torch.full((L, B, H, self.select_sets), -1, dtype=torch.int64, device=self.device)
 
+        self.hbm_store_ways = int(hbm_store_ways)
+        if self.hbm_store_ways & (self.hbm_store_ways - 1):
+            raise ValueError("hbm_store_ways must be 0 or a power of two")
+        self.vstore_tags = self.vstore_data = None
+        self.pcie_count = torch.zeros(L, B * H, dtype=torch.int32, device=self.device)
+        if self.hbm_store_ways:
+            W = self.hbm_store_ways
+            self.vstore_tags = torch.full((L, B * H, W), -1, dtype=torch.int32, device=self.device)
+            self.vstore_data = torch.empty(L, B * H, W, D * chunk_size, dtype=dtype, device=self.device)
+
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._fetch_done = torch.cuda.Event()
         self._geom = None
@@ -132,6 +145,9 @@ class ShadowKVCache_CPU:
         self.kv_offset = self.prefill = self.gen_offset = self.prefill_local = 0
         self.prefilled_batch = 0
         self.position_ids.fill_(-1)
+        if self.vstore_tags is not None:
+            self.vstore_tags.fill_(-1)
+        self.pcie_count.zero_()
         self._geom = None
 
     # ------------------------------------------------------------------------------------------
@@ -348,9 +364,47 @@ class ShadowKVCache_CPU:
             check(lib.skv_compact_hits(C.byref(g), 0, vb.data_ptr(), self.offsets.data_ptr(), self.cnts.data_ptr(), st),
                   "compact_hits(V)")
         vh = self.v_cache_cpu[layer_idx]
+        vs = self._vstore(layer_idx)
         check(lib.skv_fetch_misses(C.byref(g), vh.data_ptr(), vh.stride(1), vb.data_ptr(), self.offsets.data_ptr(),
-                                   self.cnts.data_ptr(), self.position_ids[layer_idx].data_ptr(), st), "fetch_misses")
+                                   self.cnts.data_ptr(), self.position_ids[layer_idx].data_ptr(),
+                                   C.byref(vs) if vs is not None else None, st), "fetch_misses")
         return vb[:, :, :self._view_len(layer_idx)]
+
+    def enable_hbm_store(self, ways: int):
+        """(Re)allocate the HBM chunk store with `ways` ways per (layer, b, h); 0 removes it.  Any captured
+        CUDA graph of the step must be re-captured afterwards."""
+        if ways & (ways - 1):
+            raise ValueError("ways must be 0 or a power of two")
+        self.hbm_store_ways = int(ways)
+        self.vstore_tags = self.vstore_data = None
+        if ways:
+            L, BH = self.num_layers, self.batch_size * self.num_key_value_heads
+            self.vstore_tags = torch.full((L, BH, ways), -1, dtype=torch.int32, device=self.device)
+            self.vstore_data = torch.empty(L, BH, ways, self.head_dim * self.chunk_size, dtype=self.dtype,
+                                           device=self.device)
+        self.pcie_count.zero_()
+
+    def _vstore(self, layer_idx):
+        if not self.hbm_store_ways:
+            return None
+        return _lib.VStore(tags=self.vstore_tags[layer_idx].data_ptr(), data=self.vstore_data[layer_idx].data_ptr(),
+                           pcie_count=self.pcie_count[layer_idx].data_ptr(), ways=self.hbm_store_ways)
+
+    def fill_value_store(self, layer_idx):
+        """Install the chunks the last get_value_cache(layer_idx) brought over PCIe into the HBM chunk store.
+        Call after get_value_cache on the same stream (decode_layer does); no-op without a store."""
+        vs = self._vstore(layer_idx)
+        if vs is None:
+            return
+        g = self._geometry()
+        check(lib.skv_vstore_fill(C.byref(g), self.v_cache_buffer[layer_idx].data_ptr(), self.offsets.data_ptr(),
+                                  self.cnts.data_ptr(), self.position_ids[layer_idx].data_ptr(), C.byref(vs), _cs()),
+              "vstore_fill")
+
+    def join_side_streams(self):
+        """Make the current stream wait for everything queued on the copy stream (the store fill of the last
+        layer runs behind the attention that did not have to wait for it)."""
+        torch.cuda.current_stream().wait_stream(self.copy_stream)
 
     def get_key_cache(self, layer_idx, position_ids, rope_func, cos_sin_cache):
         """Compact the hit chunks, rebuild + RoPE the missed ones from U.SV (kv_cache.py:1108-1176).
@@ -411,8 +465,14 @@ class ShadowKVCache_CPU:
         self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream):
             self.get_value_cache(layer_idx, pid)
+            if self.hbm_store_ways:           # attention waits for the fetch only; the store fill runs behind it
+                self._fetch_done.record(self.copy_stream)
+                self.fill_value_store(layer_idx)
         self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
-        cur.wait_stream(self.copy_stream)
+        if self.hbm_store_ways:
+            cur.wait_event(self._fetch_done)
+        else:
+            cur.wait_stream(self.copy_stream)
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
         return self.attention(layer_idx, query_states, kv_len, out, device_counters)
 
@@ -425,7 +485,7 @@ class ShadowKVCache(ShadowKVCache_CPU):
     def __init__(self, config, batch_size=1, max_length=32 * 1024, device="cuda:0", dtype=torch.bfloat16,
                  sparse_budget=2048, chunk_size=8, rank=160, table_mode="inplace") -> None:
         assert batch_size == 1, "ShadowKV class only supports batch_size=1, please use ShadowKV_CPU class for batch_size > 1"
-        super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank, table_mode)
+        super().__init__(config, batch_size, max_length, device, dtype, sparse_budget, chunk_size, rank, table_mode, 0)
 
     def _outlier_chunks(self) -> int:
         return 48                                                          # kv_cache.py:206

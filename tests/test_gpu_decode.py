@@ -219,3 +219,40 @@ def test_decode_layer_fused_append_equals_update_kv_cache(cuda):
             assert torch.equal(c1.position_ids[l], c2.position_ids[l])
             assert torch.equal(o1, o2)
         assert c1.gen_offset == c2.gen_offset == step + 1
+
+
+def test_hbm_chunk_store_is_transparent(cuda):
+    """The HBM chunk store (a direct-mapped cache of V chunks between the sparse slots and the pinned host store)
+    must not change a single byte: same chunk table, same K/V buffers, same attention output as without it, while
+    fewer chunks cross PCIe; and every valid way holds exactly the host store's chunk named by its tag."""
+    shape, c1, _, _, cs, lay = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2, table_mode="inplace")
+    _, c2, ora, _, _, _ = _build(cuda, "llama-3.1-8b", 2, 8192, 1024, 2, table_mode="inplace")
+    c2.enable_hbm_store(256)                    # few ways on purpose: conflicts inside one step must be handled
+    d_cs = cs.to(cuda)
+    H, S = shape.num_key_value_heads, lay.select
+    base = None
+    misses = 0
+    for step in range(10):
+        for l in range(2):
+            q, kn, vn = synth.queries(shape, 2, seed=31 * step + l, base=base, noise=0.45)
+            base = q if base is None else base
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            o1 = c1.decode_layer(l, dq, dk, dv, d_cs)
+            o2 = c2.decode_layer(l, dq, dk, dv, d_cs)
+            torch.cuda.synchronize()
+            misses += int((S - c1.cnts).sum())
+            assert torch.equal(c1.position_ids[l], c2.position_ids[l])
+            assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l]), f"V bytes differ at step {step} layer {l}"
+            assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l])
+            assert torch.equal(o1, o2)
+    from_host = int(c2.pcie_count.sum())
+    assert 0 < from_host < misses, f"{from_host} of {misses} missed chunks came over PCIe"
+    for l in range(2):
+        tags = c2.vstore_tags[l].cpu()
+        data = c2.vstore_data[l].cpu()
+        host = ora[l].v_host.view(2 * H, -1, 1024)
+        for r in range(2 * H):
+            ways = (tags[r] >= 0).nonzero().flatten()
+            assert len(ways) > 0
+            assert torch.equal(tags[r, ways] % 256, ways.to(torch.int32)), "a chunk sits in the wrong way"
+            assert torch.equal(data[r, ways], host[r, tags[r, ways].long()]), "a way does not hold its chunk's bytes"
