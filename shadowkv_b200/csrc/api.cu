@@ -1,6 +1,7 @@
 // Error reporting and identification for the C-ABI.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -11,6 +12,10 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("SKV_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 }  // namespace skv
 

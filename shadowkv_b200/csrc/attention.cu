@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kAttnMaxWarps * 32, 1)
   __shared__ float s_L[kAttnGT];
   __shared__ int s_last;
 
+  pdl_launch_dependents();      // the next layer's scoring kernel may start streaming its landmarks behind us
   const int split = blockIdx.x;
   const int h = blockIdx.y / p.ngz, gz = blockIdx.y % p.ngz, b = blockIdx.z;
   const int g0 = gz * kAttnGT;

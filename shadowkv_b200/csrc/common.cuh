@@ -59,6 +59,34 @@ inline int launch_status(const char *what) {
 
 inline bool valid_map_size(int s) { return s == 128 || s == 256 || s == 512 || s == 1024; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The kernels of the step form a chain in one stream.  Launched with the programmatic-serialization attribute,
+// a kernel may START while its predecessor still runs: its prologue (barrier init, TMEM allocation, loads of
+// data the predecessor does not produce, e.g. the landmark stream) overlaps the predecessor's tail, and the
+// launch latency disappears from the critical path.  pdl_wait() blocks until the predecessor has completed and
+// its writes are visible; pdl_launch_dependents() lets the successor be scheduled.  Both are no-ops when the
+// kernel was launched normally.  SKV_PDL=0 in the environment disables the attribute (A/B measurements).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- 128-bit streaming loads / stores --------------------------------------------------------
 __device__ __forceinline__ int4 ld_stream(const int4 *p) {
   int4 r;

@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(256)
                         int64_t dst_stride_bh, int64_t dst_base_off, const IdT *__restrict__ ids,
                         const int32_t *__restrict__ cnts, const int64_t *__restrict__ resident, int S,
                         skv_vstore vs) {
+  pdl_launch_dependents();
+  pdl_wait();                                         // offsets / cnts / resident come from the selection kernel
   const int bh = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cnt = cnts ? cnts[bh] : 0;
@@ -212,7 +214,9 @@ static int launch_fetch(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, 
   skv_vstore vs{};
   if (vstore) vs = *vstore;
   dim3 grid((S + 15) / 16, BH);
-  fetch_chunks_kernel<IdT><<<grid, 256, 0, st>>>(src, src_stride, dst, dst_stride, dst_off, ids, cnts, resident, S, vs);
+  cudaError_t e = launch_kernel(fetch_chunks_kernel<IdT>, grid, dim3(256), 0, st, /*pdl=*/true, src, src_stride, dst,
+                                dst_stride, dst_off, ids, cnts, resident, S, vs);
+  if (e != cudaSuccess) { set_error("fetch_chunks_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("fetch_chunks_kernel");
 }
 

@@ -314,11 +314,15 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   const int count = n_end - n_begin;            // only the last slice can be ragged (N % 8 != 0)
   SKV_STAMP(bh == 0 ? rank : 999, 0);
 
-  // early, independent global loads: landmark ids of this thread's first 8 landmarks, its resident id
+  // early, independent global loads: the (static) landmark ids of this thread's first 8 landmarks.  Under a
+  // programmatic launch this and the histogram clearing overlap the tail of the scoring kernel.
+  pdl_launch_dependents();
   const int64_t *lidx = landmark_idx + size_t(bh) * N + n_begin;
   int ids0[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) ids0[e] = (tid * 8 + e < count) ? static_cast<int>(lidx[tid * 8 + e]) : 0;   // map.cuh:776
+  for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
+  pdl_wait();                                   // scores, partials and the chunk table are the predecessors' outputs
   int old_id = 0;
   if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
 
@@ -328,7 +332,6 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
     reduce_partials_fast(part_max + (size_t(bh) * G + g) * T, part_sum + (size_t(bh) * G + g) * T, T, lane, m, inv);
     if (lane == 0) { s_m[g] = m; s_inv[g] = inv; }
   }
-  for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
   __syncthreads();
   SKV_STAMP(bh == 0 ? rank : 999, 1);
 
@@ -609,9 +612,10 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   {                                                                                                              \
     static int cur = 0;                                                                                          \
     if (smem > cur) { cudaFuncSetAttribute(select_kernel<SV, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cur = smem; } \
-    select_kernel<SV, IP><<<dim3(kSelCluster, BH), kThreads, smem, st>>>(w.scores, w.pmax, w.psum, landmark_idx, \
-                                                                          resident, offsets, cnts, selected_out,   \
-                                                                          score_out, G, N, w.ldn, w.T, per);       \
+    cudaError_t e = launch_kernel(select_kernel<SV, IP>, dim3(kSelCluster, BH), dim3(kThreads), smem, st, true,     \
+                                  w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
+                                  score_out, G, N, w.ldn, w.T, per);                                              \
+    if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL(SV)                                                                                              \
   case SV: {                                                                                                     \

@@ -52,6 +52,25 @@ __global__ void __launch_bounds__(kSmThreads, 2)
   const int tr = bh == 0 ? cx : 999;
   SKV_STAMP(tr, 0);
 
+  pdl_launch_dependents();                                   // the selection kernel may be scheduled behind us
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSmStages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the ring is empty: fill it right away.  The landmarks are static, so under a programmatic launch this
+    // runs while the previous kernel of the stream (the previous layer's attention) is still finishing.
+    const uint64_t pol = l2_policy_evict_first();            // landmarks are read once per step
+    for (int i = 0; i < kSmStages && i < n_my; ++i) {
+      const int row0 = bh * p.N + (cx + i * p.ctas_per_row) * kSmTileRows;
+      mbarrier_expect_tx(&full_bar[i], kSmTileBytes);
+      tma_load_2d_hint(sA + i * kSmTileBytes, &map_lm, 0, row0, &full_bar[i], pol);
+      tma_load_2d_hint(sA + i * kSmTileBytes + kSmSlabBytes, &map_lm, 64, row0, &full_bar[i], pol);
+      if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
+    }
+  }
+  // everything below touches data of the predecessor (q, the K/V buffers, the score scratch)
+  pdl_wait();
+
   // fused append (a2): the first CTA of every (b,h) writes the new token's K and V rows
   if (p.ap.k_new && cx == 0 && warp == 2) {
     const int64_t pos = p.ap.pos + (p.ap.pos_dev ? *p.ap.pos_dev : 0);
@@ -72,20 +91,6 @@ __global__ void __launch_bounds__(kSmThreads, 2)
     *reinterpret_cast<int4 *>(sQ + slab * kSmQSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
   }
   fence_proxy_async_smem();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kSmStages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // the ring is empty: fill it right away, the rest of the CTA is still setting up
-    const uint64_t pol = l2_policy_evict_first();            // landmarks are read once per step
-    for (int i = 0; i < kSmStages && i < n_my; ++i) {
-      const int row0 = bh * p.N + (cx + i * p.ctas_per_row) * kSmTileRows;
-      mbarrier_expect_tx(&full_bar[i], kSmTileBytes);
-      tma_load_2d_hint(sA + i * kSmTileBytes, &map_lm, 0, row0, &full_bar[i], pol);
-      tma_load_2d_hint(sA + i * kSmTileBytes + kSmSlabBytes, &map_lm, 64, row0, &full_bar[i], pol);
-      if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
-    }
-  }
   if (warp == 1) tcgen05_alloc(tmem_slot, 32);
   tcgen05_fence_before();
   __syncthreads();
@@ -226,7 +231,8 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
     cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  score_tcgen05_kernel<<<dim3(cpr, BH), kSmThreads, smem, st>>>(map, p);
+  cudaError_t e = launch_kernel(score_tcgen05_kernel, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p);
+  if (e != cudaSuccess) { set_error("score_tcgen05_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("score_tcgen05_kernel");
 }
 

@@ -40,7 +40,6 @@ class DecodeStepGraph:
         self.k_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
         self.v_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
         self.out_d = torch.zeros(L, B, 1, Hq, D, dtype=dt, device=dev)
-        self.hits_d = torch.zeros(L, B * H, dtype=torch.int32, device=dev)   # cnts per layer of the last token
         self.out_all = None
         if gather_heads:
             import torch.distributed as dist
@@ -61,6 +60,11 @@ class DecodeStepGraph:
         self.replays = 0
         self._presets = {}
 
+    @property
+    def hits_d(self):
+        """Chunk-cache hits per (layer, b*h) of the last token (the per-layer `cnts` the selection kernels wrote)."""
+        return self.cache.cnts_all
+
     # ----------------------------------------------------------------------------------------------
     def _body(self):
         c = self.cache
@@ -71,7 +75,6 @@ class DecodeStepGraph:
         for l in range(c.num_layers):
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
                            device_counters=True)
-            self.hits_d[l].copy_(c.cnts)
             if self.gather:
                 parallel.gather_heads(self.out_d[l], self.out_all[l])
         c.join_side_streams()

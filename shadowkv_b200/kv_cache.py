@@ -93,8 +93,13 @@ class ShadowKVCache_CPU:
         self.SV = None
 
         self.block_num = B * H
-        self.offsets = torch.zeros(self.block_num * self.select_sets, dtype=torch.int32, device=self.device)
-        self.cnts = torch.zeros(self.block_num, dtype=torch.int32, device=self.device)
+        # offsets / cnts of the reference (kv_cache.py:626-627) are one scratch pair shared by all layers; here
+        # every layer owns its pair, so kernels of layer l that run behind the critical path (the HBM store fill,
+        # programmatically launched successors) never race with the selection of layer l+1.  `offsets` / `cnts`
+        # are views of the layer that ran last.
+        self.offsets_all = torch.zeros(L, self.block_num * self.select_sets, dtype=torch.int32, device=self.device)
+        self.cnts_all = torch.zeros(L, self.block_num, dtype=torch.int32, device=self.device)
+        self.offsets, self.cnts = self.offsets_all[0], self.cnts_all[0]
         self.position_ids = torch.full((L, B, H, self.select_sets), -1, dtype=torch.int64, device=self.device)
 
         self.hbm_store_ways = int(hbm_store_ways)
@@ -109,6 +114,7 @@ class ShadowKVCache_CPU:
 
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._fetch_done = torch.cuda.Event()
+        self._k_done = torch.cuda.Event()
         self._geom = None
         self._sel_ws = None
         self._attn_ws = None
@@ -342,6 +348,7 @@ class ShadowKVCache_CPU:
             raise ValueError("decode scores one query token per step")
         g = self._geometry()
         q = query_states.contiguous()
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
         check(lib.skv_select_chunks(C.byref(g), q.data_ptr(), self.k_landmark[layer_idx].data_ptr(),
                                     self.k_landmark_idx[layer_idx].data_ptr(), self.position_ids[layer_idx].data_ptr(),
                                     self.offsets.data_ptr(), self.cnts.data_ptr(),
@@ -359,6 +366,7 @@ class ShadowKVCache_CPU:
         """Compact the hit chunks, fetch the missed ones from pinned host memory (kv_cache.py:1059-1106)."""
         g = self._geometry()
         st = _cs()
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
         vb = self.v_cache_buffer[layer_idx]
         if not g.table_mode:
             check(lib.skv_compact_hits(C.byref(g), 0, vb.data_ptr(), self.offsets.data_ptr(), self.cnts.data_ptr(), st),
@@ -397,6 +405,7 @@ class ShadowKVCache_CPU:
         if vs is None:
             return
         g = self._geometry()
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
         check(lib.skv_vstore_fill(C.byref(g), self.v_cache_buffer[layer_idx].data_ptr(), self.offsets.data_ptr(),
                                   self.cnts.data_ptr(), self.position_ids[layer_idx].data_ptr(), C.byref(vs), _cs()),
               "vstore_fill")
@@ -411,6 +420,7 @@ class ShadowKVCache_CPU:
         rope_func is accepted for signature compatibility and unused, as in the reference."""
         g = self._geometry(cos_sin_cache)
         st = _cs()
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
         kb = self.k_cache_buffer[layer_idx]
         if not g.table_mode:
             check(lib.skv_compact_hits(C.byref(g), kb.data_ptr(), 0, self.offsets.data_ptr(), self.cnts.data_ptr(), st),
@@ -461,18 +471,21 @@ class ShadowKVCache_CPU:
         if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += 1
             self.gen_offset += 1
-        cur = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(cur)
-        with torch.cuda.stream(self.copy_stream):
-            self.get_value_cache(layer_idx, pid)
-            if self.hbm_store_ways:           # attention waits for the fetch only; the store fill runs behind it
-                self._fetch_done.record(self.copy_stream)
+        # The V fetch is the long pole (PCIe), so it stays on the current stream right behind the selection kernel
+        # (programmatic launch: no launch gap); the short K rebuild runs beside it on the side stream.  base.py's
+        # choreography (:326-338) has the two swapped, which only matters for who pays the fork/join.
+        cur, side = torch.cuda.current_stream(), self.copy_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
+            self._k_done.record(side)
+        self.get_value_cache(layer_idx, pid)
+        if self.hbm_store_ways:               # the store fill runs behind the attention, on the side stream
+            self._fetch_done.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(self._fetch_done)
                 self.fill_value_store(layer_idx)
-        self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
-        if self.hbm_store_ways:
-            cur.wait_event(self._fetch_done)
-        else:
-            cur.wait_stream(self.copy_stream)
+        cur.wait_event(self._k_done)
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
         return self.attention(layer_idx, query_states, kv_len, out, device_counters)
 
