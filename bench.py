@@ -440,6 +440,14 @@ def run_ours(args, rank, world, local_rank, n_gpus):
         emit(line)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if heads_mode:
+            # destroy_process_group() does not return while CUDA graphs that captured NCCL collectives are alive
+            # (observed on torch 2.11 / NCCL 2.28): drop the graphs and leave without tearing the group down
+            for r in (run_d, run_h):
+                r.graph.reset()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
     return 0
 

@@ -256,3 +256,63 @@ def test_hbm_chunk_store_is_transparent(cuda):
             assert len(ways) > 0
             assert torch.equal(tags[r, ways] % 256, ways.to(torch.int32)), "a chunk sits in the wrong way"
             assert torch.equal(data[r, ways], host[r, tags[r, ways].long()]), "a way does not hold its chunk's bytes"
+
+
+def test_full_size_step_properties(cuda):
+    """BASELINE.json configs[1] at full size (Llama-3.1-8B shape, 124 928-token context, budget 2048, rank 160),
+    one layer, three decode steps: the oracle would take minutes here, so the step is checked through
+    size-independent properties -- selection == top-S / lowest-index rule on the kernel's own scores, every sparse
+    slot's V bytes == its chunk of the pinned host store, hit slots untouched, K of the missed slots == the
+    oracle's RoPE(U.SV) of THOSE chunks (the oracle only rebuilds the ~100 missed chunks per head), attention ==
+    the oracle's softmax attention over the assembled buffers."""
+    from shadowkv_b200.kv_cache import ShadowKVCache_CPU
+    shape = synth.MODELS["llama-3.1-8b"]
+    B, ctx, budget = 1, 124928, 2048
+    cs = synth.cos_sin_table(ctx + 1024, device=cuda)
+    st = synth.layer_state(shape, B, ctx, seed=1000, sparse_budget=budget, device=cuda, cos_sin=cs)
+    lay = st["layout"]
+    assert (lay.n_landmarks, lay.sparse_start, lay.sparse_end, lay.buf_len) == (15560, 448, 2496, 2592)
+    cache = ShadowKVCache_CPU(shape.config(1), batch_size=B, max_length=ctx, device=str(cuda), sparse_budget=budget)
+    synth.install(cache, [st])
+    H, S, C, ss = 8, lay.select, 8, lay.sparse_start
+    v_host, U, SV, cs_cpu = st["v_chunks"].cpu(), st["U"].cpu(), st["SV"].cpu(), cs.cpu()
+    lm_idx = st["k_landmark_idx"].cpu()
+    base = None
+    for step in range(3):
+        q, kn, vn = synth.queries(shape, B, seed=step, base=base, noise=0.28)
+        base = q if base is None else base
+        before = cache.position_ids[0].cpu().clone()
+        k_before = cache.k_cache_buffer[0].cpu().clone()
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, lay.n_landmarks, dtype=torch.bfloat16, device=cuda)
+        cache.update_kv_cache(kn.to(cuda), vn.to(cuda), 0)
+        pid = cache.get_retrieval_position_ids(0, q.to(cuda), selected_out=sel, score_out=score)
+        cache.get_value_cache(0, pid)
+        cache.get_key_cache(0, pid, None, cs)
+        out = cache.attention(0, q.to(cuda))
+        torch.cuda.synchronize()
+        after, cnts = cache.position_ids[0].cpu(), cache.cnts.cpu()
+        offs = cache.offsets.cpu().view(B * H, S)
+        vbuf, kbuf = cache.v_cache_buffer[0].cpu(), cache.k_cache_buffer[0].cpu()
+        for h in range(H):
+            own = score[0, h].float().cpu()
+            rule = torch.sort(own, descending=True, stable=True).indices[:S].sort().values
+            assert torch.equal(sel[0, h].cpu(), lm_idx[0, h][rule]), "selection is not top-S / lowest index of the scores"
+            new_set = set(sel[0, h].tolist())
+            assert set(after[0, h].tolist()) == new_set
+            hit = torch.tensor([int(x) in new_set for x in before[0, h].tolist()])
+            assert int(hit.sum()) == int(cnts[h]) and torch.equal(after[0, h][hit], before[0, h][hit])
+            assert torch.equal(vbuf[0, h, ss:ss + S * C].reshape(S, -1), v_host[0, h, after[0, h]]), "V slot bytes"
+            kk = kbuf[0, h, ss:ss + S * C].reshape(S, C, -1)
+            assert torch.equal(kk[hit], k_before[0, h, ss:ss + S * C].reshape(S, C, -1)[hit]), "a hit slot's K changed"
+            miss_ids = after[0, h][~hit]
+            if len(miss_ids):
+                want = O.rebuild_keys(U, SV[:, h:h + 1], miss_ids.view(1, 1, -1), cs_cpu)[0, 0].reshape(-1, C, 128)
+                assert_rope_rows_close(kk[~hit], want, frac_exact=0.90, what="rebuilt K at full size")
+            assert torch.equal(offs[h, :S - int(cnts[h])].long(), (~hit).nonzero().flatten())
+        L_att = lay.sparse_end + step + 1
+        assert torch.equal(kbuf[:, :, L_att - 1], kn[:, :, 0]) and torch.equal(vbuf[:, :, L_att - 1], vn[:, :, 0])
+        assert_close_bf16(out, O.attention(q, kbuf[:, :, :L_att], vbuf[:, :, :L_att]), max_abs=8e-3,
+                          what="attention at full size")
+        if step:
+            assert float(cnts.float().mean()) / S > 0.4, "correlated queries should hit the chunk cache"
