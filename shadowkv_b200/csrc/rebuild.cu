@@ -37,13 +37,14 @@ struct RebuildParams {
   int tile_skip;             // 1: skip by whole tiles like the reference and write every row of a kept tile
 };
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
     rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sv,
                            RebuildParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sA = smem;                                   // n_slabs x 16 KiB
-  unsigned char *sB = smem + kMaxSlabs * kSlabBytesA;         // n_slabs x 16 KiB
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kMaxSlabs * (kSlabBytesA + kSlabBytesB));
+  // sized by the slabs the rank needs (rank 160 -> 3 slabs -> 96 KiB, two CTAs per SM), not by the maximum
+  unsigned char *sB = smem + p.n_slabs * kSlabBytesA;         // n_slabs x 16 KiB
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + p.n_slabs * (kSlabBytesA + kSlabBytesB));
   uint64_t *mma_bar = full_bar + kMaxSlabs;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 1);
   int *s_ids = reinterpret_cast<int *>(tmem_slot + 2);        // [16] chunk id per tile row group (-1: skip)
@@ -318,9 +319,9 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
   if (rc) return rc;
   rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim, kSlabCols);
   if (rc) return rc;
-  const int smem = kMaxSlabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  const int smem = p.n_slabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
+  static int attr = 0;
+  if (smem > attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
   dim3 grid((p.S + kTileChunks - 1) / kTileChunks, BH);
   rebuild_tcgen05_kernel<<<grid, 128, smem, st>>>(map_u, map_sv, p);
   return launch_status("rebuild_tcgen05_kernel");
