@@ -134,7 +134,8 @@ def test_uncached_variant_token_ids(cuda):
 
 
 @pytest.mark.parametrize("model,B,prompt_len,budget", [("llama-3.1-8b", 2, 8192, 1024), ("glm-4-9b-1m", 1, 8192, 1024),
-                                                       ("llama-3.1-8b", 1, 32768, 2048)])
+                                                       ("llama-3.1-8b", 1, 32768, 2048), ("yi-9b-200k", 1, 16384, 4096),
+                                                       ("llama-3.1-8b", 1, 32768, 8192)])
 def test_inplace_table_matches_oracle_modulo_slot_order(cuda, model, B, prompt_len, budget):
     """table_mode="inplace" (the default product path): chunk-cache hits keep their slots and the i-th missed
     chunk (ascending id) takes the i-th freed slot.  Against the oracle (reference slot order) that must give:

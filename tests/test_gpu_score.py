@@ -67,7 +67,12 @@ def _select(cuda, shape, N, S, seed, glm=False):
 
 @pytest.mark.parametrize("model,N,S", [("llama-3.1-8b", 4044, 256), ("glm-4-9b-1m", 2040, 128),
                                        ("llama-3.1-8b", 15560, 256), ("yi-9b-200k", 3000, 512),
-                                       ("llama-3.1-8b", 1024, 1024)])
+                                       ("llama-3.1-8b", 1024, 1024),
+                                       # more than 2048 landmarks per CTA of the selection cluster (several rounds):
+                                       ("llama-3-8b-1m", 65480, 256),      # cfg3: 512K context
+                                       ("yi-9b-200k", 25544, 256),         # cfg5: 200K context, G = 8
+                                       ("glm-4-9b-1m", 16328, 256),        # cfg4: 128K context, G = 8
+                                       ("llama-3.1-8b", 20004, 1024), ("llama-3.1-8b", 16388, 512)])
 def test_select_chunks(cuda, model, N, S):
     shape = synth.MODELS[model]
     q, lm, idx, resident, new_res, off, cnt, sel, score = _select(cuda, shape, N, S, seed=N + S)
