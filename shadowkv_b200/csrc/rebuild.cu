@@ -303,6 +303,34 @@ int make_tensor_map_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64
   return SKV_OK;
 }
 
+// 4-D map over a K / V cache view for the attention kernel (attention_mma.cu): dims {128, rows, heads, batch},
+// strides in elements, box {64 dims, 64 rows, 1, 1}, 128-byte swizzle, zero OOB fill.
+int make_tensor_map_kv(CUtensorMap *out, const void *base, uint64_t rows, uint64_t heads, uint64_t batch, int64_t stride_row,
+                       int64_t stride_h, int64_t stride_b) {
+  typedef std::tuple<const void *, uint64_t, uint64_t, uint64_t, int64_t, int64_t, int64_t> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  Key key(base, rows, heads, batch, stride_row, stride_h, stride_b);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return SKV_OK; }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SKV_ERR_DRIVER; }
+  cuuint64_t dims[4] = {cuuint64_t(kHeadDim), rows, heads, batch};
+  cuuint64_t strides[3] = {cuuint64_t(stride_row) * 2, cuuint64_t(stride_h) * 2, cuuint64_t(stride_b) * 2};
+  cuuint32_t box[4] = {64, 64, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (kv view) failed (%d)", int(r)); return SKV_ERR_DRIVER; }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return SKV_OK;
+}
+
 static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p, int B, int impl, cudaStream_t st) {
   const int BH = B * p.H;
   if (p.R % 8 || p.R < 8 || p.R > kMaxSlabs * kSlabCols) { set_error("rebuild: rank %d unsupported", p.R); return SKV_ERR_UNSUPPORTED; }
