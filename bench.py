@@ -45,7 +45,7 @@ UNIT = "tokens/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--steps", type=int, default=192)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="llama-3.1-8b")
@@ -93,7 +93,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=self.f,
+                                          "-i", str(self.index), "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None

@@ -11,7 +11,7 @@
 namespace skv {
 
 constexpr int kAmTileKeys = 64;
-constexpr int kAmStages = 4;
+constexpr int kAmMaxStages = 4;                          // ring depth is chosen per launch (2..4)
 constexpr int kAmSlabBytes = kAmTileKeys * 128;          // 64 keys x 64 dims (128 B), swizzled
 constexpr int kAmTileBytes = 4 * kAmSlabBytes;           // K lo, K hi, V lo, V hi = 32 KiB
 constexpr int kAmConsumers = 4;                          // warps; each owns 16 keys of a tile
@@ -28,6 +28,8 @@ struct AttnMmaParams {
   int *counters;            // [B*H]
   const int32_t *kv_len_dev;
   int H, G, Gp, kv_len, keys_per_split, num_splits;
+  int stages;               // ring depth of this launch
+  int o_rows;               // head rows of the per-warp staging: 8 when G <= 8, else 16
   float scale_log2;
 };
 
@@ -62,14 +64,14 @@ __global__ void __launch_bounds__(kAmThreads, 1)
     attention_mma_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                          AttnMmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *ring = smem;                                                  // kAmStages x 32 KiB
-  float *s_o = reinterpret_cast<float *>(smem + kAmStages * kAmTileBytes);      // [4 warps][16 heads][128]
-  float *s_ml = s_o + kAmConsumers * kAmHeads * kAmOStride;                     // [4][16][2]
+  unsigned char *ring = smem;                                                  // p.stages x 32 KiB
+  float *s_o = reinterpret_cast<float *>(smem + p.stages * kAmTileBytes);       // [4 warps][o_rows heads][132]
+  float *s_ml = s_o + kAmConsumers * p.o_rows * kAmOStride;                     // [4][16][2]
   float *s_f = s_ml + kAmConsumers * kAmHeads * 2;                              // [64 splits][16 heads]
   float *s_L = s_f + kAmMaxSplits * kAmHeads;                                   // [16]
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_L + kAmHeads);
-  uint64_t *empty_bar = full_bar + kAmStages;
-  int *s_last = reinterpret_cast<int *>(empty_bar + kAmStages);
+  uint64_t *empty_bar = full_bar + kAmMaxStages;
+  int *s_last = reinterpret_cast<int *>(empty_bar + kAmMaxStages);
 
   pdl_launch_dependents();
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(kAmThreads, 1)
   const int G = p.G;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kAmStages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], kAmConsumers); }
+    for (int s = 0; s < p.stages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], kAmConsumers); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
@@ -93,8 +95,8 @@ __global__ void __launch_bounds__(kAmThreads, 1)
   if (warp == kAmConsumers) {
     // ===== TMA producer =====
     if (lane == 0) {
+      int stage = 0, ph = 0;
       for (int t = 0; t < n_tiles; ++t) {
-        const int stage = t % kAmStages, ph = (t / kAmStages) & 1;
         mbarrier_wait(&empty_bar[stage], ph ^ 1);
         mbarrier_expect_tx(&full_bar[stage], kAmTileBytes);
         unsigned char *dst = ring + stage * kAmTileBytes;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(kAmThreads, 1)
         tma_load_4d(dst + kAmSlabBytes, &map_k, 64, row0, h, b, &full_bar[stage]);
         tma_load_4d(dst + 2 * kAmSlabBytes, &map_v, 0, row0, h, b, &full_bar[stage]);
         tma_load_4d(dst + 3 * kAmSlabBytes, &map_v, 64, row0, h, b, &full_bar[stage]);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     }
   } else {
@@ -131,8 +134,8 @@ __global__ void __launch_bounds__(kAmThreads, 1)
     const int k_key = warp * 16 + (lm_m >> 1) * 8 + lm_r;    // K (non-transposed): matrices (keys lo|hi) x (dims lo8|hi8)
     const int v_key = warp * 16 + (lm_m & 1) * 8 + lm_r;     // V (transposed):     matrices (dims lo8|hi8) x (keys lo|hi)
 
+    int stage = 0, ph = 0;
     for (int t = 0; t < n_tiles; ++t) {
-      const int stage = t % kAmStages, ph = (t / kAmStages) & 1;
       const int key0 = k_begin + t * kAmTileKeys + warp * 16;            // first key of this warp's slice
       mbarrier_wait(&full_bar[stage], ph);
       if (key0 < k_end) {                                                // warp uniform
@@ -186,15 +189,16 @@ __global__ void __launch_bounds__(kAmThreads, 1)
       }
       __syncwarp();
       if (lane == 0) mbarrier_arrive(&empty_bar[stage]);
+      if (++stage == p.stages) { stage = 0; ph ^= 1; }
     }
     // ---- per-warp result to shared memory ---------------------------------------------------------------
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-    float *wo = s_o + warp * kAmHeads * kAmOStride;
+    float *wo = s_o + warp * p.o_rows * kAmOStride;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       *reinterpret_cast<float2 *>(wo + g * kAmOStride + j * 8 + tig * 2) = make_float2(o[j][0], o[j][1]);
-      *reinterpret_cast<float2 *>(wo + (g + 8) * kAmOStride + j * 8 + tig * 2) = make_float2(o[j][2], o[j][3]);
+      if (p.o_rows > 8) *reinterpret_cast<float2 *>(wo + (g + 8) * kAmOStride + j * 8 + tig * 2) = make_float2(o[j][2], o[j][3]);
     }
     if (tig == 0) {
       s_ml[(warp * kAmHeads + g) * 2] = m_lo; s_ml[(warp * kAmHeads + g) * 2 + 1] = l_lo;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(kAmThreads, 1)
       const float mw = s_ml[(w * kAmHeads + hq) * 2];
       const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - m);
       l += s_ml[(w * kAmHeads + hq) * 2 + 1] * f;
-      acc += s_o[(w * kAmHeads + hq) * kAmOStride + d] * f;
+      acc += s_o[(w * p.o_rows + hq) * kAmOStride + d] * f;
     }
     if (p.num_splits == 1) {
       p.out[(size_t(b) * p.H * G + size_t(h) * G + hq) * kHeadDim + d] = f32_to_bf16_bits(acc / l);
@@ -339,12 +343,18 @@ int launch_attention_mma(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
   p.part_o = reinterpret_cast<float *>(w);
   p.part_ml = p.part_o + rows * kAmMaxSplits * p.Gp * kHeadDim;
   p.counters = reinterpret_cast<int *>(p.part_ml + rows * kAmMaxSplits * p.Gp * 2);
-  const int smem = kAmStages * kAmTileBytes + (kAmConsumers * kAmHeads * (kAmOStride + 2) + kAmMaxSplits * kAmHeads + kAmHeads) * 4 +
-                   2 * kAmStages * 8 + 16 + 64;
-  static bool attr = false;
-  if (!attr) {
+  // Ring depth: no deeper than the tiles a CTA streams (2..4).  With a short ring (batch 1: 3 tiles) the CTA leaves
+  // room on its SM for one scoring CTA of the next layer, which then streams its landmarks behind this kernel
+  // (programmatic dependent launch).
+  const int tiles_per_cta = (kps + kAmTileKeys - 1) / kAmTileKeys;        // tiles are cut from the split's first key
+  p.stages = tiles_per_cta < 2 ? 2 : (tiles_per_cta > kAmMaxStages ? kAmMaxStages : tiles_per_cta);
+  p.o_rows = q_groups <= 8 ? 8 : 16;
+  const int smem = p.stages * kAmTileBytes + (kAmConsumers * p.o_rows * kAmOStride + kAmConsumers * kAmHeads * 2 +
+                                             kAmMaxSplits * kAmHeads + kAmHeads) * 4 + 2 * kAmMaxStages * 8 + 16 + 64;
+  static int attr = 0;
+  if (smem > attr) {
     cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
+    attr = smem;
   }
   cudaError_t e = launch_kernel(attention_mma_kernel, dim3(ns, kv_heads, batch), dim3(kAmThreads), smem, st, /*pdl=*/false,
                                 map_k, map_v, p);
