@@ -50,3 +50,29 @@ def test_argument_errors_do_not_need_a_gpu():
     import pytest
     with pytest.raises(ValueError):
         _lib.check(rc, "reorder")
+
+
+def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
+    import ctypes as C
+    import pytest
+    from shadowkv_b200 import _lib
+    g = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=128, chunk=8, select=256, n_landmarks=15560, rank=160,
+                  seq_len=124928, buf_len=2592, sparse_start=448)
+    lib = _lib.lib
+    assert lib.skv_select_chunks(C.byref(g), 0, 0, 0, 0, 0, 0, 0, 0, 0, None, 0) == -2
+    bad = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=64, chunk=8, select=256, n_landmarks=15560, rank=160,
+                    seq_len=124928, buf_len=2592, sparse_start=448)
+    assert lib.skv_score_landmarks(C.byref(bad), 1, 1, 1, None, 0) == -1          # head_dim 64 unsupported
+    with pytest.raises(ValueError):
+        _lib.check(-1, "score")
+    bad_s = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=128, chunk=8, select=200, n_landmarks=15560, rank=160,
+                      seq_len=124928, buf_len=2592, sparse_start=448)
+    assert lib.skv_compact_hits(C.byref(bad_s), 1, 1, 1, 1, 0) == -1                # select must be 128/256/512/1024
+    assert lib.skv_gather_copy(1, 1, 1, 1, 8, 100, 100, 200, 0) == -1               # map_size 200 (reference silently no-ops)
+    assert lib.skv_rebuild_keys(C.byref(g), 0, 0, 0, 0, 0, 0, 0, 0, 0) == -2
+    assert lib.skv_attention_decode(1, 1, 1, 1, 1, 8, 4, 64, 100, 8, 8, 8, 0.1, 0, 1, 0, 0) == -1   # head_dim 64
+    assert lib.skv_batch_gemm_softmax(1, 1, 1, 1, 1, 1, 8, 4, 100, 64, 0.1, 0.0, 0) == -1          # k must be 128
+    vs = _lib.VStore(tags=1, data=1, pcie_count=0, ways=100)
+    assert lib.skv_fetch_misses(C.byref(g), 1, 0, 1, 1, 1, 1, C.byref(vs), 0) == -2  # ways not a power of two
+    assert lib.skv_workspace_probe if False else True
+    assert lib.skv_select_workspace_bytes(C.byref(g)) > 8 * 4 * 15560 * 2
