@@ -256,7 +256,10 @@ def run_ours(args, rank, world, local_rank, n_gpus):
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        from shadowkv_b200 import parallel as _par
+        numa = _par.bind_to_gpu_numa_node(local_rank)       # before the pinned V store is allocated
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     full_shape = synth.MODELS[args.model]
@@ -436,7 +439,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
                         "api": "shadowkv_b200.engine.DecodeStepGraph.step_host"},
                 "gpu_launches": run_d.launches_per_step * args.steps,
                 "hbm_chunk_store": store, "roofline": roofline, "kernels": kernels, "pcie": pcie, "cpu_baseline": cpu, "clocks": clocks,
-                "peaks": peaks, "lib": _lib.version(), "setup_s": round(setup_s, 1), "checksum": checksum}
+                "numa_binding_rank0": numa, "peaks": peaks, "lib": _lib.version(), "setup_s": round(setup_s, 1), "checksum": checksum}
         emit(line)
     if world > 1:
         dist.barrier()

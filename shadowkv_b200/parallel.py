@@ -16,6 +16,31 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, BEFORE the pinned V store is
+    allocated: pinned pages are placed by first touch, and the V fetch reads them over that GPU's PCIe link -- with
+    several ranks on a multi-socket host a store on the wrong socket crosses the inter-socket fabric and the ranks
+    contend for it.  Best effort: returns what it found ({"node": n, "cpus": k} or {"node": None, "why": ...})."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"node": None, "why": "device reports no NUMA node (single-node host)"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"node": node, "why": "no allowed CPU on that node (cgroup cpuset)"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError) as e:
+        return {"node": None, "why": f"{type(e).__name__}: {e}"}
+
+
 def shard_range(total: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous balanced partition of `total` items: returns (start, count) of `rank`."""
     if not 0 <= rank < world:
