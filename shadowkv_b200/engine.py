@@ -10,10 +10,10 @@ Two public entry points:
   the device INSIDE the replayed graph, and the attention outputs are copied back to pinned host memory
   inside the same graph.  This is the call ``bench.py`` times as ``e2e``.
 
-The graph holds, per layer: score (+ fused append) -> select -> {V miss fetch on the copy stream || tcgen05 K
-rebuild} -> split-K attention, i.e. 5 kernels (7 with table_mode="reference": two hit compactions more), plus
-one counter-advance kernel per token.  The generation offset lives on the device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the
-same graph is valid for every token.
+The graph holds, per layer: score (+ fused append) -> select -> {V miss fetch || tcgen05 K rebuild on the side
+stream} -> split-K attention, i.e. 5 kernels (7 with table_mode="reference": two hit compactions more; +1 with
+the HBM chunk store: its fill), plus one counter-advance kernel per token.  The generation offset lives on the
+device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the same graph is valid for every token.
 """
 from __future__ import annotations
 
@@ -21,7 +21,6 @@ import torch
 
 from . import parallel
 from .kv_cache import ShadowKVCache_CPU
-
 
 
 class DecodeStepGraph:

@@ -4,21 +4,22 @@
  so ``models/base.py:296-341`` can drive it unchanged, but every decode-step
 method lands in the fused sm_100a kernels behind the C ABI:
 
-=============================  =================================================================
+=============================  =====================================================================
 reference method (kv_cache.py)  here
-=============================  =================================================================
-update_kv_cache  (:1227-1271)   ``skv_append_kv``                         (1 launch, was 2 copies)
-get_retrieval_position_ids      ``skv_select_chunks``: scoring + softmax + GQA max + top-k + id
-  (:983-1057)                   gather + chunk-table update               (2 launches, was 8+)
-get_value_cache  (:1059-1106)   ``skv_compact_hits`` (V) + ``skv_fetch_misses`` from pinned host
-get_key_cache    (:1108-1176)   ``skv_compact_hits`` (K) + ``skv_rebuild_keys`` (tcgen05, RoPE in the
-                                epilogue; no bf16 scratch round trip)     (2 launches, was 3)
-=============================  =================================================================
+=============================  =====================================================================
+update_kv_cache  (:1227-1271)   ``skv_append_kv`` (``decode_layer`` fuses it into the scoring launch)
+get_retrieval_position_ids      ``skv_select_chunks``: TMA + tcgen05 scoring, then softmax + GQA max +
+  (:983-1057)                   top-k + id gather + chunk-table update    (2 launches, was 8+)
+get_value_cache  (:1059-1106)   ``skv_fetch_misses`` from pinned host memory (+ ``skv_compact_hits`` only
+                                when ``table_mode="reference"``; optional HBM chunk store)
+get_key_cache    (:1108-1176)   ``skv_rebuild_keys`` (tcgen05, RoPE in the epilogue; no bf16 scratch round
+                                trip; + ``skv_compact_hits`` only in reference table mode)
+(base.py:341 flash-attn call)   ``attention`` / ``shadowkv_b200.attention.flash_attn_with_kvcache``
+=============================  =====================================================================
 
-``decode_layer`` runs the whole per-layer step with the reference's stream choreography
-(``base.py:326-338``: V fetch on ``copy_stream`` overlapped with the K path) and the attention kernel.
-The prefill-side methods (``get_svd``, ``prefill_kv_cache``) build the state with torch ops; they are
-outside the hot path and kept only so the class is usable end to end.
+``decode_layer`` runs the whole per-layer step (score+append -> select -> {V fetch || K rebuild on the side
+stream} -> attention).  The prefill-side methods (``get_svd``, ``prefill_kv_cache``) build the state with torch
+ops; they are outside the hot path and kept only so the class is usable end to end.
 """
 from __future__ import annotations
 

@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
 from ._lib import lib, check
 
 __all__ = [

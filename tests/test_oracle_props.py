@@ -1,7 +1,4 @@
 """Self-consistency of the oracle's floating-point restatement (CPU only, small sizes)."""
-import math
-
-import numpy as np
 import torch
 
 from oracle import shadowkv_oracle as O

@@ -1,5 +1,5 @@
 """Debug aid for the kv-head split under torchrun (2 ranks): eager all-gather, then graph capture, with progress."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import dataclasses
