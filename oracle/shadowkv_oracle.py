@@ -334,11 +334,15 @@ def decode_step(st: LayerState, geo: Geometry, q, k_new, v_new, cos_sin, fused_r
 # (a10) uncached pure-torch variant  models/kv_cache.py:421-470 (ShadowKVCache)
 # --------------------------------------------------------------------------
 def decode_step_uncached(landmarks, landmark_idx, U, SV_rd, v_full, k_buf, v_buf, geo: Geometry,
-                         q, k_new, v_new, rope_fn):
+                         q, k_new, v_new, rope_fn, fp32_accumulate: bool = False, selected_override=None):
     """The batch-1 reference PyTorch path: no chunk cache, everything rebuilt
     every step, selection kept in top-k order.  SV_rd is [B,H,R,D]
     (kv_cache.py:304), v_full [B,H,L,D].  rope_fn(x, token_positions) is the
-    model's apply_rotary_pos_emb_single.  This is what ``--impl reference`` times."""
+    model's apply_rotary_pos_emb_single.  This is what ``--impl reference`` times.
+
+    fp32_accumulate=True (parity tests): the two bf16 contractions are evaluated in fp32 and rounded to bf16
+    once, which is what the reference gets from cuBLAS on the GPU; torch's CPU bf16 einsum may round partial
+    sums, which is fine for timing but not for comparing numbers."""
     B, H, N, D = landmarks.shape
     Hq = q.shape[1]
     G = Hq // H
@@ -349,7 +353,11 @@ def decode_step_uncached(landmarks, landmark_idx, U, SV_rd, v_full, k_buf, v_buf
     k_buf[:, :, pos:pos + 1] = k_new
     v_buf[:, :, pos:pos + 1] = v_new
     # kv_cache.py:425-434
-    attn = torch.einsum('bhgqd,bhdc->bhgqc', q.view(B, H, G, 1, D), landmarks.transpose(2, 3)).squeeze(2) / math.sqrt(128)
+    if fp32_accumulate:
+        attn = (torch.einsum('bhgqd,bhdc->bhgqc', q.view(B, H, G, 1, D).float(), landmarks.transpose(2, 3).float())
+                .to(BF16).squeeze(2) / math.sqrt(128))
+    else:
+        attn = torch.einsum('bhgqd,bhdc->bhgqc', q.view(B, H, G, 1, D), landmarks.transpose(2, 3)).squeeze(2) / math.sqrt(128)
     attn = torch.softmax(attn, dim=-1, dtype=torch.float32).to(BF16)
     attn = attn.sum(dim=-2) if attn.dim() == 5 else attn
     attn = attn.view(B, H, G, N)
@@ -358,17 +366,22 @@ def decode_step_uncached(landmarks, landmark_idx, U, SV_rd, v_full, k_buf, v_buf
     else:
         attn = attn.squeeze(-2)
     top = torch.topk(attn, k=S, dim=-1).indices
-    sel = landmark_idx.gather(-1, top)
+    sel = own_sel = landmark_idx.gather(-1, top)
+    if selected_override is not None:       # parity tests: same chunk set as the path under test (see decode_step)
+        sel = selected_override.to(torch.int64).cpu()
     tok = (sel.unsqueeze(-1) * C + torch.arange(C)).view(B, H, -1)
     # kv_cache.py:449-450
     v_buf[:, :, ss:se] = v_full.gather(-2, tok.unsqueeze(-1).expand(-1, -1, -1, D))
     # kv_cache.py:457-467
     u_exp = U.unsqueeze(1).expand(-1, H, -1, -1)
     U_head = torch.gather(u_exp, 2, tok.unsqueeze(-1).expand(-1, -1, -1, U.shape[-1]))
-    k = torch.einsum('bhrk,bhkd->bhrd', U_head, SV_rd)
+    if fp32_accumulate:
+        k = torch.einsum('bhrk,bhkd->bhrd', U_head.float(), SV_rd.float()).to(BF16)
+    else:
+        k = torch.einsum('bhrk,bhkd->bhrd', U_head, SV_rd)
     k_buf[:, :, ss:se] = rope_fn(k, tok)
     out = attention(q, k_buf[:, :, :pos + 1], v_buf[:, :, :pos + 1])
-    return out, sel
+    return out, own_sel
 
 
 def rope_torch(x, cos_sin, tok):

@@ -317,3 +317,45 @@ def test_full_size_step_properties(cuda):
                           what="attention at full size")
         if step:
             assert float(cnts.float().mean()) / S > 0.4, "correlated queries should hit the chunk cache"
+
+
+def test_forty_steps_against_the_uncached_reference_path(cuda):
+    """Long run without re-synchronising anything: the cached CUDA path (in-place chunk table, K rows kept across
+    steps, V chunks fetched once) against the oracle's restatement of the reference's UNCACHED PyTorch path
+    (kv_cache.py:421-470: everything rebuilt from U.SV and gathered from the full V every step).  The attention
+    output must stay within the bf16 tolerance at every step -- no drift from reusing rebuilt K rows -- and the
+    selected chunk sets may differ only at top-k ties."""
+    from shadowkv_b200.kv_cache import ShadowKVCache_CPU
+    shape = synth.MODELS["llama-3.1-8b"]
+    B, prompt_len, budget, steps = 1, 8192, 1024, 40
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    st = synth.layer_state(shape, B, prompt_len, seed=21, sparse_budget=budget, cos_sin=cs)
+    lay = st["layout"]
+    cache = ShadowKVCache_CPU(shape.config(1), batch_size=B, max_length=prompt_len, device=str(cuda), sparse_budget=budget)
+    synth.install(cache, [st])
+    H, S = shape.num_key_value_heads, lay.select
+    geo = O.Geometry(sparse_start=lay.sparse_start, sparse_end=lay.sparse_end)
+    k_ref, v_ref = st["k_buf"].clone(), st["v_buf"].clone()
+    v_full = st["v_chunks"].view(B, H, -1, 128)
+    SV_rd = st["SV"].transpose(-1, -2).contiguous()                    # [B,H,R,D], kv_cache.py:304
+    rope = lambda x, tok: O.rope_bf16(x.to(torch.bfloat16), cs[tok])   # bf16 RoPE as the CUDA kernels do it
+    d_cs = cs.to(cuda)
+    base, worst, diffs = None, 0.0, 0
+    for step in range(steps):
+        q, kn, vn = synth.queries(shape, B, seed=900 + step, base=base, noise=0.3)
+        base = q if base is None else base
+        geo.gen_offset = step
+        out = cache.decode_layer(0, q.to(cuda), kn.to(cuda), vn.to(cuda), d_cs)
+        torch.cuda.synchronize()
+        got = cache.position_ids[0].cpu()
+        # the oracle attends over OUR chunk set (one boundary chunk of random data moves the output by more than
+        # the tolerance); its own top-k result is compared separately below
+        want, sel_ref = O.decode_step_uncached(st["k_landmark"], st["k_landmark_idx"], st["U"], SV_rd, v_full, k_ref, v_ref,
+                                               geo, q, kn, vn, rope, fp32_accumulate=True, selected_override=got)
+        err, _ = assert_close_bf16(out, want, what=f"step {step} vs uncached reference path")
+        worst = max(worst, err)
+        for h in range(H):
+            diffs += len(set(got[0, h].tolist()) ^ set(sel_ref[0, h].tolist()))
+    assert diffs <= steps * H * 4, f"{diffs} chunk differences over {steps} steps: more than top-k ties explain"
+    assert cache.gen_offset == steps
+    print(f"max-abs over {steps} steps {worst:.4g}, chunk-set differences {diffs}")
