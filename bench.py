@@ -497,7 +497,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     reps = 4 * L
     t_score = timed(score, reps)
     score_bytes = B * (H * N * D * 2 + H * G * D * 2)
-    roofline = {"kernel": "score_tiles_kernel (landmark scoring)", "bound": "hbm",
+    roofline = {"kernel": "score_tcgen05_kernel (landmark scoring, TMA ring + tcgen05)", "bound": "hbm",
                 "achieved": score_bytes / t_score * 1e-3, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": score_bytes / t_score * 1e-3 / peaks["hbm"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 1 / 8 kv heads / 15 560 landmarks,
