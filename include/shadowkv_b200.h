@@ -274,6 +274,33 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
                          int64_t stride_h, int64_t stride_row, float scale, int num_splits, void *workspace,
                          const int32_t *kv_len_dev, skv_stream_t stream);
 
+/* ======================================================================
+ * Part 3 -- prefill-side state build (reference models/kv_cache.py:788-980, ShadowKVCache_CPU.prefill_kv_cache)
+ * ====================================================================== */
+
+/* Per chunk of 8 keys of the post-RoPE prompt keys k (element strides batch / head / row, head_dim 128 contiguous):
+ * means[bh, c, :] = bf16 mean of the chunk (landmark candidate, kv_cache.py:856) and mincos[bh, c] = min over the 8
+ * keys of cosine_similarity(mean, key) (:859-866), with the bf16 rounding points of the torch ops the reference
+ * applies to bf16 tensors. */
+int skv_chunk_stats(const skv_bf16 *k, int batch, int kv_heads, int chunks, int64_t stride_b, int64_t stride_h,
+                    int64_t stride_row, skv_bf16 *means, skv_bf16 *mincos, skv_stream_t stream);
+
+/* Per row (b,h): the n_outliers chunks with the smallest mincos (kv_cache.py:868; ties: lowest chunk index) in
+ * ascending chunk order -> outliers [rows, n_outliers]; all other chunks ascending -> rest_idx
+ * [rows, chunks - n_outliers] (the landmark index, :909-915). */
+int skv_select_outliers(const skv_bf16 *mincos, int rows, int chunks, int n_outliers, int64_t *outliers,
+                        int64_t *rest_idx, skv_stream_t stream);
+
+/* dst[row, i, :] = src[row, idx[row, i], :] for 128-element bf16 rows (landmarks = means[rest_idx], :917-921). */
+int skv_gather_rows(const skv_bf16 *src, const int64_t *idx, skv_bf16 *dst, int rows, int n_src, int n,
+                    skv_stream_t stream);
+
+/* Chunk gather without the map-size restriction of skv_gather_copy: for every row and i < n_ids,
+ *   dst[row*dst_stride + dst_offset + i*1024 ..] <- src[row*src_stride + ids[row*n_ids + i]*1024 ..]
+ * (outlier K/V chunks :870-907, first fill of the sparse region :957-970).  src may be device or pinned host. */
+int skv_gather_chunks(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, int64_t dst_stride, int64_t dst_offset,
+                      const int64_t *ids, int n_ids, int rows, skv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

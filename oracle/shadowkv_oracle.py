@@ -400,3 +400,104 @@ def rope_torch(x, cos_sin, tok):
     o = torch.stack([xr[..., 0::2] * cs[..., :q] - xr[..., 1::2] * cs[..., q:],
                      xr[..., 1::2] * cs[..., :q] + xr[..., 0::2] * cs[..., q:]], -1).flatten(-2)
     return torch.cat((o, xp), dim=-1)
+
+
+# --------------------------------------------------------------------------
+# (f1) prefill-side state build      models/kv_cache.py:788-980 (prefill_kv_cache)
+# --------------------------------------------------------------------------
+def chunk_stats(k_ctx: torch.Tensor):
+    """k_ctx [B,H,chunks,C,D] bf16 (post-RoPE prompt keys, chunked).  Returns (means [B,H,chunks,D] bf16,
+    mincos [B,H,chunks] bf16): the landmark candidates ``k_ctx.mean(dim=-2)`` (kv_cache.py:856) and
+    ``cosine_similarity(mean, key, dim=-1).min(dim=-1)`` (:859-868).
+
+    The reference calls torch ops on bf16 tensors, so every intermediate is rounded to bf16.  The chain below is
+    torch 2.3's ``cosine_similarity`` (ATen/native/Distance.cpp; the version the reference pins,
+    requirements.txt): ``n = linalg_vector_norm(x)`` (fp32 accumulate, bf16 result) -> ``clamp_min(eps=1e-8)`` ->
+    ``(x1 / n1) * (x2 / n2)`` elementwise (each bf16) -> ``sum`` (fp32 accumulate, bf16 result).  It is spelled
+    out in fp32 with explicit roundings so it does not depend on the torch version installed here;
+    tests/test_oracle_props.py checks it against ``torch.nn.functional.cosine_similarity`` of this image."""
+    x = k_ctx.float()
+    means = (x.sum(dim=-2) * (1.0 / k_ctx.shape[-2])).to(BF16)
+    m = means.float().unsqueeze(-2)
+
+    def norm(t):
+        return t.pow(2).sum(dim=-1, keepdim=True).sqrt().to(BF16).float().clamp_min(1e-8)
+
+    a = (m / norm(m)).to(BF16).float()
+    b = (x / norm(x)).to(BF16).float()
+    cos = (a * b).to(BF16).float().sum(dim=-1).to(BF16)
+    return means, cos.float().min(dim=-1).values.to(BF16)
+
+
+def select_outliers(mincos: torch.Tensor, n_out: int):
+    """mincos [B,H,chunks] bf16 -> (outliers [B,H,n_out] ascending, rest_idx [B,H,chunks-n_out] ascending).
+    ``topk(largest=False)`` (kv_cache.py:868) with ties resolved to the lowest chunk index; the reference keeps
+    the outliers in top-k order, which only permutes rows of the attention buffer."""
+    order = torch.sort(mincos.float(), dim=-1, descending=False, stable=True).indices
+    out = order[..., :n_out].sort(dim=-1).values
+    keep = torch.ones_like(mincos, dtype=torch.bool)
+    keep.scatter_(-1, out, False)
+    B, H, n = mincos.shape
+    rest = torch.arange(n).expand(B, H, n)[keep].view(B, H, n - n_out)
+    return out, rest
+
+
+def prefill_state(k_roped: torch.Tensor, v: torch.Tensor, last_q: torch.Tensor, *, budget: int = 2048, chunk: int = 8,
+                  local_chunk: int = 4, buf_len: int | None = None, outliers_override=None, selected_override=None):
+    """One layer of ShadowKVCache_CPU.prefill_kv_cache (kv_cache.py:788-980) for k_roped, v [B,H,L,D] bf16 and the
+    prompt's last query last_q [B,Hq,D].  Returns a dict with the host V store, the K/V buffers, landmarks, landmark
+    index, outlier and selected chunk ids."""
+    B, H, L, D = v.shape
+    n_out = (budget // 1024) * 24                                            # :548
+    chunks = L // chunk - local_chunk
+    chunks -= chunks % 8                                                     # :836
+    prefill_local = L - chunks * chunk
+    ss = prefill_local + n_out * chunk
+    se = ss + budget
+    buf_len = buf_len or budget + 128 + (n_out + local_chunk) * chunk        # :574
+    S = budget // chunk
+    v_store = v[:, :, :(L // chunk) * chunk].reshape(B, H, L // chunk, chunk * D).clone()      # :819-823
+    k_buf = torch.zeros(B, H, buf_len, D, dtype=BF16)
+    v_buf = torch.zeros(B, H, buf_len, D, dtype=BF16)
+    k_buf[:, :, :prefill_local] = k_roped[:, :, -prefill_local:]             # :842-844
+    v_buf[:, :, :prefill_local] = v[:, :, -prefill_local:]
+    k_ctx = k_roped[:, :, :chunks * chunk].view(B, H, chunks, chunk, D)
+    v_ctx = v[:, :, :chunks * chunk].view(B, H, chunks, chunk, D)
+    means, mincos = chunk_stats(k_ctx)
+    outliers, rest = select_outliers(mincos, n_out)
+    own_outliers = outliers
+    if outliers_override is not None:
+        outliers = outliers_override.cpu().sort(dim=-1).values
+        keep = torch.ones(B, H, chunks, dtype=torch.bool)
+        keep.scatter_(-1, outliers, False)
+        rest = torch.arange(chunks).expand(B, H, chunks)[keep].view(B, H, chunks - n_out)
+    ex = outliers[..., None, None].expand(-1, -1, -1, chunk, D)
+    k_buf[:, :, prefill_local:ss] = k_ctx.gather(2, ex).reshape(B, H, -1, D)  # :870-907
+    v_buf[:, :, prefill_local:ss] = v_ctx.gather(2, ex).reshape(B, H, -1, D)
+    landmarks = means.gather(2, rest.unsqueeze(-1).expand(-1, -1, -1, D))     # :917-921
+    # first fill of the sparse region with the prompt's last query (:926-970)
+    G = last_q.shape[1] // H
+    _, soft = landmark_scores(last_q.view(B, H * G, 1, D), landmarks)
+    selected, _, _ = select_chunks(soft, rest, S)
+    own_selected = selected
+    if selected_override is not None:
+        selected = selected_override.cpu()
+    tok = (selected.unsqueeze(-1) * chunk + torch.arange(chunk)).view(B, H, -1)
+    exs = tok.unsqueeze(-1).expand(-1, -1, -1, D)
+    v_buf[:, :, ss:se] = v.gather(-2, exs)
+    k_buf[:, :, ss:se] = k_roped.gather(-2, exs)
+    return dict(v_store=v_store, k_buf=k_buf, v_buf=v_buf, means=means, mincos=mincos, outliers=outliers,
+                own_outliers=own_outliers, rest_idx=rest, landmarks=landmarks, selected=selected,
+                own_selected=own_selected, prefill_local=prefill_local, sparse_start=ss, sparse_end=se, chunks=chunks)
+
+
+def low_rank_factors(k_pre: torch.Tensor, rank: int, H: int):
+    """get_svd (kv_cache.py:666-737): k_pre [B,L,H*D] pre-RoPE keys -> U [B,L,rank] bf16, SV [B,H,D,rank] bf16 from
+    the rank-truncated SVD in fp32.  Singular vectors are defined up to sign (and rotation inside repeated
+    singular values), so parity is on the product U.SV, never on the factors."""
+    u, s, vh = torch.linalg.svd(k_pre.float(), full_matrices=False)
+    B = k_pre.shape[0]
+    U = u[:, :, :rank].to(BF16)
+    sv = (s[:, :rank, None] * vh[:, :rank]).to(BF16)                          # [B, rank, H*D]
+    SV = sv.view(B, rank, H, -1).permute(0, 2, 3, 1).contiguous()
+    return U, SV

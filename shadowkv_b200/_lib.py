@@ -61,6 +61,10 @@ _SIGS = {
     "skv_fetch_misses": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, C.POINTER(VStore), _p],
     "skv_vstore_fill": [C.POINTER(Geom), _p, _p, _p, _p, C.POINTER(VStore), _p],
     "skv_rebuild_keys": [C.POINTER(Geom)] + [_p] * 7 + [_i, _p],
+    "skv_chunk_stats": [_p, _i, _i, _i, _l, _l, _l, _p, _p, _p],
+    "skv_select_outliers": [_p, _i, _i, _i, _p, _p, _p],
+    "skv_gather_rows": [_p, _p, _p, _i, _i, _i, _p],
+    "skv_gather_chunks": [_p, _l, _p, _l, _l, _p, _i, _i, _p],
     "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
 }

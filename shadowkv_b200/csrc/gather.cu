@@ -295,6 +295,14 @@ int skv_gather_copy(const skv_bf16 *values, skv_bf16 *v_cache_buffer, const int6
                                batch_size * heads, map_size, as_stream(stream));
 }
 
+int skv_gather_chunks(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, int64_t dst_stride, int64_t dst_offset,
+                      const int64_t *ids, int n_ids, int rows, skv_stream_t stream) {
+  if (!src || !dst || !ids) { set_error("gather_chunks: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (n_ids < 1 || rows < 1) return SKV_OK;
+  return launch_fetch<int64_t>(src, src_stride, dst, dst_stride, dst_offset, ids, nullptr, nullptr, rows, n_ids,
+                               as_stream(stream));
+}
+
 int skv_gather_copy_d2d_with_offsets(skv_bf16 *keys, const int32_t *offsets, const int32_t *cnts, int batch_size,
                                      int heads, int gpu_k_length, int gpu_k_offset, int gpu_k_stride, int map_size,
                                      skv_stream_t stream) {

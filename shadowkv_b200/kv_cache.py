@@ -53,6 +53,7 @@ class ShadowKVCache_CPU:
         if table_mode not in ("inplace", "reference"):
             raise ValueError("table_mode must be 'inplace' or 'reference'")
         self.table_mode = table_mode
+        self.svd_method = "gram"     # "svd": the reference's full torch.svd (kv_cache.py:711)
         self.config = config
         self.batch_size = batch_size
         self.max_length = max_length
@@ -204,7 +205,12 @@ class ShadowKVCache_CPU:
     # prefill side (torch ops; outside the hot path)
     # ------------------------------------------------------------------------------------------
     def get_svd(self, new_k_cache, layer_idx):
-        """Rank-`rank` factorisation of the pre-RoPE keys (kv_cache.py:666-737)."""
+        """Rank-`rank` factorisation of the pre-RoPE keys (kv_cache.py:666-737): U [L, rank], SV [H, D, rank].
+        The reference runs a full fp32 torch.svd of the [L, H*D] key matrix.  Here (svd_method="gram", default) the
+        right singular vectors come from the eigen-decomposition of the H*D x H*D Gram matrix K^T K -- one GEMM
+        over the keys and a 1024 x 1024 symmetric eigensolve instead of an SVD of a 124928 x 1024 matrix -- and
+        U = K V / sigma.  Same subspace and the same product U.SV up to fp32 rounding; the factors themselves are
+        only defined up to sign.  svd_method="svd" keeps the reference's call."""
         if new_k_cache.shape[1] <= 32:
             k = new_k_cache.transpose(1, 2).reshape(new_k_cache.shape[0], -1, self.num_key_value_heads * self.head_dim)
         else:
@@ -214,11 +220,21 @@ class ShadowKVCache_CPU:
             self.U = torch.zeros(self.num_layers, self.batch_size, L, self.rank, dtype=self.dtype, device="cpu")
             self.SV = torch.zeros(self.num_layers, self.batch_size, self.num_key_value_heads, self.head_dim,
                                   self.rank, dtype=self.dtype, device="cpu")
-        u, s, vh = torch.linalg.svd(k.float(), full_matrices=False)
+        kf = k.float()
+        if self.svd_method == "gram":
+            gram = kf.transpose(1, 2) @ kf                                           # [bsz, HD, HD] fp32
+            evals, evecs = torch.linalg.eigh(gram)                                   # ascending
+            top = evecs[:, :, -self.rank:].flip(-1)                                  # [bsz, HD, rank], largest first
+            sigma = evals[:, -self.rank:].flip(-1).clamp_min(0).sqrt()               # [bsz, rank]
+            u = (kf @ top) / sigma.clamp_min(1e-20).unsqueeze(1)                     # [bsz, L, rank]
+            sv = sigma.unsqueeze(-1) * top.transpose(1, 2)                           # [bsz, rank, HD]
+        else:
+            uu, ss, vh = torch.linalg.svd(kf, full_matrices=False)
+            u = uu[:, :, :self.rank]
+            sv = ss[:, :self.rank, None] * vh[:, :self.rank]
         sl = slice(self.prefilled_batch, self.prefilled_batch + bsz)
-        self.U[layer_idx][sl].copy_(u[:, :, :self.rank].to(self.dtype))
-        sv = (s[:, :self.rank, None] * vh[:, :self.rank]).to(self.dtype)             # [bsz, rank, H*D]
-        sv = sv.view(bsz, self.rank, self.num_key_value_heads, self.head_dim).permute(0, 2, 3, 1)
+        self.U[layer_idx][sl].copy_(u.to(self.dtype))
+        sv = sv.to(self.dtype).view(bsz, self.rank, self.num_key_value_heads, self.head_dim).permute(0, 2, 3, 1)
         self.SV[layer_idx][sl].copy_(sv)                                             # [bsz, H, D, rank]
 
     def register_k_landmark(self, k_landmark, k_landmark_idx, layer_idx):
@@ -234,46 +250,63 @@ class ShadowKVCache_CPU:
         self.k_landmark[layer_idx][sl].copy_(k_landmark)
         self.k_landmark_idx[layer_idx][sl].copy_(k_landmark_idx)
 
-    def prefill_kv_cache(self, new_v_cache, layer_idx, key_states_roped, last_query_states=None):
-        """Builds one layer of decode state from the prompt's K/V (kv_cache.py:788-980)."""
+    def prefill_kv_cache(self, new_v_cache, layer_idx, key_states_roped, last_query_states=None, outliers_out=None):
+        """Builds one layer of decode state from the prompt's K/V (kv_cache.py:788-980).  The chunk statistics
+        (bf16 chunk means, min cosine similarity per chunk), the outlier / landmark split, the landmark compaction
+        and all chunk gathers run in the CUDA kernels of csrc/prefill.cu and csrc/gather.cu; the first fill of the
+        sparse region reuses the decode path's scoring + selection kernels.  outliers_out (optional int64
+        [bsz,H,outlier_chunk]) receives the outlier chunk ids (tests)."""
         bsz, H, incoming, D = new_v_cache.shape
         C_ = self.chunk_size
         self._set_layout(incoming)
         sl = slice(self.prefilled_batch, self.prefilled_batch + bsz)
+        st = _cs()
         n_chunks_all = incoming // C_
         self.v_cache_cpu[layer_idx][sl, :, :n_chunks_all].copy_(
             new_v_cache[:, :, :self.max_ctx_chunks_len].reshape(bsz, H, n_chunks_all, C_ * D), non_blocking=True)
+        kb, vb = self.k_cache_buffer[layer_idx][sl], self.v_cache_buffer[layer_idx][sl]
         # local window = the tail of the prompt
-        self.k_cache_buffer[layer_idx][sl, :, :self.prefill_local].copy_(key_states_roped[:, :, -self.prefill_local:])
-        self.v_cache_buffer[layer_idx][sl, :, :self.prefill_local].copy_(new_v_cache[:, :, -self.prefill_local:])
+        kb[:, :, :self.prefill_local].copy_(key_states_roped[:, :, -self.prefill_local:])
+        vb[:, :, :self.prefill_local].copy_(new_v_cache[:, :, -self.prefill_local:])
 
-        n = self.chunks
-        k_ctx = key_states_roped[:, :, :n * C_].view(bsz, H, n, C_, D)
-        v_ctx = new_v_cache[:, :, :n * C_].view(bsz, H, n, C_, D)
-        means = k_ctx.mean(dim=-2)
-        cos = torch.nn.functional.cosine_similarity(means.unsqueeze(3).expand(-1, -1, -1, C_, -1), k_ctx, dim=-1)
-        outlier = cos.min(dim=-1).values.topk(self.outlier_chunk, largest=False).indices        # [bsz,H,o]
-        ex = outlier[..., None, None].expand(-1, -1, -1, C_, D)
-        lo, hi = self.prefill_local, self.sparse_start
-        self.k_cache_buffer[layer_idx][sl, :, lo:hi].copy_(k_ctx.gather(2, ex).reshape(bsz, H, -1, D))
-        self.v_cache_buffer[layer_idx][sl, :, lo:hi].copy_(v_ctx.gather(2, ex).reshape(bsz, H, -1, D))
-
-        keep = torch.ones(bsz, H, n, dtype=torch.bool, device=means.device)
-        keep.scatter_(-1, outlier, False)
-        rest_idx = torch.arange(n, device=means.device).expand(bsz, H, -1)[keep].view(bsz, H, -1)
-        lm = means.gather(2, rest_idx.unsqueeze(-1).expand(-1, -1, -1, D))
+        n, n_out = self.chunks, self.outlier_chunk
+        k = key_states_roped if key_states_roped.is_contiguous() else key_states_roped.contiguous()
+        v = new_v_cache if new_v_cache.is_contiguous() else new_v_cache.contiguous()
+        means = torch.empty(bsz, H, n, D, dtype=self.dtype, device=k.device)
+        mincos = torch.empty(bsz, H, n, dtype=self.dtype, device=k.device)
+        check(lib.skv_chunk_stats(k.data_ptr(), bsz, H, n, k.stride(0), k.stride(1), k.stride(2), means.data_ptr(),
+                                  mincos.data_ptr(), st), "chunk_stats")
+        outliers = torch.empty(bsz, H, n_out, dtype=torch.int64, device=k.device)
+        rest_idx = torch.empty(bsz, H, n - n_out, dtype=torch.int64, device=k.device)
+        check(lib.skv_select_outliers(mincos.data_ptr(), bsz * H, n, n_out, outliers.data_ptr(), rest_idx.data_ptr(), st),
+              "select_outliers")
+        if outliers_out is not None:
+            outliers_out.copy_(outliers)
+        buf_stride = self.buf_len * D
+        for src, dst in ((k, kb), (v, vb)):             # outlier chunks, exact K and V (kv_cache.py:870-907)
+            check(lib.skv_gather_chunks(src.data_ptr(), src.stride(1), dst.data_ptr(), buf_stride, self.prefill_local * D,
+                                        outliers.data_ptr(), n_out, bsz * H, st), "gather_chunks(outliers)")
+        lm = torch.empty(bsz, H, n - n_out, D, dtype=self.dtype, device=k.device)
+        check(lib.skv_gather_rows(means.data_ptr(), rest_idx.data_ptr(), lm.data_ptr(), bsz * H, n, n - n_out, st),
+              "gather_rows")
         self.register_k_landmark(lm, rest_idx, layer_idx)
 
-        # first fill of the sparse region with the prompt's last query (kv_cache.py:926-970)
-        q = last_query_states.view(-1, H, self.num_key_value_groups, D)
-        att = torch.einsum("bhgd,bhcd->bhgc", q, lm.to(q.device)) / math.sqrt(128)
-        att = torch.softmax(att, dim=-1, dtype=torch.float32).to(self.dtype).max(dim=-2).values
-        sel = rest_idx.to(q.device).gather(-1, att.topk(self.select_sets, dim=-1).indices)
-        self.position_ids[layer_idx][sl].copy_(sel)
-        tok = (sel.unsqueeze(-1) * C_ + torch.arange(C_, device=sel.device)).view(bsz, H, -1)
-        ex = tok.unsqueeze(-1).expand(-1, -1, -1, D)
-        self.v_cache_buffer[layer_idx][sl, :, self.sparse_start:self.sparse_end].copy_(new_v_cache.gather(-2, ex))
-        self.k_cache_buffer[layer_idx][sl, :, self.sparse_start:self.sparse_end].copy_(key_states_roped.gather(-2, ex))
+        # first fill of the sparse region with the prompt's last query (kv_cache.py:926-970): the decode path's
+        # scoring + selection kernels on an empty chunk table (every selected chunk is a miss)
+        g = Geom(batch=bsz, kv_heads=H, q_groups=self.num_key_value_groups, head_dim=D, chunk=C_, select=self.select_sets,
+                 n_landmarks=n - n_out, rank=self.rank, seq_len=incoming, buf_len=self.buf_len,
+                 sparse_start=self.sparse_start, table_mode=1)
+        ws = torch.empty(lib.skv_select_workspace_bytes(C.byref(g)), dtype=torch.uint8, device=k.device)
+        q = last_query_states.reshape(bsz, H * self.num_key_value_groups, D).contiguous()
+        pid = self.position_ids[layer_idx][sl]
+        pid.fill_(-1)
+        offs = torch.empty(bsz * H * self.select_sets, dtype=torch.int32, device=k.device)
+        cnt = torch.empty(bsz * H, dtype=torch.int32, device=k.device)
+        check(lib.skv_select_chunks(C.byref(g), q.data_ptr(), lm.data_ptr(), rest_idx.data_ptr(), pid.data_ptr(),
+                                    offs.data_ptr(), cnt.data_ptr(), 0, 0, ws.data_ptr(), None, st), "select_chunks(prefill)")
+        for src, dst in ((k, kb), (v, vb)):             # exact K and V of the selected chunks
+            check(lib.skv_gather_chunks(src.data_ptr(), src.stride(1), dst.data_ptr(), buf_stride, self.sparse_start * D,
+                                        pid.data_ptr(), self.select_sets, bsz * H, st), "gather_chunks(selected)")
 
         if layer_idx == self.num_layers - 1:
             assert self.sparse_budget < incoming

@@ -95,3 +95,24 @@ def test_attention_matches_sdpa():
     Vr = V.float().repeat_interleave(4, dim=1)
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), Kr, Vr).transpose(1, 2)
     assert_close_bf16(got, ref, what="attention")
+
+
+def test_chunk_stats_chain_equals_torch_cosine_similarity():
+    """The oracle spells torch's bf16 cosine_similarity out with explicit roundings (so that it does not depend on
+    the installed torch); on this image the two must agree bit for bit, and the mean must equal torch.mean."""
+    g = torch.Generator().manual_seed(3)
+    k = (torch.randn(2, 3, 96, 1, 128, generator=g) + torch.randn(2, 3, 96, 8, 128, generator=g) *
+         torch.rand(2, 3, 96, 1, 1, generator=g) * 2).to(torch.bfloat16)
+    means, mincos = O.chunk_stats(k)
+    lm = k.mean(dim=-2)
+    assert torch.equal(lm, means)
+    cos = torch.nn.functional.cosine_similarity(lm.unsqueeze(3).expand(-1, -1, -1, 8, -1), k, dim=-1)
+    assert torch.equal(cos.min(dim=-1).values, mincos)
+    out, rest = O.select_outliers(mincos, 24)
+    ref = mincos.float().topk(24, largest=False).indices
+    for b in range(2):
+        for h in range(3):
+            kth = mincos[b, h].float().sort().values[23]
+            assert all(float(mincos[b, h, c]) <= float(kth) for c in out[b, h].tolist())
+            assert set(ref[b, h].tolist()) ^ set(out[b, h].tolist()) <= set((mincos[b, h].float() == kth).nonzero().flatten().tolist())
+            assert sorted(out[b, h].tolist() + rest[b, h].tolist()) == list(range(96))
