@@ -352,8 +352,8 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
         const float m = s_m[g], inv = s_inv[g];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint16_t b0 = f32_to_bf16_bits(expf(bf16_lo(u[e]) - m) * inv);
-          const uint16_t b1 = f32_to_bf16_bits(expf(bf16_hi(u[e]) - m) * inv);
+          const uint16_t b0 = f32_to_bf16_bits(__expf(bf16_lo(u[e]) - m) * inv);
+          const uint16_t b1 = f32_to_bf16_bits(__expf(bf16_hi(u[e]) - m) * inv);
           best[2 * e] = b0 > best[2 * e] ? b0 : best[2 * e];
           best[2 * e + 1] = b1 > best[2 * e + 1] ? b1 : best[2 * e + 1];
         }
