@@ -1,9 +1,9 @@
 // Low-rank pre-RoPE key rebuild for the missed chunks:  K[r,:] = U[b, id*8 + r%8, :R] . SV[b,h,:, :R]^T
 // (reference kernels/batch_gather_gemm.cu:193-287 + rope_new.cu:321-370/429-493, three launches and a bf16
-// scratch round trip there).  Here: one launch.  The chunk-gathered U rows (8 contiguous rows of 2R bytes
-// per chunk = exactly one 128B-swizzle atom per 64-column slab) and the SV panel are brought in by TMA, the
-// 128x128xR product runs on tcgen05 with the fp32 accumulator in TMEM, and the epilogue rounds to bf16,
-// applies the rotary embedding in bf16 at token position id*8+r and writes straight into the K buffer.
+// scratch round trip there).  Here: one launch.  The chunk-gathered U rows (8 contiguous rows of 2R bytes per
+// chunk) are written into 128-byte-swizzled K-major slabs by 16-byte cp.async from all threads, the SV panel
+// comes by TMA, the 128x128xR product runs on tcgen05 with the fp32 accumulator in TMEM, and the epilogue rounds to
+// bf16, applies the rotary embedding in bf16 at token position id*8+r and writes straight into the K buffer.
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -27,6 +27,7 @@ struct RebuildParams {
   const int64_t *resident;   // [BH, S] chunk ids (after reorder)
   const int32_t *ids32;      // alternative int32 ids (drop-in batch_gather_gemm); one of the two is set
   const int32_t *cnts;       // [BH]
+  const __nv_bfloat16 *U;    // [B, L, R]: rows of the missed chunks are gathered with cp.async by all threads
   const int32_t *miss_slots; // in-place table: [BH, S] slot of the i-th miss (i < S - cnt); null = slots cnt..S-1
   const __nv_bfloat16 *cos_sin;
   __nv_bfloat16 *out;        // K buffer (fused) or scratch [BH, S*8, 128] (drop-in)
@@ -38,8 +39,7 @@ struct RebuildParams {
 };
 
 __global__ void __launch_bounds__(128, 2)
-    rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_sv,
-                           RebuildParams p) {
+    rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_sv, RebuildParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sA = smem;                                   // n_slabs x 16 KiB
   // sized by the slabs the rank needs (rank 160 -> 3 slabs -> 96 KiB, two CTAs per SM), not by the maximum
@@ -78,7 +78,6 @@ __global__ void __launch_bounds__(128, 2)
     for (int s = 0; s < p.n_slabs; ++s) mbarrier_init(&full_bar[s], 1);
     mbarrier_init(mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_u) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_sv) : "memory");
   }
   if (warp == 0) tcgen05_alloc(tmem_slot, 128);
@@ -87,18 +86,39 @@ __global__ void __launch_bounds__(128, 2)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (threadIdx.x == 0) {
-    int n_valid = 0;
-    for (int j = 0; j < kTileChunks; ++j) n_valid += s_ids[j] >= 0;
-    // producer: one barrier per 64-column slab so the MMAs of slab 0 overlap the loads of slabs 1..
-    for (int s = 0; s < p.n_slabs; ++s) {
-      mbarrier_expect_tx(&full_bar[s], kSlabBytesB + n_valid * 1024);
-      tma_load_2d(sB + s * kSlabBytesB, &map_sv, s * kSlabCols, bh * kHeadDim, &full_bar[s]);
-      for (int j = 0; j < kTileChunks; ++j)
-        if (s_ids[j] >= 0)
-          tma_load_2d(sA + s * kSlabBytesA + j * 1024, &map_u, s * kSlabCols, b * p.L + s_ids[j] * kChunkTokens,
-                      &full_bar[s]);
+  // U rows of the tile's chunks: 128 threads x 16-byte cp.async into the 128-byte-swizzled K-major layout the MMA
+  // descriptor expects (piece c of row r lands at piece c ^ (r & 7) of its 128-byte line).  One TMA box per chunk
+  // and slab (48 serial issues by one thread) was the longest part of this kernel; here every load is in flight
+  // at once.  The SV panel still comes by TMA (three 16 KiB boxes).
+  {
+    const int ppr = p.R >> 3;                                  // 16-byte pieces per U row
+    const __nv_bfloat16 *ub = p.U + size_t(b) * p.L * p.R;
+    for (int q = threadIdx.x; q < kTileRows * ppr; q += 128) {
+      const int r = q / ppr, c = q - r * ppr;
+      const int id = s_ids[r >> 3];
+      if (id >= 0) {
+        const __nv_bfloat16 *src = ub + (size_t(id) * kChunkTokens + (r & 7)) * p.R + c * 8;
+        const uint32_t dst = smem_addr(sA + (c >> 3) * kSlabBytesA + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
     }
+    if (p.R & 8) {                                             // last 16-column MMA step is half valid: zero the rest
+      const int r = threadIdx.x, c = ppr;
+      *reinterpret_cast<int4 *>(sA + (c >> 3) * kSlabBytesA + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) =
+          make_int4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_slabs; ++s) {
+      mbarrier_expect_tx(&full_bar[s], kSlabBytesB);
+      tma_load_2d(sB + s * kSlabBytesB, &map_sv, s * kSlabCols, bh * kHeadDim, &full_bar[s]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  fence_proxy_async_smem();                                    // cp.async wrote through the generic proxy
+  __syncthreads();
+  if (threadIdx.x == 0) {
     // MMA issuer
     int step = 0;
     for (int s = 0; s < p.n_slabs; ++s) {
@@ -342,16 +362,15 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
                                               reinterpret_cast<const __nv_bfloat16 *>(SV), p);
     return launch_status("rebuild_simt_kernel");
   }
-  CUtensorMap map_u, map_sv;
-  int rc = make_tensor_map_2d(&map_u, U, uint64_t(B) * p.L, p.R, kChunkTokens, kSlabCols);
+  CUtensorMap map_sv;
+  int rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim, kSlabCols);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim, kSlabCols);
-  if (rc) return rc;
+  p.U = reinterpret_cast<const __nv_bfloat16 *>(U);
   const int smem = p.n_slabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
   static int attr = 0;
   if (smem > attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
   dim3 grid((p.S + kTileChunks - 1) / kTileChunks, BH);
-  rebuild_tcgen05_kernel<<<grid, 128, smem, st>>>(map_u, map_sv, p);
+  rebuild_tcgen05_kernel<<<grid, 128, smem, st>>>(map_sv, p);
   return launch_status("rebuild_tcgen05_kernel");
 }
 
