@@ -5,10 +5,11 @@ plus flash_attn_with_kvcache from the flash-attn wheel, driven with exactly the 
 ShadowKVCache_CPU decode methods (models/kv_cache.py:983-1176) and base.py:320-341's stream choreography, on the
 same synthetic decode state and queries bench.py uses.
 
-Checker-side tool: it is not part of the product path and bench.py does not call it.  Output: one JSON line
+Checker-side tool (it lives under tests/ because it executes oracle/_ref): not part of the product path, not
+collected by pytest, and bench.py does not call it.  Output: one JSON line
 (tokens/s of the hot path for all layers, us per layer-step, per-stage CUDA-event times).
 
-    python tools/bench_ref_cuda.py [--steps 48] [--warmup 8] [--batch 1] > gpurun_out/ref_cuda.json
+    python tests/ref_cuda_bench.py [--steps 48] [--warmup 8] [--batch 1] > gpurun_out/ref_cuda.json
 """
 import argparse
 import json
@@ -16,7 +17,7 @@ import math
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "kernels"))
 
