@@ -509,6 +509,11 @@ class ShadowKVCache_CPU:
         # (programmatic launch: no launch gap); the short K rebuild runs beside it on the side stream.  base.py's
         # choreography (:326-338) has the two swapped, which only matters for who pays the fork/join.
         cur, side = torch.cuda.current_stream(), self.copy_stream
+        if self.hbm_store_ways and self.num_layers == 1 and not torch.cuda.is_current_stream_capturing():
+            # a single-layer cache driven eagerly: the store fill of the previous token (side stream) must be done
+            # before this token's fetch reads the store; with more layers, or inside a replayed graph, the joins
+            # below and the graph boundary already order them
+            cur.wait_stream(side)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
