@@ -478,7 +478,8 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-        gt += k > thr; eq += k == thr;
+        const bool real = off + e < count;                   // the ragged tail of the last slice never counts
+        gt += real && k > thr; eq += real && k == thr;
       }
       int pg, pe, tg, te;
       block_excl_scan2<kWarps>(gt, eq, s_wa, s_wb, pg, pe, tg, te);
@@ -487,9 +488,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-          const bool take = k > thr || (k == thr && eq_seen < need_eq);
+          const bool real = off + e < count;
+          const bool take = real && (k > thr || (k == thr && eq_seen < need_eq));
           if (take) dst[gt_seen + min(eq_seen, need_eq)] = base == 0 ? ids0[e] : static_cast<int>(lidx[off + e]);
-          gt_seen += k > thr; eq_seen += k == thr;
+          gt_seen += real && k > thr; eq_seen += real && k == thr;
         }
       }
       gt_before += tg; eq_before += te;

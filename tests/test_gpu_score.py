@@ -123,3 +123,35 @@ def test_select_massive_ties(cuda):
     torch.cuda.synchronize()
     assert (cnt.cpu() == 0).all()
     assert torch.equal(res.cpu(), (torch.arange(S) * 3).expand(B, H, S))
+
+
+def test_select_underflowed_probabilities_and_ragged_tail(cuda):
+    """One landmark takes all the probability mass; every other softmax value underflows to bf16 zero, so the
+    threshold key is 0 and N is not a multiple of 8 (the last 16-byte group of the last cluster slice is ragged):
+    the padding must never be selected -- the answer is that landmark plus the S-1 lowest indices."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    B, H, G, N, S = 1, 2, 4, 1004, 128
+    q = torch.full((B, H * G, 1, 128), 4.0, dtype=torch.bfloat16)
+    lm = torch.full((B, H, N, 128), -4.0, dtype=torch.bfloat16)
+    lm[:, :, 777] = 4.0
+    idx = (torch.arange(N) * 2 + 5).expand(B, H, N).contiguous()
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 16 + 64, buf_len=2000, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    res = torch.full((B, H, S), -1, dtype=torch.int64, device=cuda)
+    off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+    sel = torch.full((B, H, S), -7, dtype=torch.int64, device=cuda)
+    score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+    d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(), d_idx.data_ptr(), res.data_ptr(),
+                                          off.data_ptr(), cnt.data_ptr(), sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                          None, torch.cuda.current_stream().cuda_stream), "select")
+    torch.cuda.synchronize()
+    sc = score.float().cpu()
+    assert float(sc[0, 0, 777]) == 1.0 and float(sc[0, 0].sum()) == 1.0        # everything else underflowed
+    want = torch.cat([torch.arange(127), torch.tensor([777])]) * 2 + 5
+    for h in range(H):
+        assert torch.equal(sel[0, h].cpu(), want), "underflow ties must resolve to the lowest landmark indices"
+        assert torch.equal(res[0, h].cpu(), want)
