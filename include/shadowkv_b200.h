@@ -301,6 +301,59 @@ int skv_gather_rows(const skv_bf16 *src, const int64_t *idx, skv_bf16 *dst, int 
 int skv_gather_chunks(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, int64_t dst_stride, int64_t dst_offset,
                       const int64_t *ids, int n_ids, int rows, skv_stream_t stream);
 
+/* ======================================================================
+ * Part 4 -- dense remainder of the decode layer: what reference models/llama.py:354-427
+ * (pre_attention_compute / post_attention_compute), models/glm.py:312-403 and the lm_head of models/base.py:157
+ * do for ONE decode token per sequence through library calls (flashinfer rmsnorm, F.linear = cuBLAS,
+ * vllm rotary_embedding and silu_and_mul, torch residual adds).  Here: one weight-streaming kernel
+ * (TMA ring + tcgen05, stream-K over 148 SMs, HBM bound) with the element-wise work in its epilogue.
+ * ====================================================================== */
+
+#define SKV_DENSE_F32 0      /* out f32 [B, out_features] = float(bf16(x W^T))            (lm_head, base.py:157) */
+#define SKV_DENSE_RESID 1    /* out bf16 = bf16(resid + bf16(x W^T (+ bias)))  (o_proj / down_proj + residual,
+                              * llama.py:410-412, 424-426); resid NULL: plain F.linear                          */
+#define SKV_DENSE_SILU_MUL 2 /* W = [gate; up] (2*F rows): out bf16 [B, F] = bf16(silu(gate)) * up, rounding points
+                              * of vllm silu_and_mul (llama.py:416-421)                                          */
+#define SKV_DENSE_QKV_ROPE 3 /* W = fused wqkv ((q_heads + 2 kv_heads) * 128 rows): q [B,q_heads,128], k, v
+                              * [B,kv_heads,128] bf16 with the rotary embedding of vllm rotary_embedding applied to
+                              * q and k at the token's position (llama.py:296, 377-385; glm.py:344, 421)         */
+
+typedef struct skv_dense_epilogue {
+  int32_t mode;          /* SKV_DENSE_*                                                         */
+  int32_t q_heads;       /* QKV_ROPE                                                            */
+  int32_t kv_heads;      /* QKV_ROPE                                                            */
+  int32_t rope_mode;     /* QKV_ROPE: 0 none, 1 neox over 128 dims (cos_sin row = [cos64|sin64]),
+                          * 2 GLM: interleaved pairs over the first 64 dims (row = [cos32|sin32]) */
+  int32_t cos_sin_rows;  /* rows of the cos_sin table                                           */
+  int32_t pos;           /* token position (+ *pos_dev when pos_dev != NULL)                    */
+  const int32_t *pos_dev;
+  const skv_bf16 *bias;  /* [out_features] or NULL (GLM's bqkv)                                 */
+  const skv_bf16 *resid; /* RESID: [B, out_features] or NULL; may alias out                     */
+  const skv_bf16 *cos_sin;
+  void *out;             /* F32: float*; RESID / SILU_MUL: bf16*; QKV_ROPE: q                   */
+  skv_bf16 *k_out;       /* QKV_ROPE                                                            */
+  skv_bf16 *v_out;       /* QKV_ROPE                                                            */
+} skv_dense_epilogue;
+
+/* Device scratch of skv_dense_linear (split-tile partial sums and per-tile arrival counters).  The caller
+ * zero-fills it ONCE; the kernel leaves the counters at zero.  One workspace serves every launch of a stream. */
+int64_t skv_dense_workspace_bytes(void);
+
+/* y = x W^T for a skinny x [batch <= 32, in_features] bf16 and a row-major W [out_features, in_features] bf16
+ * (torch Linear layout), fp32 accumulation, epilogue per `epi`.  in_features % 64 == 0. */
+int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_features, int out_features,
+                     const skv_dense_epilogue *epi, void *workspace, skv_stream_t stream);
+
+/* h[b,:] = bf16(x[b,:] * rsqrt(mean(x^2) + eps) * w) (flashinfer rmsnorm, tensor_op.py:34-39).  With tok != NULL the
+ * row is first looked up, x[b,:] = emb[tok[b],:] (F.embedding, base.py:141), and written to x_out (the residual
+ * stream) when x_out != NULL. */
+int skv_rmsnorm(const skv_bf16 *x, const int64_t *tok, const skv_bf16 *emb, const skv_bf16 *w, float eps,
+                skv_bf16 *x_out, skv_bf16 *h_out, int batch, int hidden, skv_stream_t stream);
+
+/* tok[b] = index of the largest logit of row b (lowest index on ties): greedy decoding,
+ * sample_token with temperature 0 (tensor_op.py:291-293, called at base.py:612). */
+int skv_argmax(const float *logits, int64_t *tok, int batch, int vocab, skv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,14 @@ class VStore(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class DenseEpilogue(C.Structure):
+    """struct skv_dense_epilogue (include/shadowkv_b200.h)."""
+    _fields_ = [("mode", C.c_int32), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("rope_mode", C.c_int32),
+                ("cos_sin_rows", C.c_int32), ("pos", C.c_int32), ("pos_dev", C.c_void_p), ("bias", C.c_void_p),
+                ("resid", C.c_void_p), ("cos_sin", C.c_void_p), ("out", C.c_void_p), ("k_out", C.c_void_p),
+                ("v_out", C.c_void_p)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`)."
@@ -67,10 +75,13 @@ _SIGS = {
     "skv_gather_chunks": [_p, _l, _p, _l, _l, _p, _i, _i, _p],
     "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
+    "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
+    "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    "skv_argmax": [_p, _p, _i, _i, _p],
 }
 # every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
 EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",
-                                "skv_attention_workspace_bytes"])
+                                "skv_attention_workspace_bytes", "skv_dense_workspace_bytes"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -82,6 +93,8 @@ lib.skv_select_workspace_bytes.argtypes = [C.POINTER(Geom)]
 lib.skv_select_workspace_bytes.restype = C.c_int64
 lib.skv_attention_workspace_bytes.argtypes = [_i] * 5
 lib.skv_attention_workspace_bytes.restype = C.c_int64
+lib.skv_dense_workspace_bytes.argtypes = []
+lib.skv_dense_workspace_bytes.restype = C.c_int64
 
 
 def check(rc: int, what: str) -> None:

@@ -1,0 +1,516 @@
+// Dense remainder of the decode layer: one decode token per sequence through
+//   rmsnorm -> fused QKV (+bias) -> RoPE(q,k)            reference models/llama.py:354-385, glm.py:312-357
+//   o_proj + residual -> rmsnorm -> gate/up -> SiLU*mul -> down + residual      llama.py:387-427, glm.py:359-403
+//   final rmsnorm -> lm_head -> argmax                                        base.py:150-159, tensor_op.py:291-293
+// The reference runs these through library kernels (flashinfer rmsnorm, cuBLAS F.linear, vllm rotary_embedding /
+// silu_and_mul, torch adds): ~11 launches per layer.  With batch <= 32 every linear is a weight stream
+// (0.436 GB per Llama-8B layer against 8 KB of activations per sequence), i.e. HBM bound, so the design is one
+// weight-streaming kernel with all element-wise work in its epilogue:
+//
+//  * W [out, in] is cut into tiles of 128 rows x 64-column slabs (16 KiB).  The (tile, slab) space is linearised
+//    and split EVENLY over one persistent CTA per SM (stream-K): every SM streams the same number of bytes whatever
+//    the matrix shape (4096 x 4096 has only 32 row tiles; 148 SMs).
+//  * warp 0 = TMA producer: W slab (two 64-row boxes, 128-byte swizzle, L2 evict-first) + the matching 64 columns
+//    of x (rows beyond the batch are zero filled by TMA) into a shared-memory ring.  The weights are static, so under
+//    a programmatic dependent launch the ring is filled BEFORE griddepcontrol.wait, while the previous kernel drains.
+//  * warp 1 = MMA issuer: tcgen05.mma M=128 (W rows) x N=16/32 (batch, padded) x K=16, fp32 accumulators in TMEM,
+//    double buffered so the stream continues while a finished tile is in its epilogue.
+//  * warps 2..5 = epilogue, thread = W row.  A tile whose slabs were split between CTAs is finished by the
+//    last-arriving CTA, which sums the partials in CTA order (deterministic), then: bias, bf16 round, residual add /
+//    SiLU*mul (gate and up rows interleaved into the same tile) / rotary embedding (one tile = one head).
+#include "sm100_ptx.cuh"
+
+#include <cstdlib>
+
+namespace skv {
+
+constexpr int kDnWBytes = 128 * 128;          // W part of a stage: 128 rows x 64 bf16
+constexpr int kDnMaxStages = 12;
+constexpr int kDnThreads = 64 + 128;
+constexpr int kDnMaxBatch = 32;
+constexpr int kDnMaxCtas = 2 * kNumSMs;
+constexpr int kDnMaxTiles = 4096;             // arrival counters in the workspace
+constexpr int64_t kDnCounterBytes = kDnMaxTiles * 4;
+constexpr int64_t kDnPartBytes = int64_t(kDnMaxCtas) * 2 * kDnMaxBatch * 128 * 4;
+
+struct DenseParams {
+  int B, K, KS, Nout, T, mode, stages, total;
+  float *part;            // [ctas][2][32][128] fp32 partial tiles
+  int *tile_cnt;          // [T] arrivals per split tile; zero between launches
+  const __nv_bfloat16 *resid, *bias, *cos_sin;
+  __nv_bfloat16 *out, *k_out, *v_out;
+  float *out_f32;
+  int up_row0;            // SILU_MUL: first "up" row of W (= F); tile t = gate rows [64t, 64t+64) + up rows [F+64t, ..)
+  int q_heads, kv_heads, rope_mode, cos_sin_rows, pos;
+  const int *pos_dev;
+};
+
+__device__ __forceinline__ int dn_begin(int c, int total, int n) { return int((long long)c * total / n); }
+__device__ __forceinline__ int dn_cta_of(int w, int total, int n) {
+  int c = int((long long)w * n / total);
+  while (c + 1 < n && dn_begin(c + 1, total, n) <= w) ++c;
+  while (c > 0 && dn_begin(c, total, n) > w) --c;
+  return c;
+}
+__device__ __forceinline__ float bfr(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int NPAD>
+__device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int row, float (&v)[NPAD], float *s_x,
+                                               int pos) {
+  constexpr int LD = NPAD + 1;
+  if (p.mode == SKV_DENSE_F32) {
+    const int n = t * 128 + row;
+    if (n < p.Nout) {
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) p.out_f32[size_t(b) * p.Nout + n] = bfr(v[b]);
+    }
+  } else if (p.mode == SKV_DENSE_RESID) {
+    const int n = t * 128 + row;
+    if (n < p.Nout) {
+      const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) {
+          float y = bfr(v[b] + bias);
+          if (p.resid) y = bfr(__bfloat162float(p.resid[size_t(b) * p.Nout + n]) + y);
+          p.out[size_t(b) * p.Nout + n] = __float2bfloat16_rn(y);
+        }
+    }
+  } else if (p.mode == SKV_DENSE_SILU_MUL) {
+    // rows 0..63 = gate, 64..127 = up of the same 64 output features (vllm silu_and_mul: silu in fp32, rounded to
+    // bf16, then a bf16 multiply)
+    if (row >= 64) {
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) s_x[(row - 64) * LD + b] = bfr(v[b]);
+    }
+    epi_bar();
+    if (row < 64) {
+      const int n = t * 64 + row;
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) {
+          const float g = bfr(v[b]);
+          const float sl = bfr(g / (1.0f + expf(-g)));
+          p.out[size_t(b) * p.up_row0 + n] = __float2bfloat16_rn(sl * s_x[row * LD + b]);
+        }
+    }
+    epi_bar();
+  } else {  // SKV_DENSE_QKV_ROPE: tile = head
+    const int n = t * 128 + row;
+    const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+    const bool is_q = t < p.q_heads, is_k = !is_q && t < p.q_heads + p.kv_heads;
+    const bool rope = p.rope_mode != 0 && (is_q || is_k);          // uniform over the tile
+#pragma unroll
+    for (int b = 0; b < NPAD; ++b) v[b] = bfr(v[b] + bias);
+    if (rope) {
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) s_x[row * LD + b] = v[b];
+      epi_bar();
+      // vllm rotary_embedding: first = x*cos - y*sin, second = y*cos + x*sin, evaluated in fp32 and rounded once (what
+      // the vllm build of this image does, bit for bit: tests/golden/dense_golden.npz)
+      int partner = -1;
+      bool first = true;
+      float cs = 1.f, sn = 0.f;
+      if (p.rope_mode == 1) {
+        const int j = row & 63;
+        first = row < 64;
+        partner = first ? row + 64 : row - 64;
+        cs = __bfloat162float(p.cos_sin[size_t(pos) * 128 + j]);
+        sn = __bfloat162float(p.cos_sin[size_t(pos) * 128 + 64 + j]);
+      } else if (row < 64) {
+        const int j = row >> 1;
+        first = (row & 1) == 0;
+        partner = row ^ 1;
+        cs = __bfloat162float(p.cos_sin[size_t(pos) * 64 + j]);
+        sn = __bfloat162float(p.cos_sin[size_t(pos) * 64 + 32 + j]);
+      }
+      if (partner >= 0) {
+#pragma unroll
+        for (int b = 0; b < NPAD; ++b)
+          if (b < p.B) {
+            const float other = s_x[partner * LD + b];
+            v[b] = first ? bfr(v[b] * cs - other * sn) : bfr(v[b] * cs + other * sn);
+          }
+      }
+      epi_bar();
+    }
+    __nv_bfloat16 *dst;
+    int heads, head;
+    if (is_q) { dst = p.out; heads = p.q_heads; head = t; }
+    else if (is_k) { dst = p.k_out; heads = p.kv_heads; head = t - p.q_heads; }
+    else { dst = p.v_out; heads = p.kv_heads; head = t - p.q_heads - p.kv_heads; }
+#pragma unroll
+    for (int b = 0; b < NPAD; ++b)
+      if (b < p.B) dst[(size_t(b) * heads + head) * 128 + row] = __float2bfloat16_rn(v[b]);
+  }
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kDnThreads, 2)
+    dense_streamk_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                         DenseParams p) {
+  constexpr int kStageBytes = kDnWBytes + NPAD * 128;
+  constexpr int kAccCols = NPAD;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *ring = smem;
+  float *s_x = reinterpret_cast<float *>(smem + p.stages * kStageBytes);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_x + 128 * (NPAD + 1));
+  uint64_t *empty_bar = full_bar + kDnMaxStages;
+  uint64_t *acc_full = empty_bar + kDnMaxStages;
+  uint64_t *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  int *s_flag = reinterpret_cast<int *>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x, nc = gridDim.x;
+  const int w0 = dn_begin(c, p.total, nc), w1 = dn_begin(c + 1, p.total, nc);
+  const int n_slabs = w1 - w0;
+  const int stages = p.stages;
+
+  auto tile_rows = [&](int t, int &r0, int &r1) {
+    if (p.mode == SKV_DENSE_SILU_MUL) { r0 = t * 64; r1 = p.up_row0 + t * 64; }
+    else { r0 = t * 128; r1 = r0 + 64; }
+  };
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // The weights do not depend on the previous kernel: fill the ring now (under a programmatic launch this runs
+    // while the predecessor is still finishing).
+    const uint64_t pol = l2_policy_evict_first();
+    for (int it = 0; it < stages && it < n_slabs; ++it) {
+      const int w = w0 + it, t = w / p.KS, s = w - t * p.KS;
+      int r0, r1;
+      tile_rows(t, r0, r1);
+      unsigned char *dst = ring + it * kStageBytes;
+      mbarrier_expect_tx(&full_bar[it], kStageBytes);
+      tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[it], pol);
+      tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[it], pol);
+    }
+  }
+  // x, the residual, the workspace and every output belong to the predecessor until here
+  pdl_wait();
+
+  if (warp == 1) tcgen05_alloc(tmem_slot, 2 * kAccCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      for (int it = 0; it < n_slabs; ++it) {
+        const int stage = it % stages;
+        const int w = w0 + it, t = w / p.KS, s = w - t * p.KS;
+        unsigned char *dst = ring + stage * kStageBytes;
+        if (it >= stages) {
+          int r0, r1;
+          tile_rows(t, r0, r1);
+          mbarrier_wait(&empty_bar[stage], ((it / stages) & 1) ^ 1);
+          mbarrier_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[stage], pol);
+          tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[stage], pol);
+        }
+        tma_load_2d(dst + kDnWBytes, &map_x, s * 64, 0, &full_bar[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(kAccCols);
+      int it = 0, seg = 0;
+      for (int w = w0; w < w1; ++seg) {
+        const int t = w / p.KS, s0 = w - t * p.KS;
+        const int s1 = min(p.KS, s0 + (w1 - w));
+        const int acc = seg & 1;
+        mbarrier_wait(&acc_empty[acc], ((seg >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + acc * kAccCols;
+        for (int s = s0; s < s1; ++s, ++it) {
+          const int stage = it % stages;
+          mbarrier_wait(&full_bar[stage], (it / stages) & 1);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_addr(ring + stage * kStageBytes));
+          const uint64_t db = umma_desc_k_sw128(smem_addr(ring + stage * kStageBytes + kDnWBytes));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tcgen05_mma_bf16(d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (s > s0 || kk > 0) ? 1u : 0u);
+          tcgen05_commit(&empty_bar[stage]);
+        }
+        tcgen05_commit(&acc_full[acc]);
+        w += s1 - s0;
+      }
+    }
+  } else {
+    // ===== epilogue: thread = W row of the tile =====
+    const int lg = warp & 3;                       // TMEM lane group this warp may read
+    const int row = lg * 32 + lane;
+    const bool leader = threadIdx.x == 64;
+    int pos = 0;
+    if (p.mode == SKV_DENSE_QKV_ROPE && p.rope_mode) {
+      pos = p.pos + (p.pos_dev ? *p.pos_dev : 0);
+      pos = max(0, min(pos, p.cos_sin_rows - 1));
+    }
+    int seg = 0;
+    for (int w = w0; w < w1; ++seg) {
+      const int t = w / p.KS, s0 = w - t * p.KS;
+      const int s1 = min(p.KS, s0 + (w1 - w));
+      w += s1 - s0;
+      const int acc = seg & 1;
+      mbarrier_wait(&acc_full[acc], (seg >> 1) & 1);
+      tcgen05_fence_after();
+      float v[NPAD];
+      {
+        uint32_t r[NPAD];
+        if constexpr (NPAD == 16) tcgen05_ld16(tmem_base + (uint32_t(lg * 32) << 16) + acc * kAccCols, r);
+        else tcgen05_ld32(tmem_base + (uint32_t(lg * 32) << 16) + acc * kAccCols, r);
+        tcgen05_wait_ld();
+#pragma unroll
+        for (int b = 0; b < NPAD; ++b) v[b] = __uint_as_float(r[b]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbarrier_arrive(&acc_empty[acc]);
+
+      if (!(s0 == 0 && s1 == p.KS)) {
+        // split tile: park the partial sums; the CTA that arrives last adds them up in CTA order
+        const int slot = (t * p.KS < w0) ? 0 : 1;
+        float *mine = p.part + (size_t(c) * 2 + slot) * kDnMaxBatch * 128;
+#pragma unroll
+        for (int b = 0; b < NPAD; ++b)
+          if (b < p.B) __stcg(mine + b * 128 + row, v[b]);
+        __threadfence();
+        epi_bar();
+        if (leader) {
+          const int cf = dn_cta_of(t * p.KS, p.total, nc), cl = dn_cta_of(t * p.KS + p.KS - 1, p.total, nc);
+          const int old = atomicAdd(&p.tile_cnt[t], 1);
+          const int last = old == cl - cf;
+          if (last) p.tile_cnt[t] = 0;                 // every contributor has arrived: ready for the next launch
+          s_flag[0] = last; s_flag[1] = cf; s_flag[2] = cl;
+        }
+        epi_bar();
+        const int last = s_flag[0], cf = s_flag[1], cl = s_flag[2];
+        epi_bar();                                     // s_flag may be rewritten by the next split tile
+        if (!last) continue;
+        __threadfence();
+#pragma unroll
+        for (int b = 0; b < NPAD; ++b) v[b] = 0.f;
+        for (int cc = cf; cc <= cl; ++cc) {
+          const int sl = (t * p.KS < dn_begin(cc, p.total, nc)) ? 0 : 1;
+          const float *src = p.part + (size_t(cc) * 2 + sl) * kDnMaxBatch * 128;
+#pragma unroll
+          for (int b = 0; b < NPAD; ++b)
+            if (b < p.B) v[b] += __ldcg(src + b * 128 + row);
+        }
+      }
+      dense_epilogue<NPAD>(p, t, row, v, s_x, pos);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tcgen05_dealloc(tmem_base, 2 * kAccCols);
+}
+
+// ---- rmsnorm (+ optional embedding lookup) ---------------------------------------------------------------
+constexpr int kNormThreads = 512;
+__global__ void __launch_bounds__(kNormThreads)
+    rmsnorm_kernel(const __nv_bfloat16 *x, const int64_t *tok, const __nv_bfloat16 *emb, const __nv_bfloat16 *w, float eps,
+                   __nv_bfloat16 *x_out, __nv_bfloat16 *h_out, int hidden) {
+  __shared__ float s_part[kNormThreads / 32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const __nv_bfloat16 *src = tok ? emb + size_t(tok[b]) * hidden : x + size_t(b) * hidden;
+  const int nvec = hidden >> 3;
+  int4 v[2];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    v[i] = make_int4(0, 0, 0, 0);
+    if (j < nvec) {
+      v[i] = reinterpret_cast<const int4 *>(src)[j];
+      const uint32_t *u = reinterpret_cast<const uint32_t *>(&v[i]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float a = bf16_lo(u[k]), c = bf16_hi(u[k]); ss += a * a; ss += c * c; }
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_part[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormThreads / 32; ++i) tot += s_part[i];
+  const float r = rsqrtf(tot / float(hidden) + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    if (j < nvec) {
+      if (x_out && tok) reinterpret_cast<int4 *>(x_out + size_t(b) * hidden)[j] = v[i];
+      const int4 wv = reinterpret_cast<const int4 *>(w)[j];
+      const uint32_t *u = reinterpret_cast<const uint32_t *>(&v[i]);
+      const uint32_t *uw = reinterpret_cast<const uint32_t *>(&wv);
+      int4 o;
+      uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        uo[k] = pack_bf16(__float2bfloat16_rn(bf16_lo(u[k]) * r * bf16_lo(uw[k])),
+                          __float2bfloat16_rn(bf16_hi(u[k]) * r * bf16_hi(uw[k])));
+      reinterpret_cast<int4 *>(h_out + size_t(b) * hidden)[j] = o;
+    }
+  }
+}
+
+// ---- greedy token ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) argmax_kernel(const float *logits, int64_t *tok, int vocab) {
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const float *row = logits + size_t(b) * vocab;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < vocab; i += 1024) {
+    const float x = row[i];
+    if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+  }
+  auto merge = [&](float ov, int oi) { if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; } };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) merge(__shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = s_v[lane]; bi = s_i[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) merge(__shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    if (lane == 0) tok[b] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+template <int NPAD>
+static int launch_dense(const CUtensorMap &mw, const CUtensorMap &mx, DenseParams &p, int ctas, cudaStream_t st) {
+  constexpr int kStageBytes = kDnWBytes + NPAD * 128;
+  const int fixed = 128 * (NPAD + 1) * 4 + (2 * kDnMaxStages + 4) * 8 + 8 + 16 + 64;
+  // default: a ring that leaves room for the NEXT kernel's CTA on the same SM (227 KiB per SM), so its weight
+  // prefetch overlaps this kernel's tail
+  int stages = env_int("SKV_DENSE_STAGES", NPAD == 16 ? 5 : 4);
+  if (stages < 2) stages = 2;
+  if (stages > kDnMaxStages) stages = kDnMaxStages;
+  while (stages > 2 && stages * kStageBytes + fixed > 227 * 1024) --stages;
+  p.stages = stages;
+  const int smem = stages * kStageBytes + fixed;
+  static int attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(dense_streamk_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("dense_streamk_kernel: smem attribute: %s", cudaGetErrorString(e)); return int(e); }
+    attr = smem;
+  }
+  cudaError_t e = launch_kernel(dense_streamk_kernel<NPAD>, dim3(ctas), dim3(kDnThreads), smem, st, /*pdl=*/true, mw, mx, p);
+  if (e != cudaSuccess) { set_error("dense_streamk_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("dense_streamk_kernel");
+}
+
+}  // namespace skv
+
+using namespace skv;
+
+extern "C" {
+
+int64_t skv_dense_workspace_bytes(void) { return kDnCounterBytes + kDnPartBytes; }
+
+int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_features, int out_features,
+                     const skv_dense_epilogue *epi, void *workspace, skv_stream_t stream) {
+  if (!x || !W || !epi || !workspace || !epi->out) { set_error("dense_linear: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (batch < 1 || batch > kDnMaxBatch || in_features < 64 || in_features % 64 || out_features < 1) {
+    set_error("dense_linear: batch %d (1..32), in_features %d (multiple of 64), out_features %d", batch, in_features,
+              out_features);
+    return SKV_ERR_UNSUPPORTED;
+  }
+  DenseParams p{};
+  p.B = batch; p.K = in_features; p.KS = in_features / 64; p.Nout = out_features; p.mode = epi->mode;
+  p.tile_cnt = reinterpret_cast<int *>(workspace);
+  p.part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + kDnCounterBytes);
+  p.bias = reinterpret_cast<const __nv_bfloat16 *>(epi->bias);
+  p.resid = reinterpret_cast<const __nv_bfloat16 *>(epi->resid);
+  p.out = reinterpret_cast<__nv_bfloat16 *>(epi->out);
+  p.out_f32 = reinterpret_cast<float *>(epi->out);
+  switch (epi->mode) {
+    case SKV_DENSE_F32:
+    case SKV_DENSE_RESID:
+      p.T = (out_features + 127) / 128;
+      break;
+    case SKV_DENSE_SILU_MUL:
+      if (out_features % 128) { set_error("dense_linear: silu_mul needs out_features = 2F, F %% 64 == 0"); return SKV_ERR_UNSUPPORTED; }
+      p.up_row0 = out_features / 2;
+      p.T = p.up_row0 / 64;
+      break;
+    case SKV_DENSE_QKV_ROPE:
+      if (epi->q_heads < 1 || epi->kv_heads < 1 || out_features != (epi->q_heads + 2 * epi->kv_heads) * 128 || !epi->k_out ||
+          !epi->v_out || epi->rope_mode < 0 || epi->rope_mode > 2 || (epi->rope_mode && (!epi->cos_sin || epi->cos_sin_rows < 1))) {
+        set_error("dense_linear: qkv_rope needs out_features = (q_heads + 2 kv_heads) * 128, k_out, v_out and a cos_sin table");
+        return SKV_ERR_ARGUMENT;
+      }
+      p.T = epi->q_heads + 2 * epi->kv_heads;
+      p.q_heads = epi->q_heads; p.kv_heads = epi->kv_heads; p.rope_mode = epi->rope_mode;
+      p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(epi->cos_sin);
+      p.cos_sin_rows = epi->cos_sin_rows; p.pos = epi->pos; p.pos_dev = epi->pos_dev;
+      p.k_out = reinterpret_cast<__nv_bfloat16 *>(epi->k_out);
+      p.v_out = reinterpret_cast<__nv_bfloat16 *>(epi->v_out);
+      break;
+    default:
+      set_error("dense_linear: unknown epilogue mode %d", epi->mode);
+      return SKV_ERR_ARGUMENT;
+  }
+  if (p.T > kDnMaxTiles) { set_error("dense_linear: more than %d row tiles", kDnMaxTiles); return SKV_ERR_UNSUPPORTED; }
+  p.total = p.T * p.KS;
+  int ctas = kNumSMs * env_int("SKV_DENSE_CTAS_PER_SM", 1);
+  if (ctas > kDnMaxCtas) ctas = kDnMaxCtas;
+  if (ctas < 1) ctas = 1;
+  if (ctas > p.total) ctas = p.total;
+  const int npad = batch <= 16 ? 16 : 32;
+  CUtensorMap mw, mx;
+  int rc = make_tensor_map_2d(&mw, W, uint64_t(out_features), uint64_t(in_features), 64, 64);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&mx, x, uint64_t(batch), uint64_t(in_features), uint32_t(npad), 64);
+  if (rc) return rc;
+  return npad == 16 ? launch_dense<16>(mw, mx, p, ctas, as_stream(stream)) : launch_dense<32>(mw, mx, p, ctas, as_stream(stream));
+}
+
+int skv_rmsnorm(const skv_bf16 *x, const int64_t *tok, const skv_bf16 *emb, const skv_bf16 *w, float eps, skv_bf16 *x_out,
+                skv_bf16 *h_out, int batch, int hidden, skv_stream_t stream) {
+  if ((!x && !tok) || (tok && !emb) || !w || !h_out) { set_error("rmsnorm: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (batch < 1 || hidden < 8 || hidden % 8 || hidden > 2 * kNormThreads * 8) {
+    set_error("rmsnorm: hidden %d must be a multiple of 8, at most %d", hidden, 2 * kNormThreads * 8);
+    return SKV_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = launch_kernel(rmsnorm_kernel, dim3(batch), dim3(kNormThreads), 0, as_stream(stream), true,
+                                reinterpret_cast<const __nv_bfloat16 *>(x), tok, reinterpret_cast<const __nv_bfloat16 *>(emb),
+                                reinterpret_cast<const __nv_bfloat16 *>(w), eps, reinterpret_cast<__nv_bfloat16 *>(x_out),
+                                reinterpret_cast<__nv_bfloat16 *>(h_out), hidden);
+  if (e != cudaSuccess) { set_error("rmsnorm_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("rmsnorm_kernel");
+}
+
+int skv_argmax(const float *logits, int64_t *tok, int batch, int vocab, skv_stream_t stream) {
+  if (!logits || !tok) { set_error("argmax: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (batch < 1 || vocab < 1) { set_error("argmax: empty input"); return SKV_ERR_UNSUPPORTED; }
+  cudaError_t e = launch_kernel(argmax_kernel, dim3(batch), dim3(1024), 0, as_stream(stream), true, logits, tok, vocab);
+  if (e != cudaSuccess) { set_error("argmax_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("argmax_kernel");
+}
+
+}  // extern "C"

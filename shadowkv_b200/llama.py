@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's model classes for the DECODE step (reference models/llama.py ``LlamaLayer`` /
+``Llama``, models/glm.py ``GLMLayer`` / ``GLM``, token loop models/base.py:131-159, 296-349, 573-655): the same method
+names and argument meaning, every operator landing in the kernels of this repo (dense.py -> Part 4 of the C ABI,
+kv_cache.py -> Parts 1-2).  One class serves Llama-3 / 3.1, Yi (same architecture) and GLM-4 (QKV bias, interleaved
+rotary embedding over 64 dims); the differences are data (``ModelShape.glm_rope``), not code paths.
+
+There is no hub access here, so ``init_parameters`` draws random weights N(0, 0.02) of the named architecture (the
+reference loads them from ``LlamaForCausalLM.from_pretrained``, llama.py:310-352).  Prefill of the dense stack
+(q_len > 1) is outside this path and raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import dense, synth
+from .kv_cache import ShadowKVCache_CPU
+
+BF16 = torch.bfloat16
+
+
+class LlamaLayer:
+    """Weights of one decoder layer, named as in reference models/llama.py:62-123 (``GLMLayer``: glm.py:79-131, whose
+    fused gate/up matrix is called ``up_proj`` there and whose QKV projection has a bias ``bqkv``)."""
+
+    def __init__(self, layer_idx: int) -> None:
+        self.layer_idx = layer_idx
+        self.wqkv = self.wo = self.gate_up_proj = self.down_proj = None
+        self.bqkv = None
+        self.input_layernorm_weight = self.post_attention_layernorm_weight = None
+        self.input_layernorm_variance_epsilon = self.post_attention_layernorm_variance_epsilon = 1e-5
+        self.q_size = self.kv_size = 0
+
+    def init_parameters(self, shape: synth.ModelShape, generator: torch.Generator, device, std: float = 0.02):
+        hid, ffn = shape.hidden_size, shape.intermediate_size
+        self.q_size = shape.num_attention_heads * 128
+        self.kv_size = shape.num_key_value_heads * 128
+
+        def w(*s):
+            return (torch.randn(*s, generator=generator, device=device) * std).to(BF16)
+
+        self.wqkv = w(self.q_size + 2 * self.kv_size, hid)              # cat(q_proj, k_proj, v_proj), llama.py:95-99
+        self.wo = w(hid, self.q_size)
+        self.gate_up_proj = w(2 * ffn, hid)                             # cat(gate_proj, up_proj), llama.py:104
+        self.down_proj = w(hid, ffn)
+        self.bqkv = w(self.q_size + 2 * self.kv_size) if shape.glm_rope else None     # glm.py:118
+        self.input_layernorm_weight = (1.0 + 0.1 * torch.randn(hid, generator=generator, device=device)).to(BF16)
+        self.post_attention_layernorm_weight = (1.0 + 0.1 * torch.randn(hid, generator=generator, device=device)).to(BF16)
+        return self
+
+
+class Llama:
+    """Decode-side mirror of reference ``Llama`` (models/llama.py:126-427) + ``LLM`` (models/base.py)."""
+
+    def __init__(self, model: str | synth.ModelShape = "llama-3.1-8b", batch_size: int = 1, max_length: int = 124928,
+                 device: str = "cuda:0", sparse_budget: int = 2048, rank: int = 160, chunk_size: int = 8,
+                 num_layers: int | None = None, seed: int = 0, kv_cache: ShadowKVCache_CPU | None = None,
+                 hbm_store_ways: int = 0) -> None:
+        self.shape = synth.MODELS[model] if isinstance(model, str) else model
+        self.device = torch.device(device)
+        self.batch_size, self.max_length = batch_size, max_length
+        self.num_layers = num_layers or self.shape.num_hidden_layers
+        self.hidden_size = self.shape.hidden_size
+        self.num_heads = self.shape.num_attention_heads
+        self.num_key_value_heads = self.shape.num_key_value_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.vocab_size = self.shape.vocab_size
+        self.norm_variance_epsilon = 1e-5
+        if self.head_dim != 128:
+            raise ValueError("head_dim must be 128")
+        if batch_size > dense.MAX_BATCH:
+            raise ValueError(f"the dense decode kernels take at most {dense.MAX_BATCH} sequences per GPU")
+        self.kv_cache = kv_cache if kv_cache is not None else ShadowKVCache_CPU(
+            self.shape.config(self.num_layers), batch_size=batch_size, max_length=max_length, device=device,
+            sparse_budget=sparse_budget, chunk_size=chunk_size, rank=rank, hbm_store_ways=hbm_store_ways)
+        self.init_parameters(seed)
+        B, hid, dev = batch_size, self.hidden_size, self.device
+        # static activations of one decode token (graph-capturable)
+        self.x = torch.zeros(B, hid, dtype=BF16, device=dev)            # residual stream
+        self.h = torch.zeros(B, hid, dtype=BF16, device=dev)            # normalised input of the next linear
+        self.q = torch.zeros(B, self.num_heads, 1, 128, dtype=BF16, device=dev)
+        self.k = torch.zeros(B, self.num_key_value_heads, 1, 128, dtype=BF16, device=dev)
+        self.v = torch.zeros(B, self.num_key_value_heads, 1, 128, dtype=BF16, device=dev)
+        self.attn = torch.zeros(B, 1, self.num_heads, 128, dtype=BF16, device=dev)
+        self.act = torch.zeros(B, self.shape.intermediate_size, dtype=BF16, device=dev)
+        self.logits = torch.zeros(B, self.vocab_size, dtype=torch.float32, device=dev)
+        self.tok = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=dev)
+        # kernels of libshadowkv_b200.so per token: embed+norm, per layer qkv + 5 (sparse-KV step) + o_proj + norm +
+        # gate/up + down + norm, lm_head, argmax, counter advance
+        self.launches_per_token = 1 + self.num_layers * (5 + 5 + (1 if self.kv_cache.hbm_store_ways else 0)) + 2
+
+    # ---- parameters ----------------------------------------------------------------------------------------
+    def init_parameters(self, seed: int = 0):
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        sh, dev = self.shape, self.device
+        self.embed_tokens = (torch.randn(sh.vocab_size, sh.hidden_size, generator=g, device=dev) * 0.02).to(BF16)
+        self.lm_head = (torch.randn(sh.vocab_size, sh.hidden_size, generator=g, device=dev) * 0.02).to(BF16)
+        self.norm_weight = (1.0 + 0.1 * torch.randn(sh.hidden_size, generator=g, device=dev)).to(BF16)
+        self.cos_sin_cache = synth.cos_sin_table(self.max_length + 1024, theta=sh.rope_theta, glm=sh.glm_rope, device=dev)
+        self.layers = [LlamaLayer(i).init_parameters(sh, g, dev) for i in range(self.num_layers)]
+
+    def weight_bytes(self) -> int:
+        """Bytes one decode token streams from the dense weights (every layer + lm_head; embedding rows excluded)."""
+        per = sum(t.numel() * 2 for t in (self.layers[0].wqkv, self.layers[0].wo, self.layers[0].gate_up_proj,
+                                          self.layers[0].down_proj))
+        return per * self.num_layers + self.lm_head.numel() * 2
+
+    # ---- reference-named pieces of layer_compute --------------------------------------------------------------
+    def pre_attention_compute(self, hidden_states, buffer: LlamaLayer, num_heads: int, num_key_value_heads: int,
+                              head_dim: int, position: int | None = None, pos_dev=None, normed=None, out=None):
+        """llama.py:354-385 (+ ``apply_rotary_pos_emb``, :283-301, when ``position`` is given -- the reference applies
+        it right after, base.py:320).  hidden_states [B, hidden] (or [B,1,hidden]); returns q [B,Hq,1,D], k, v
+        [B,H,1,D].  ``normed``: the already normalised input (the whole-token runner fuses the norm into the
+        previous step)."""
+        x = hidden_states.reshape(-1, self.hidden_size) if hidden_states is not None else None
+        h = normed if normed is not None else dense.rmsnorm(x, buffer.input_layernorm_weight,
+                                                            buffer.input_layernorm_variance_epsilon)
+        q_out, k_out, v_out = out if out is not None else (None, None, None)
+        return dense.linear_qkv_rope(h, buffer.wqkv, num_heads, num_key_value_heads,
+                                     self.cos_sin_cache if position is not None else None, position or 0,
+                                     bias=buffer.bqkv, glm=self.shape.glm_rope, pos_dev=pos_dev,
+                                     q_out=q_out, k_out=k_out, v_out=v_out)
+
+    def post_attention_compute(self, attn_output, residual, buffer: LlamaLayer, out=None):
+        """llama.py:387-427: o_proj + residual, rmsnorm, gate/up, SiLU*mul, down + residual.  attn_output
+        [B, 1, Hq, D] / [B, hidden]; residual [B, hidden]; returns the new hidden states [B, hidden] (``out`` may be
+        ``residual``)."""
+        B = residual.shape[0]
+        x1 = dense.linear(attn_output.reshape(B, -1), buffer.wo, residual=residual, out=out)
+        h = dense.rmsnorm(x1, buffer.post_attention_layernorm_weight, buffer.post_attention_layernorm_variance_epsilon,
+                          out=self.h if out is not None else None)
+        act = dense.linear_silu_mul(h, buffer.gate_up_proj, out=self.act if out is not None else None)
+        return dense.linear(act, buffer.down_proj, residual=x1, out=x1 if out is not None else None)
+
+    def layer_compute(self, buffer: LlamaLayer, layer_idx: int, hidden_states, position_ids):
+        """base.py:296-349, decode branch: hidden_states [B,1,hidden], position_ids [B,1] (all rows equal, as the
+        reference's generate loop makes them, base.py:628-636)."""
+        if hidden_states.shape[1] != 1:
+            raise NotImplementedError("prefill (q_len > 1) of the dense stack is outside the decode path of this repo")
+        pos = int(position_ids.reshape(-1)[0])
+        residual = hidden_states.reshape(-1, self.hidden_size).contiguous()
+        q, k, v = self.pre_attention_compute(residual, buffer, self.num_heads, self.num_key_value_heads, self.head_dim,
+                                             position=pos)
+        attn = self.kv_cache.decode_layer(layer_idx, q, k, v, self.cos_sin_cache)
+        return self.post_attention_compute(attn, residual, buffer).view(-1, 1, self.hidden_size)
+
+    def inference(self, input_ids, position_ids):
+        """base.py:131-159 for a decode token: [B,1] ids -> logits [B,1,vocab] float32."""
+        hidden_states = self.embed_tokens[input_ids]                      # F.embedding, base.py:141
+        for idx in range(self.num_layers):
+            hidden_states = self.layer_compute(self.layers[idx], idx, hidden_states, position_ids)
+        h = dense.rmsnorm(hidden_states.reshape(-1, self.hidden_size), self.norm_weight, self.norm_variance_epsilon)
+        return dense.linear_f32(h, self.lm_head).view(-1, 1, self.vocab_size)
+
+    # ---- one decode token with device-side counters: the body of the CUDA graph ---------------------------------
+    def _token_body(self):
+        c, L = self.kv_cache, self.layers
+        Hq, H = self.num_heads, self.num_key_value_heads
+        dense.embed_rmsnorm(self.tok, self.embed_tokens, L[0].input_layernorm_weight,
+                            L[0].input_layernorm_variance_epsilon, self.x, self.h)
+        for l, buf in enumerate(L):
+            self.pre_attention_compute(None, buf, Hq, H, 128, position=c.prefill, pos_dev=c.gen_dev, normed=self.h,
+                                       out=(self.q, self.k, self.v))
+            c.decode_layer(l, self.q, self.k, self.v, self.cos_sin_cache, out=self.attn, device_counters=True)
+            dense.linear(self.attn.view(self.batch_size, -1), buf.wo, residual=self.x, out=self.x)
+            dense.rmsnorm(self.x, buf.post_attention_layernorm_weight, buf.post_attention_layernorm_variance_epsilon,
+                          out=self.h)
+            dense.linear_silu_mul(self.h, buf.gate_up_proj, out=self.act)
+            dense.linear(self.act, buf.down_proj, residual=self.x, out=self.x)
+            nxt = L[l + 1].input_layernorm_weight if l + 1 < len(L) else self.norm_weight
+            dense.rmsnorm(self.x, nxt, self.norm_variance_epsilon, out=self.h)
+        dense.linear_f32(self.h, self.lm_head, out=self.logits)
+        dense.argmax(self.logits, out=self.tok)
+        c.join_side_streams()
+        c.advance_device_counters()
+
+    def capture(self, warmup: int = 1):
+        """Warm up eagerly (real decode steps), then capture one token as a CUDA graph."""
+        c = self.kv_cache
+        c.reset_device_counters()
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self._token_body()
+                c.note_replayed_steps(1)
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._token_body()
+        return self
+
+    def decode_token(self):
+        """Enqueue one greedy decode token (input: ``self.tok``; output: ``self.tok`` / ``self.logits``)."""
+        c = self.kv_cache
+        if c.sparse_end + c.gen_offset + 1 > c.buf_len:
+            raise RuntimeError(f"generation buffer full ({c.buf_len - c.sparse_end} tokens)")
+        with torch.cuda.stream(self.stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._token_body()
+        c.note_replayed_steps(1)
+
+    def generate(self, first_token: torch.Tensor, gen_len: int):
+        """Greedy loop of base.py:626-640 (temperature 0): returns [B, gen_len] generated ids."""
+        with torch.cuda.stream(self.stream):
+            self.tok.copy_(first_token.reshape(-1))
+        out = []
+        for _ in range(gen_len):
+            self.decode_token()
+            with torch.cuda.stream(self.stream):
+                out.append(self.tok.clone())
+        self.stream.synchronize()
+        return torch.stack(out, dim=1)
