@@ -65,6 +65,9 @@ def parse_args():
                     help="ways per (layer,b,h) of the optional HBM chunk store measured as a SECOND configuration "
                          "after the headline run (0 = skip); the headline numbers never use it")
     ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--no-whole-model", action="store_true",
+                    help="skip the whole-layer-stack section (dense remainder of every layer + lm_head, SURVEY.md 8 f2)")
+    ap.add_argument("--whole-model-steps", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -419,6 +422,22 @@ def run_ours(args, rank, world, local_rank, n_gpus):
         kernels, roofline, pcie = kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev,
                                                full=not args.no_kernel_table)
 
+    # ---- whole layer stack (section 8 f2): dense remainder of every layer + lm_head around the same decode step ------
+    whole = None
+    if world == 1 and not args.no_whole_model and B <= 32 and not heads_mode:
+        try:
+            from shadowkv_b200.llama import Llama
+            from tools.bench_decode_model import whole_model
+            model = Llama(full_shape, batch_size=B, max_length=args.ctx, device=f"cuda:{local_rank}", num_layers=L,
+                          kv_cache=cache)
+            whole = whole_model(model, steps=args.whole_model_steps, warmup=4, noise=args.noise,
+                                modes=("hot", "native", "library"), ops=True)
+            whole["note"] = ("context for the headline, not part of value / e2e: decode tokens/s of the whole model with "
+                             "random-init weights; the sparse-KV step consumes the same synthetic q/k/v as the headline")
+            del model
+        except Exception as e:  # noqa: BLE001  -- the headline must not die with the extra section
+            whole = {"error": repr(e)[:300]}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         dt, threads, done = cpu_reference_layer_time(args, shape, L, warmup=2, steps=1000, max_seconds=args.cpu_seconds)
@@ -438,7 +457,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
                         "d2h_bytes_per_step": run_h.d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "api": "shadowkv_b200.engine.DecodeStepGraph.step_host"},
                 "gpu_launches": run_d.launches_per_step * args.steps,
-                "hbm_chunk_store": store, "roofline": roofline, "kernels": kernels, "pcie": pcie, "cpu_baseline": cpu, "clocks": clocks,
+                "hbm_chunk_store": store, "whole_model": whole, "roofline": roofline, "kernels": kernels, "pcie": pcie, "cpu_baseline": cpu, "clocks": clocks,
                 "numa_binding_rank0": numa, "peaks": peaks, "lib": _lib.version(), "setup_s": round(setup_s, 1), "checksum": checksum}
         emit(line)
     if world > 1:

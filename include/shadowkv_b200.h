@@ -326,6 +326,11 @@ typedef struct skv_dense_epilogue {
                           * 2 GLM: interleaved pairs over the first 64 dims (row = [cos32|sin32]) */
   int32_t cos_sin_rows;  /* rows of the cos_sin table                                           */
   int32_t pos;           /* token position (+ *pos_dev when pos_dev != NULL)                    */
+  int32_t static_weights; /* nonzero: W was written before the PREVIOUS kernel of the stream started (model
+                          * weights).  The kernel then streams W into shared memory before it waits for that
+                          * kernel (programmatic dependent launch), hiding its ramp-up.  0: W may have been
+                          * produced by the previous kernel; nothing is read early.               */
+  int32_t reserved;
   const int32_t *pos_dev;
   const skv_bf16 *bias;  /* [out_features] or NULL (GLM's bqkv)                                 */
   const skv_bf16 *resid; /* RESID: [B, out_features] or NULL; may alias out                     */
@@ -333,6 +338,9 @@ typedef struct skv_dense_epilogue {
   void *out;             /* F32: float*; RESID / SILU_MUL: bf16*; QKV_ROPE: q                   */
   skv_bf16 *k_out;       /* QKV_ROPE                                                            */
   skv_bf16 *v_out;       /* QKV_ROPE                                                            */
+  const void *prefetch_next; /* optional hint: the weights the NEXT linear of the stream will read (16-byte aligned).   */
+  int64_t prefetch_bytes;    /* Every CTA pulls its share of the first prefetch_bytes into L2 once it has issued its own
+                              * last load, so HBM keeps streaming through the kernel's tail and the hand-over.         */
 } skv_dense_epilogue;
 
 /* Device scratch of skv_dense_linear (split-tile partial sums and per-tile arrival counters).  The caller
@@ -349,6 +357,11 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
  * stream) when x_out != NULL. */
 int skv_rmsnorm(const skv_bf16 *x, const int64_t *tok, const skv_bf16 *emb, const skv_bf16 *w, float eps,
                 skv_bf16 *x_out, skv_bf16 *h_out, int batch, int hidden, skv_stream_t stream);
+
+/* Hint: pull `bytes` bytes at `ptr` (16-byte aligned; weights of an upcoming skv_dense_linear) into L2.  Returns as
+ * soon as the prefetches are issued; reads nothing the caller can observe.  Used by the whole-token runner to keep
+ * HBM streaming while the sparse-KV step waits on PCIe. */
+int skv_l2_prefetch(const void *ptr, int64_t bytes, skv_stream_t stream);
 
 /* tok[b] = index of the largest logit of row b (lowest index on ties): greedy decoding,
  * sample_token with temperature 0 (tensor_op.py:291-293, called at base.py:612). */

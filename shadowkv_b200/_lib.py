@@ -35,9 +35,10 @@ class VStore(C.Structure):
 class DenseEpilogue(C.Structure):
     """struct skv_dense_epilogue (include/shadowkv_b200.h)."""
     _fields_ = [("mode", C.c_int32), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("rope_mode", C.c_int32),
-                ("cos_sin_rows", C.c_int32), ("pos", C.c_int32), ("pos_dev", C.c_void_p), ("bias", C.c_void_p),
+                ("cos_sin_rows", C.c_int32), ("pos", C.c_int32), ("static_weights", C.c_int32), ("reserved", C.c_int32),
+                ("pos_dev", C.c_void_p), ("bias", C.c_void_p),
                 ("resid", C.c_void_p), ("cos_sin", C.c_void_p), ("out", C.c_void_p), ("k_out", C.c_void_p),
-                ("v_out", C.c_void_p)]
+                ("v_out", C.c_void_p), ("prefetch_next", C.c_void_p), ("prefetch_bytes", C.c_int64)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -78,6 +79,7 @@ _SIGS = {
     "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
     "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "skv_argmax": [_p, _p, _i, _i, _p],
+    "skv_l2_prefetch": [_p, _l, _p],
 }
 # every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
 EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",

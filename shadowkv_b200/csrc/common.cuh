@@ -34,6 +34,15 @@ static __device__ long long g_skv_trace[8192];
   do {                                                                                   \
     if ((cta) < 256) g_skv_trace[(cta) * 32 + (slot)] = clock64();                       \
   } while (0)
+// wall-clock variant (%globaltimer, ns): comparable across CTAs and across consecutive launches
+#define SKV_STAMP_NS(row, slot)                                                          \
+  do {                                                                                   \
+    if ((row) >= 0 && (row) < 256) {                                                     \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      g_skv_trace[(row) * 32 + (slot)] = (long long)t_;                                  \
+    }                                                                                    \
+  } while (0)
 #define SKV_TRACE_READER(unit)                                                           \
   extern "C" int skv_debug_read_trace_##unit(long long *host_out, int n) {               \
     cudaDeviceSynchronize();                                                             \
@@ -42,6 +51,7 @@ static __device__ long long g_skv_trace[8192];
 #else
 #define SKV_STAMP(cta, slot) do { } while (0)
 #define SKV_STAMP_ANY(cta, slot) do { } while (0)
+#define SKV_STAMP_NS(row, slot) do { } while (0)
 #define SKV_TRACE_READER(unit)
 #endif
 

@@ -35,13 +35,18 @@ constexpr int64_t kDnPartBytes = int64_t(kDnMaxCtas) * 2 * kDnMaxBatch * 128 * 4
 
 struct DenseParams {
   int B, K, KS, Nout, T, mode, stages, total;
-  float *part;            // [ctas][2][32][128] fp32 partial tiles
+  float *part;            // [ctas][2][128 rows][NPAD] fp32 partial tiles
   int *tile_cnt;          // [T] arrivals per split tile; zero between launches
   const __nv_bfloat16 *resid, *bias, *cos_sin;
   __nv_bfloat16 *out, *k_out, *v_out;
   float *out_f32;
   int up_row0;            // SILU_MUL: first "up" row of W (= F); tile t = gate rows [64t, 64t+64) + up rows [F+64t, ..)
   int q_heads, kv_heads, rope_mode, cos_sin_rows, pos;
+  int static_w;           // W may be read before griddepcontrol.wait
+  int trace_id;           // SKV_TRACE builds: launch counter
+  int reorder;            // split tiles first (SegOrder)
+  const unsigned char *pf_ptr;   // next linear's weights: pulled into L2 once this CTA has issued its last load
+  long long pf_bytes;
   const int *pos_dev;
 };
 
@@ -52,6 +57,28 @@ __device__ __forceinline__ int dn_cta_of(int w, int total, int n) {
   while (c > 0 && dn_begin(c, total, n) > w) --c;
   return c;
 }
+// The slabs [w0, w1) of one CTA as tile segments, in PROCESSING order: the segment that finishes a tile begun by the
+// previous CTA first, then the segment that begins a tile the next CTA finishes, then the tiles the CTA owns alone.
+// Split tiles need a cross-CTA fix-up (partials through L2, last arriver sums); doing them first hides that latency
+// behind the stream of the complete tiles instead of leaving it at the end of the kernel.
+struct SegOrder {
+  int w0, w1, KS, ta, n, last_partial;
+  __device__ SegOrder(int w0_, int w1_, int KS_, int reorder) : w0(w0_), w1(w1_), KS(KS_) {
+    ta = w0 / KS;
+    const int tb = (w1 - 1) / KS;
+    n = w1 > w0 ? tb - ta + 1 : 0;
+    last_partial = (reorder && n >= 2 && (w1 % KS) != 0) ? 1 : 0;
+  }
+  __device__ void get(int i, int &t, int &s0, int &s1) const {
+    if (i == 0) { t = ta; s0 = w0 - ta * KS; s1 = min(KS, w1 - ta * KS); return; }
+    if (last_partial) {
+      if (i == 1) { t = ta + n - 1; s0 = 0; s1 = w1 - t * KS; return; }
+      t = ta + i - 1; s0 = 0; s1 = KS; return;
+    }
+    t = ta + i; s0 = 0; s1 = min(KS, w1 - t * KS);
+  }
+};
+
 __device__ __forceinline__ float bfr(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -150,7 +177,7 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int 
 }
 
 template <int NPAD>
-__global__ void __launch_bounds__(kDnThreads, 2)
+__global__ void __launch_bounds__(kDnThreads, 1)
     dense_streamk_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                          DenseParams p) {
   constexpr int kStageBytes = kDnWBytes + NPAD * 128;
@@ -168,7 +195,7 @@ __global__ void __launch_bounds__(kDnThreads, 2)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x, nc = gridDim.x;
   const int w0 = dn_begin(c, p.total, nc), w1 = dn_begin(c + 1, p.total, nc);
-  const int n_slabs = w1 - w0;
+  const SegOrder order(w0, w1, p.KS, p.reorder);
   const int stages = p.stages;
 
   auto tile_rows = [&](int t, int &r0, int &r1) {
@@ -176,6 +203,9 @@ __global__ void __launch_bounds__(kDnThreads, 2)
     else { r0 = t * 128; r1 = r0 + 64; }
   };
 
+  // trace rows: 16 per launch (first and last 8 CTAs), 16 launches
+  const int trow = (c < 8 ? c : (c >= nc - 8 ? 8 + c - (nc - 8) : -1000)) + (p.trace_id & 15) * 16;
+  if (threadIdx.x == 0) SKV_STAMP_NS(trow, 0);
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
@@ -184,52 +214,72 @@ __global__ void __launch_bounds__(kDnThreads, 2)
     // The weights do not depend on the previous kernel: fill the ring now (under a programmatic launch this runs
     // while the predecessor is still finishing).
     const uint64_t pol = l2_policy_evict_first();
-    for (int it = 0; it < stages && it < n_slabs; ++it) {
-      const int w = w0 + it, t = w / p.KS, s = w - t * p.KS;
-      int r0, r1;
-      tile_rows(t, r0, r1);
-      unsigned char *dst = ring + it * kStageBytes;
-      mbarrier_expect_tx(&full_bar[it], kStageBytes);
-      tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[it], pol);
-      tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[it], pol);
+    if (p.static_w) {
+      int it = 0;
+      for (int i = 0; i < order.n && it < stages; ++i) {
+        int t, s0, s1, r0, r1;
+        order.get(i, t, s0, s1);
+        tile_rows(t, r0, r1);
+        for (int s = s0; s < s1 && it < stages; ++s, ++it) {
+          unsigned char *dst = ring + it * kStageBytes;
+          mbarrier_expect_tx(&full_bar[it], kStageBytes);
+          tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[it], pol);
+          tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[it], pol);
+        }
+      }
     }
   }
-  // x, the residual, the workspace and every output belong to the predecessor until here
-  pdl_wait();
-
+  if (threadIdx.x == 0) SKV_STAMP_NS(trow, 1);
   if (warp == 1) tcgen05_alloc(tmem_slot, 2 * kAccCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SKV_STAMP_NS(trow, 3);
+  // x, the residual, the workspace and every output belong to the predecessor until here
+  pdl_wait();
+  if (threadIdx.x == 0) SKV_STAMP_NS(trow, 2);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      for (int it = 0; it < n_slabs; ++it) {
-        const int stage = it % stages;
-        const int w = w0 + it, t = w / p.KS, s = w - t * p.KS;
-        unsigned char *dst = ring + stage * kStageBytes;
-        if (it >= stages) {
-          int r0, r1;
-          tile_rows(t, r0, r1);
-          mbarrier_wait(&empty_bar[stage], ((it / stages) & 1) ^ 1);
-          mbarrier_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[stage], pol);
-          tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[stage], pol);
+      int it = 0;
+      for (int i = 0; i < order.n; ++i) {
+        int t, s0, s1, r0, r1;
+        order.get(i, t, s0, s1);
+        tile_rows(t, r0, r1);
+        for (int s = s0; s < s1; ++s, ++it) {
+          const int stage = it % stages;
+          unsigned char *dst = ring + stage * kStageBytes;
+          if (it >= stages || !p.static_w) {
+            if (it >= stages) mbarrier_wait(&empty_bar[stage], ((it / stages) & 1) ^ 1);
+            mbarrier_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d_hint(dst, &map_w, s * 64, r0, &full_bar[stage], pol);
+            tma_load_2d_hint(dst + kDnWBytes / 2, &map_w, s * 64, r1, &full_bar[stage], pol);
+          }
+          tma_load_2d(dst + kDnWBytes, &map_x, s * 64, 0, &full_bar[stage]);
         }
-        tma_load_2d(dst + kDnWBytes, &map_x, s * 64, 0, &full_bar[stage]);
+      }
+      // This CTA's stream is issued.  What follows in the kernel (split-tile fix-up, epilogues, hand-over to the next
+      // kernel) leaves HBM idle for microseconds: use them to pull the head of the NEXT linear's weights into L2.
+      if (p.pf_bytes > 0) {
+        const long long slice = ((p.pf_bytes + nc - 1) / nc + 4095) & ~4095LL;
+        const long long lo = (long long)c * slice, hi = min(p.pf_bytes, lo + slice);
+        for (long long o = lo; o < hi; o += 4096) {
+          const int n = int(min(4096LL, hi - o)) & ~15;
+          if (n > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + o), "r"(n) : "memory");
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_m128(kAccCols);
-      int it = 0, seg = 0;
-      for (int w = w0; w < w1; ++seg) {
-        const int t = w / p.KS, s0 = w - t * p.KS;
-        const int s1 = min(p.KS, s0 + (w1 - w));
+      int it = 0;
+      for (int seg = 0; seg < order.n; ++seg) {
+        int t, s0, s1;
+        order.get(seg, t, s0, s1);
         const int acc = seg & 1;
         mbarrier_wait(&acc_empty[acc], ((seg >> 1) & 1) ^ 1);
         tcgen05_fence_after();
@@ -237,6 +287,7 @@ __global__ void __launch_bounds__(kDnThreads, 2)
         for (int s = s0; s < s1; ++s, ++it) {
           const int stage = it % stages;
           mbarrier_wait(&full_bar[stage], (it / stages) & 1);
+          if (it == 0) SKV_STAMP_NS(trow, 4);
           tcgen05_fence_after();
           const uint64_t da = umma_desc_k_sw128(smem_addr(ring + stage * kStageBytes));
           const uint64_t db = umma_desc_k_sw128(smem_addr(ring + stage * kStageBytes + kDnWBytes));
@@ -246,8 +297,8 @@ __global__ void __launch_bounds__(kDnThreads, 2)
           tcgen05_commit(&empty_bar[stage]);
         }
         tcgen05_commit(&acc_full[acc]);
-        w += s1 - s0;
       }
+      SKV_STAMP_NS(trow, 5);
     }
   } else {
     // ===== epilogue: thread = W row of the tile =====
@@ -259,13 +310,13 @@ __global__ void __launch_bounds__(kDnThreads, 2)
       pos = p.pos + (p.pos_dev ? *p.pos_dev : 0);
       pos = max(0, min(pos, p.cos_sin_rows - 1));
     }
-    int seg = 0;
-    for (int w = w0; w < w1; ++seg) {
-      const int t = w / p.KS, s0 = w - t * p.KS;
-      const int s1 = min(p.KS, s0 + (w1 - w));
-      w += s1 - s0;
+    for (int seg = 0; seg < order.n; ++seg) {
+      int t, s0, s1;
+      order.get(seg, t, s0, s1);
+      const bool final_seg = seg == order.n - 1;
       const int acc = seg & 1;
       mbarrier_wait(&acc_full[acc], (seg >> 1) & 1);
+      if (leader && final_seg) SKV_STAMP_NS(trow, 6);
       tcgen05_fence_after();
       float v[NPAD];
       {
@@ -283,11 +334,13 @@ __global__ void __launch_bounds__(kDnThreads, 2)
       if (!(s0 == 0 && s1 == p.KS)) {
         // split tile: park the partial sums; the CTA that arrives last adds them up in CTA order
         const int slot = (t * p.KS < w0) ? 0 : 1;
-        float *mine = p.part + (size_t(c) * 2 + slot) * kDnMaxBatch * 128;
+        constexpr int kPartFloats = 128 * NPAD;        // one partial tile: [row][NPAD] fp32, a thread's row contiguous
+        float4 *mine = reinterpret_cast<float4 *>(p.part + (size_t(c) * 2 + slot) * kPartFloats + row * NPAD);
 #pragma unroll
-        for (int b = 0; b < NPAD; ++b)
-          if (b < p.B) __stcg(mine + b * 128 + row, v[b]);
+        for (int j = 0; j < NPAD / 4; ++j)
+          if (4 * j < p.B) __stcg(mine + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         __threadfence();
+        if (leader && final_seg) SKV_STAMP_NS(trow, 7);
         epi_bar();
         if (leader) {
           const int cf = dn_cta_of(t * p.KS, p.total, nc), cl = dn_cta_of(t * p.KS + p.KS - 1, p.total, nc);
@@ -299,23 +352,44 @@ __global__ void __launch_bounds__(kDnThreads, 2)
         epi_bar();
         const int last = s_flag[0], cf = s_flag[1], cl = s_flag[2];
         epi_bar();                                     // s_flag may be rewritten by the next split tile
+        if (leader && final_seg) SKV_STAMP_NS(trow, 8);
         if (!last) continue;
         __threadfence();
 #pragma unroll
         for (int b = 0; b < NPAD; ++b) v[b] = 0.f;
-        for (int cc = cf; cc <= cl; ++cc) {
-          const int sl = (t * p.KS < dn_begin(cc, p.total, nc)) ? 0 : 1;
-          const float *src = p.part + (size_t(cc) * 2 + sl) * kDnMaxBatch * 128;
+        // sum in CTA order (deterministic); the loads of kGroup contributors are in flight together
+        constexpr int kGroup = NPAD == 16 ? 8 : 4;
+        for (int c0 = cf; c0 <= cl; c0 += kGroup) {
+          float4 tmp[kGroup][NPAD / 4];
 #pragma unroll
-          for (int b = 0; b < NPAD; ++b)
-            if (b < p.B) v[b] += __ldcg(src + b * 128 + row);
+          for (int g = 0; g < kGroup; ++g) {
+            const int cc = min(c0 + g, cl);
+            const int sl = (t * p.KS < dn_begin(cc, p.total, nc)) ? 0 : 1;
+            const float4 *src = reinterpret_cast<const float4 *>(p.part + (size_t(cc) * 2 + sl) * kPartFloats + row * NPAD);
+#pragma unroll
+            for (int j = 0; j < NPAD / 4; ++j)
+              if (4 * j < p.B) tmp[g][j] = __ldcg(src + j);
+          }
+#pragma unroll
+          for (int g = 0; g < kGroup; ++g) {
+            if (c0 + g <= cl) {
+#pragma unroll
+              for (int j = 0; j < NPAD / 4; ++j) {
+                if (4 * j >= p.B) continue;
+                v[4 * j] += tmp[g][j].x; v[4 * j + 1] += tmp[g][j].y; v[4 * j + 2] += tmp[g][j].z; v[4 * j + 3] += tmp[g][j].w;
+              }
+            }
+          }
         }
       }
+      if (leader && final_seg) SKV_STAMP_NS(trow, 9);
       dense_epilogue<NPAD>(p, t, row, v, s_x, pos);
+      if (leader && final_seg) SKV_STAMP_NS(trow, 10);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SKV_STAMP_NS(trow, 11);
   if (warp == 1) tcgen05_dealloc(tmem_base, 2 * kAccCols);
 }
 
@@ -396,6 +470,23 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float *logits, int64
   }
 }
 
+// ---- L2 prefetch of a byte range (weights of an upcoming linear) --------------------------------------------
+// One elected thread per warp issues bulk L2 prefetches of 8 KiB pieces; the kernel returns as soon as they are issued.
+constexpr int kPfPiece = 8192;
+__global__ void __launch_bounds__(128) l2_prefetch_kernel(const unsigned char *base, long long bytes) {
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  if (lane == 0) {
+    for (long long off = warp * kPfPiece; off < bytes; off += nwarps * kPfPiece) {
+      const long long n = min((long long)kPfPiece, bytes - off) & ~15LL;
+      if (n > 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(int(n)) : "memory");
+    }
+  }
+}
+
 static int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
@@ -405,13 +496,17 @@ template <int NPAD>
 static int launch_dense(const CUtensorMap &mw, const CUtensorMap &mx, DenseParams &p, int ctas, cudaStream_t st) {
   constexpr int kStageBytes = kDnWBytes + NPAD * 128;
   const int fixed = 128 * (NPAD + 1) * 4 + (2 * kDnMaxStages + 4) * 8 + 8 + 16 + 64;
-  // default: a ring that leaves room for the NEXT kernel's CTA on the same SM (227 KiB per SM), so its weight
-  // prefetch overlaps this kernel's tail
-  int stages = env_int("SKV_DENSE_STAGES", NPAD == 16 ? 5 : 4);
+  // default: 6 stages (96 KiB of weights in flight per SM, 14 MB over the GPU ~ the bandwidth-delay product).  Measured
+  // on the lm_head stream: 5 stages 171 us, 6: 163 us (= the measured HBM copy peak), 8: 167 us, 11: 183 us -- a deeper
+  // ring oversubscribes the memory system and the SMs finish up to 10 us apart.
+  int stages = env_int("SKV_DENSE_STAGES", 6);
   if (stages < 2) stages = 2;
   if (stages > kDnMaxStages) stages = kDnMaxStages;
   while (stages > 2 && stages * kStageBytes + fixed > 227 * 1024) --stages;
   p.stages = stages;
+  p.reorder = env_int("SKV_DENSE_ORDER", 1);
+  static int launches = 0;
+  p.trace_id = launches++;
   const int smem = stages * kStageBytes + fixed;
   static int attr = 0;
   if (smem > attr) {
@@ -441,6 +536,11 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
     return SKV_ERR_UNSUPPORTED;
   }
   DenseParams p{};
+  p.static_w = epi->static_weights != 0;
+  if (epi->prefetch_next && epi->prefetch_bytes > 0 && (reinterpret_cast<uintptr_t>(epi->prefetch_next) & 15) == 0) {
+    p.pf_ptr = reinterpret_cast<const unsigned char *>(epi->prefetch_next);
+    p.pf_bytes = epi->prefetch_bytes;
+  }
   p.B = batch; p.K = in_features; p.KS = in_features / 64; p.Nout = out_features; p.mode = epi->mode;
   p.tile_cnt = reinterpret_cast<int *>(workspace);
   p.part = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + kDnCounterBytes);
@@ -505,6 +605,18 @@ int skv_rmsnorm(const skv_bf16 *x, const int64_t *tok, const skv_bf16 *emb, cons
   return launch_status("rmsnorm_kernel");
 }
 
+int skv_l2_prefetch(const void *ptr, int64_t bytes, skv_stream_t stream) {
+  if (!ptr || bytes < 0) { set_error("l2_prefetch: bad argument"); return SKV_ERR_ARGUMENT; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) { set_error("l2_prefetch: pointer must be 16-byte aligned"); return SKV_ERR_ARGUMENT; }
+  if (bytes < 16) return SKV_OK;
+  long long pieces = (bytes + kPfPiece - 1) / kPfPiece;
+  int grid = int(pieces < 4LL * kNumSMs ? (pieces + 3) / 4 : kNumSMs);
+  cudaError_t e = launch_kernel(l2_prefetch_kernel, dim3(grid), dim3(128), 0, as_stream(stream), true,
+                                reinterpret_cast<const unsigned char *>(ptr), (long long)bytes);
+  if (e != cudaSuccess) { set_error("l2_prefetch_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("l2_prefetch_kernel");
+}
+
 int skv_argmax(const float *logits, int64_t *tok, int batch, int vocab, skv_stream_t stream) {
   if (!logits || !tok) { set_error("argmax: null pointer"); return SKV_ERR_ARGUMENT; }
   if (batch < 1 || vocab < 1) { set_error("argmax: empty input"); return SKV_ERR_UNSUPPORTED; }
@@ -514,3 +626,5 @@ int skv_argmax(const float *logits, int64_t *tok, int batch, int vocab, skv_stre
 }
 
 }  // extern "C"
+
+SKV_TRACE_READER(dense)

@@ -127,6 +127,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void *smem_dst, const CUtensorM
       : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
 // 2-D bf16 row-major [rows, cols] tensor map with box {box_cols, box_rows}, 128-byte swizzle, zero OOB fill.
 // Cached per (base, shape, box); returns SKV_OK or SKV_ERR_DRIVER.
 int make_tensor_map_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,

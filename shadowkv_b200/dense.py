@@ -1,7 +1,12 @@
 """Dense remainder of the decode layer: torch-tensor wrappers over Part 4 of the C ABI
 (include/shadowkv_b200.h).  Each function replaces the library call named in its docstring for the decode case
 (one token per sequence, batch <= 32); every output can be preallocated (``out=``) so a whole token can be captured
-in a CUDA graph.  No fallback: the kernels are the only implementation."""
+in a CUDA graph.  No fallback: the kernels are the only implementation.
+
+``static_weights=True`` (model weights: written long before the call) lets the kernel stream W into shared memory
+while the previous kernel of the stream is still running (programmatic dependent launch); with the default False
+nothing is read before the previous kernel has completed.  ``prefetch=(tensor, byte_offset, nbytes)`` names the head
+of the weights the NEXT linear will read: the kernel pulls it into L2 during its own tail."""
 from __future__ import annotations
 
 import ctypes as C
@@ -42,7 +47,12 @@ def _check_x(x: torch.Tensor, W: torch.Tensor):
         raise ValueError("x and W must be CUDA tensors")
 
 
-def _launch(x, W, epi: "_lib.DenseEpilogue", what: str):
+def _launch(x, W, epi: "_lib.DenseEpilogue", what: str, prefetch=None):
+    if prefetch is not None:            # (tensor, byte offset, bytes): head of the next linear's weights -> L2
+        t, off, n = prefetch
+        n = min(n, t.numel() * t.element_size() - off)
+        if n > 0:
+            epi.prefetch_next, epi.prefetch_bytes = t.data_ptr() + off, n
     check(lib.skv_dense_linear(x.data_ptr(), W.data_ptr(), x.shape[0], x.shape[1], W.shape[0], C.byref(epi),
                                workspace(x.device).data_ptr(), _cs()), what)
 
@@ -69,38 +79,41 @@ def embed_rmsnorm(tok: torch.Tensor, emb: torch.Tensor, w: torch.Tensor, eps: fl
 
 
 def linear(x: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
-           out: torch.Tensor | None = None) -> torch.Tensor:
+           out: torch.Tensor | None = None, static_weights: bool = False, prefetch=None) -> torch.Tensor:
     """``F.linear(x, W, bias)`` (+ ``residual + ...``): o_proj and down_proj with their residual adds, reference
     models/llama.py:408-412, 424-426.  ``out`` may be ``residual`` (in-place residual stream)."""
     _check_x(x, W)
     out = torch.empty(x.shape[0], W.shape[0], dtype=torch.bfloat16, device=x.device) if out is None else out
     epi = _lib.DenseEpilogue(mode=RESID, bias=bias.data_ptr() if bias is not None else None,
-                             resid=residual.data_ptr() if residual is not None else None, out=out.data_ptr())
-    _launch(x, W, epi, "dense_linear")
+                             resid=residual.data_ptr() if residual is not None else None, out=out.data_ptr(),
+                             static_weights=int(static_weights))
+    _launch(x, W, epi, "dense_linear", prefetch)
     return out
 
 
-def linear_f32(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def linear_f32(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor | None = None,
+               static_weights: bool = False, prefetch=None) -> torch.Tensor:
     """``F.linear(x, lm_head).float()`` (reference models/base.py:157)."""
     _check_x(x, W)
     out = torch.empty(x.shape[0], W.shape[0], dtype=torch.float32, device=x.device) if out is None else out
-    _launch(x, W, _lib.DenseEpilogue(mode=F32, out=out.data_ptr()), "dense_linear_f32")
+    _launch(x, W, _lib.DenseEpilogue(mode=F32, out=out.data_ptr(), static_weights=int(static_weights)), "dense_linear_f32", prefetch)
     return out
 
 
-def linear_silu_mul(x: torch.Tensor, W_gate_up: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def linear_silu_mul(x: torch.Tensor, W_gate_up: torch.Tensor, out: torch.Tensor | None = None,
+                    static_weights: bool = False, prefetch=None) -> torch.Tensor:
     """``F.linear(x, gate_up_proj)`` + ``vllm._custom_ops.silu_and_mul`` (reference models/llama.py:415-421):
     W_gate_up [2F, in] = [gate; up] -> [B, F]."""
     _check_x(x, W_gate_up)
     F_ = W_gate_up.shape[0] // 2
     out = torch.empty(x.shape[0], F_, dtype=torch.bfloat16, device=x.device) if out is None else out
-    _launch(x, W_gate_up, _lib.DenseEpilogue(mode=SILU_MUL, out=out.data_ptr()), "dense_linear_silu_mul")
+    _launch(x, W_gate_up, _lib.DenseEpilogue(mode=SILU_MUL, out=out.data_ptr(), static_weights=int(static_weights)), "dense_linear_silu_mul", prefetch)
     return out
 
 
 def linear_qkv_rope(x: torch.Tensor, wqkv: torch.Tensor, q_heads: int, kv_heads: int, cos_sin: torch.Tensor | None,
                     pos: int, *, bias: torch.Tensor | None = None, glm: bool = False, pos_dev: torch.Tensor | None = None,
-                    q_out=None, k_out=None, v_out=None):
+                    q_out=None, k_out=None, v_out=None, static_weights: bool = False, prefetch=None):
     """``F.linear(h, wqkv[, bqkv])`` + split + ``vllm._custom_ops.rotary_embedding`` on q and k (reference
     models/llama.py:377-385 + 296; models/glm.py:344-357 + 421).  Returns q [B,q_heads,1,128], k, v [B,kv_heads,1,128]
     -- the layout ``ShadowKVCache_CPU.decode_layer`` takes.  cos_sin None: no rotary embedding.  The token position is
@@ -116,8 +129,9 @@ def linear_qkv_rope(x: torch.Tensor, wqkv: torch.Tensor, q_heads: int, kv_heads:
                              pos_dev=pos_dev.data_ptr() if pos_dev is not None else None,
                              bias=bias.data_ptr() if bias is not None else None,
                              cos_sin=cos_sin.data_ptr() if cos_sin is not None else None,
-                             out=q.data_ptr(), k_out=k.data_ptr(), v_out=v.data_ptr())
-    _launch(x, wqkv, epi, "dense_linear_qkv_rope")
+                             out=q.data_ptr(), k_out=k.data_ptr(), v_out=v.data_ptr(),
+                             static_weights=int(static_weights))
+    _launch(x, wqkv, epi, "dense_linear_qkv_rope", prefetch)
     return q, k, v
 
 
@@ -128,3 +142,11 @@ def argmax(logits: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tenso
     out = torch.empty(logits.shape[0], dtype=torch.int64, device=logits.device) if out is None else out
     check(lib.skv_argmax(logits.data_ptr(), out.data_ptr(), logits.shape[0], logits.shape[1], _cs()), "argmax")
     return out
+
+
+def l2_prefetch(t: torch.Tensor, nbytes: int | None = None, offset: int = 0) -> None:
+    """Hint: pull (a byte range of) a contiguous tensor into L2 on the current stream (weights of an upcoming linear)."""
+    total = t.numel() * t.element_size()
+    nbytes = total - offset if nbytes is None else min(nbytes, total - offset)
+    if nbytes > 0:
+        check(lib.skv_l2_prefetch(t.data_ptr() + offset, nbytes, _cs()), "l2_prefetch")

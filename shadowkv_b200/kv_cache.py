@@ -485,7 +485,7 @@ class ShadowKVCache_CPU:
         return out
 
     def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
-                     device_counters=False):
+                     device_counters=False, after_select=None):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
         query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
@@ -502,6 +502,10 @@ class ShadowKVCache_CPU:
                          v_buf=self.v_cache_buffer[layer_idx].data_ptr(),
                          pos_dev=self.gen_dev.data_ptr() if device_counters else None, pos=pos)
         pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
+        if after_select is not None:
+            # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
+            # idle; the runner uses the window to pull the next dense weights into L2 on its own stream
+            after_select()
         if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += 1
             self.gen_offset += 1

@@ -54,7 +54,10 @@ class Llama:
     def __init__(self, model: str | synth.ModelShape = "llama-3.1-8b", batch_size: int = 1, max_length: int = 124928,
                  device: str = "cuda:0", sparse_budget: int = 2048, rank: int = 160, chunk_size: int = 8,
                  num_layers: int | None = None, seed: int = 0, kv_cache: ShadowKVCache_CPU | None = None,
-                 hbm_store_ways: int = 0) -> None:
+                 hbm_store_ways: int = 0, l2_prefetch_mb: float = 96.0, next_prefetch_mb: float = 32.0) -> None:
+        """l2_prefetch_mb: bytes of the layer's o_proj / gate_up weights pulled into L2 (126 MB on B200) on a side
+        stream while the sparse-KV step of the same layer waits on its PCIe fetch (0 disables).
+        next_prefetch_mb: head of the next linear's weights each dense kernel pulls into L2 during its own tail."""
         self.shape = synth.MODELS[model] if isinstance(model, str) else model
         self.device = torch.device(device)
         self.batch_size, self.max_length = batch_size, max_length
@@ -85,6 +88,10 @@ class Llama:
         self.logits = torch.zeros(B, self.vocab_size, dtype=torch.float32, device=dev)
         self.tok = torch.zeros(B, dtype=torch.int64, device=dev)
         self.graph = None
+        self.l2_prefetch_bytes = int(l2_prefetch_mb * 1e6)
+        self.next_prefetch_bytes = int(next_prefetch_mb * 1e6) & ~15
+        self.prefetch_stream = torch.cuda.Stream(device=dev)
+        self._prepared = False
         self.stream = torch.cuda.Stream(device=dev)
         # kernels of libshadowkv_b200.so per token: embed+norm, per layer qkv + 5 (sparse-KV step) + o_proj + norm +
         # gate/up + down + norm, lm_head, argmax, counter advance
@@ -120,18 +127,18 @@ class Llama:
         return dense.linear_qkv_rope(h, buffer.wqkv, num_heads, num_key_value_heads,
                                      self.cos_sin_cache if position is not None else None, position or 0,
                                      bias=buffer.bqkv, glm=self.shape.glm_rope, pos_dev=pos_dev,
-                                     q_out=q_out, k_out=k_out, v_out=v_out)
+                                     q_out=q_out, k_out=k_out, v_out=v_out, static_weights=True)
 
     def post_attention_compute(self, attn_output, residual, buffer: LlamaLayer, out=None):
         """llama.py:387-427: o_proj + residual, rmsnorm, gate/up, SiLU*mul, down + residual.  attn_output
         [B, 1, Hq, D] / [B, hidden]; residual [B, hidden]; returns the new hidden states [B, hidden] (``out`` may be
         ``residual``)."""
         B = residual.shape[0]
-        x1 = dense.linear(attn_output.reshape(B, -1), buffer.wo, residual=residual, out=out)
+        x1 = dense.linear(attn_output.reshape(B, -1), buffer.wo, residual=residual, out=out, static_weights=True)
         h = dense.rmsnorm(x1, buffer.post_attention_layernorm_weight, buffer.post_attention_layernorm_variance_epsilon,
                           out=self.h if out is not None else None)
-        act = dense.linear_silu_mul(h, buffer.gate_up_proj, out=self.act if out is not None else None)
-        return dense.linear(act, buffer.down_proj, residual=x1, out=x1 if out is not None else None)
+        act = dense.linear_silu_mul(h, buffer.gate_up_proj, out=self.act if out is not None else None, static_weights=True)
+        return dense.linear(act, buffer.down_proj, residual=x1, out=x1 if out is not None else None, static_weights=True)
 
     def layer_compute(self, buffer: LlamaLayer, layer_idx: int, hidden_states, position_ids):
         """base.py:296-349, decode branch: hidden_states [B,1,hidden], position_ids [B,1] (all rows equal, as the
@@ -151,34 +158,80 @@ class Llama:
         for idx in range(self.num_layers):
             hidden_states = self.layer_compute(self.layers[idx], idx, hidden_states, position_ids)
         h = dense.rmsnorm(hidden_states.reshape(-1, self.hidden_size), self.norm_weight, self.norm_variance_epsilon)
-        return dense.linear_f32(h, self.lm_head).view(-1, 1, self.vocab_size)
+        return dense.linear_f32(h, self.lm_head, static_weights=True).view(-1, 1, self.vocab_size)
 
     # ---- one decode token with device-side counters: the body of the CUDA graph ---------------------------------
+    def _pre_attention_step(self, l: int):
+        """Fused QKV + RoPE of layer l from the already normalised self.h (device-side position counter)."""
+        c, buf = self.kv_cache, self.layers[l]
+        self.pre_attention_compute(None, buf, self.num_heads, self.num_key_value_heads, 128, position=c.prefill,
+                                   pos_dev=c.gen_dev, normed=self.h, out=(self.q, self.k, self.v))
+
+    def _after_select_hook(self, l: int):
+        return (lambda b=self.layers[l]: self._prefetch_post_attention_weights(b)) if self.l2_prefetch_bytes else None
+
+    def _post_attention_step(self, l: int):
+        """o_proj + residual, norm, gate/up + SiLU*mul, down + residual, next norm -- in place on self.x / self.h.
+        Each linear names the head of the NEXT linear's weights: they are pulled into L2 during its own tail."""
+        L, buf, n = self.layers, self.layers[l], self.next_prefetch_bytes
+        gu_done = max(0, self.l2_prefetch_bytes - buf.wo.numel() * 2)        # what the hot-path window already pulled
+        nxt_w = L[l + 1].wqkv if l + 1 < len(L) else self.lm_head
+        nxt_n = L[l + 1].input_layernorm_weight if l + 1 < len(L) else self.norm_weight
+        dense.linear(self.attn.view(self.batch_size, -1), buf.wo, residual=self.x, out=self.x, static_weights=True,
+                     prefetch=(buf.gate_up_proj, gu_done, n) if n else None)
+        dense.rmsnorm(self.x, buf.post_attention_layernorm_weight, buf.post_attention_layernorm_variance_epsilon,
+                      out=self.h)
+        dense.linear_silu_mul(self.h, buf.gate_up_proj, out=self.act, static_weights=True,
+                              prefetch=(buf.down_proj, 0, n) if n else None)
+        dense.linear(self.act, buf.down_proj, residual=self.x, out=self.x, static_weights=True,
+                     prefetch=(nxt_w, 0, n) if n else None)
+        dense.rmsnorm(self.x, nxt_n, self.norm_variance_epsilon, out=self.h)
+
+    def _head_step(self):
+        n = self.next_prefetch_bytes
+        dense.linear_f32(self.h, self.lm_head, out=self.logits, static_weights=True,
+                         prefetch=(self.layers[0].wqkv, 0, n) if n else None)      # the next token starts there
+        dense.argmax(self.logits, out=self.tok)
+
     def _token_body(self):
         c, L = self.kv_cache, self.layers
-        Hq, H = self.num_heads, self.num_key_value_heads
         dense.embed_rmsnorm(self.tok, self.embed_tokens, L[0].input_layernorm_weight,
                             L[0].input_layernorm_variance_epsilon, self.x, self.h)
-        for l, buf in enumerate(L):
-            self.pre_attention_compute(None, buf, Hq, H, 128, position=c.prefill, pos_dev=c.gen_dev, normed=self.h,
-                                       out=(self.q, self.k, self.v))
-            c.decode_layer(l, self.q, self.k, self.v, self.cos_sin_cache, out=self.attn, device_counters=True)
-            dense.linear(self.attn.view(self.batch_size, -1), buf.wo, residual=self.x, out=self.x)
-            dense.rmsnorm(self.x, buf.post_attention_layernorm_weight, buf.post_attention_layernorm_variance_epsilon,
-                          out=self.h)
-            dense.linear_silu_mul(self.h, buf.gate_up_proj, out=self.act)
-            dense.linear(self.act, buf.down_proj, residual=self.x, out=self.x)
-            nxt = L[l + 1].input_layernorm_weight if l + 1 < len(L) else self.norm_weight
-            dense.rmsnorm(self.x, nxt, self.norm_variance_epsilon, out=self.h)
-        dense.linear_f32(self.h, self.lm_head, out=self.logits)
-        dense.argmax(self.logits, out=self.tok)
+        for l in range(len(L)):
+            self._pre_attention_step(l)
+            c.decode_layer(l, self.q, self.k, self.v, self.cos_sin_cache, out=self.attn, device_counters=True,
+                           after_select=self._after_select_hook(l))
+            self._post_attention_step(l)
+        self._head_step()
+        if self.l2_prefetch_bytes:
+            torch.cuda.current_stream().wait_stream(self.prefetch_stream)
         c.join_side_streams()
         c.advance_device_counters()
+
+    def _prefetch_post_attention_weights(self, buf: LlamaLayer):
+        """Runs on `prefetch_stream`, ordered behind the selection kernel of the layer: o_proj first, then as much of
+        the gate/up matrix as the budget allows.  A hint only: nothing waits for it except the end of the token."""
+        cur, pf = torch.cuda.current_stream(), self.prefetch_stream
+        pf.wait_stream(cur)
+        with torch.cuda.stream(pf):
+            left = self.l2_prefetch_bytes
+            for w in (buf.wo, buf.gate_up_proj):
+                n = min(left, w.numel() * 2)
+                if n > 0:
+                    dense.l2_prefetch(w, nbytes=n)
+                left -= n
+
+    def prepare(self):
+        """Before the first token of the runner: order it behind whatever built the weights / cache state on other
+        streams, and load the device-side counters from the host-side generation offset."""
+        torch.cuda.synchronize(self.device)
+        self.kv_cache.reset_device_counters()
+        self._prepared = True
 
     def capture(self, warmup: int = 1):
         """Warm up eagerly (real decode steps), then capture one token as a CUDA graph."""
         c = self.kv_cache
-        c.reset_device_counters()
+        self.prepare()
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 self._token_body()
@@ -194,6 +247,8 @@ class Llama:
         c = self.kv_cache
         if c.sparse_end + c.gen_offset + 1 > c.buf_len:
             raise RuntimeError(f"generation buffer full ({c.buf_len - c.sparse_end} tokens)")
+        if not self._prepared:
+            self.prepare()
         with torch.cuda.stream(self.stream):
             if self.graph is not None:
                 self.graph.replay()
@@ -203,6 +258,7 @@ class Llama:
 
     def generate(self, first_token: torch.Tensor, gen_len: int):
         """Greedy loop of base.py:626-640 (temperature 0): returns [B, gen_len] generated ids."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             self.tok.copy_(first_token.reshape(-1))
         out = []

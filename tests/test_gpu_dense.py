@@ -87,6 +87,8 @@ def test_linear_is_deterministic_and_leaves_the_counters_at_zero(cuda):
     a = dense.linear(x, W)
     for _ in range(5):
         assert torch.equal(dense.linear(x, W), a)
+    for _ in range(3):                                   # weights streamed ahead of the previous kernel's completion
+        assert torch.equal(dense.linear(x, W, static_weights=True), a)
     torch.cuda.synchronize()
     ws = dense.workspace(cuda)
     assert int(ws[:16384].view(torch.int32).abs().sum()) == 0
@@ -122,7 +124,8 @@ def test_linear_silu_mul(cuda, B, K, F):
     got = dense.linear_silu_mul(x.to(cuda), W.to(cuda))
     # gate and up each within 1 ulp -> silu(gate) within ~1.1 ulp (|d silu / silu| <= 1.1 |dg / g| for |g| <~ 4)
     # -> product within 3 ulp
-    assert_ulp_bf16(got, want, ulps=3, frac_exact=0.93, abs_floor=1e-4, what="silu_mul")
+    # typically; for negative gates |d ln silu / d ln g| = |1 + g (1 - sigmoid(g))| reaches ~2, hence the 6-ulp tail
+    assert_ulp_bf16(got, want, ulps=6, frac_exact=0.93, abs_floor=1e-4, what="silu_mul")
     # entries reach |16| here (1 bf16 ulp = 0.0625), so the absolute bar scales with the magnitude
     assert_close_bf16(got, want, max_abs=3 * 2.0 ** -8 * float(want.float().abs().max()), what="silu_mul")
 
@@ -190,46 +193,74 @@ def test_layer_methods_against_oracle(cuda, model):
     got = m.post_attention_compute(attn.to(cuda), x.to(cuda), lay)
     want = DO.post_attention(attn.reshape(B, -1), x, cpu(lay.wo), cpu(lay.post_attention_layernorm_weight), 1e-5,
                              cpu(lay.gate_up_proj), cpu(lay.down_proj))
-    assert_close_bf16(got, want, what="post_attention_compute")
+    # hidden states reach |8| here (1 bf16 ulp = 0.0625): the absolute bar scales with the magnitude
+    assert_close_bf16(got, want, max_abs=max(2e-2, 2.0 ** -6 * float(want.float().abs().max())),
+                      what="post_attention_compute")
     exact = float((got.cpu().view(torch.int16) == want.view(torch.int16)).float().mean())
-    assert exact > 0.85, exact
+    assert exact > 0.75, exact
 
 
-def test_whole_token_graph_matches_eager_and_generates(cuda):
-    """Two layers of the Llama-3.1-8B shape at a short context: the captured whole-token graph (device-side counters,
-    fused norms, in-place residual stream) produces the same logits as the eager reference-named call chain
-    (inference -> layer_compute), token after token."""
+def _build_model(layers, B, ctx, hbm_store_ways=0):
     from shadowkv_b200.llama import Llama
-    B, ctx = 2, 8192
     sh = synth.MODELS["llama-3.1-8b"]
+    m = Llama("llama-3.1-8b", batch_size=B, max_length=ctx, device="cuda:0", num_layers=layers, seed=7,
+              hbm_store_ways=hbm_store_ways)
+    states = [synth.layer_state(sh, B, ctx, seed=100 + l, device="cuda:0", cos_sin=m.cos_sin_cache) for l in range(layers)]
+    synth.install(m.kv_cache, states)
+    torch.cuda.synchronize()
+    return m
 
-    def build():
-        m = Llama("llama-3.1-8b", batch_size=B, max_length=ctx, device="cuda:0", num_layers=2, seed=7)
-        states = [synth.layer_state(sh, B, ctx, seed=100 + l, device="cuda:0", cos_sin=m.cos_sin_cache) for l in range(2)]
-        synth.install(m.kv_cache, states)
-        return m
 
-    first = torch.tensor([11, 4242], dtype=torch.int64, device=cuda)
-    a = build()
-    toks_eager, logits_eager = [], []
-    tok = first.clone()
+def test_token_runner_matches_the_reference_named_call_chain(cuda):
+    """One layer of the Llama-3.1-8B shape at a short context: the whole-token runner (device-side counters, norms
+    fused into the previous step, in-place residual stream) against the eager reference-named chain
+    inference -> layer_compute -> pre/post_attention_compute, token after token on the same token ids.  (One layer:
+    the two paths split the attention differently, and with more layers a last-bit difference can flip a chunk of the
+    next layer's top-S selection, which is a discontinuity, not an error.)"""
+    B, ctx = 2, 8192
+    a, b = _build_model(1, B, ctx), _build_model(1, B, ctx)
+    tok = torch.tensor([11, 4242], dtype=torch.int64, device=cuda)
     for t in range(3):
         pos = torch.full((B, 1), ctx + t, dtype=torch.int64, device=cuda)
-        lg = a.inference(tok.view(B, 1), pos)
-        logits_eager.append(lg[:, 0].clone())
-        tok = lg[:, 0].argmax(dim=-1)
-        toks_eager.append(tok.clone())
-    b = build()
+        want = a.inference(tok.view(B, 1), pos)[:, 0]
+        b.stream.wait_stream(torch.cuda.current_stream())        # tok was produced on the default stream
+        with torch.cuda.stream(b.stream):
+            b.tok.copy_(tok)
+        b.decode_token()
+        b.stream.synchronize()
+        assert_close_bf16(b.logits, want, max_abs=max(2e-2, 2.0 ** -6 * float(want.abs().max())), what=f"token {t} logits")
+        tok = want.argmax(dim=-1)
+    assert a.kv_cache.gen_offset == b.kv_cache.gen_offset == 3
+
+
+def test_whole_token_graph_replay_is_bit_identical_to_eager_launches(cuda):
+    """Two layers: the captured CUDA graph (programmatic dependent launches, side-stream fork/join inside) replays to
+    exactly the logits and tokens of the same kernels launched eagerly, and the greedy loop runs."""
+    B, ctx = 2, 8192
+    first = torch.tensor([11, 4242], dtype=torch.int64, device=cuda)
+    a = _build_model(2, B, ctx)
+    with torch.cuda.stream(a.stream):
+        a.tok.copy_(first)
+    want_logits, want_tok = [], []
+    for t in range(3):
+        a.decode_token()                         # no graph captured: eager launches
+        a.stream.synchronize()
+        want_logits.append(a.logits.clone())
+        want_tok.append(a.tok.clone())
+    b = _build_model(2, B, ctx)
     with torch.cuda.stream(b.stream):
         b.tok.copy_(first)
-    b.capture(warmup=1)                      # token 0 runs eagerly (device-side counters), then the graph is captured
+    b.capture(warmup=1)                          # token 0 eagerly, then the graph is captured
     for t in range(3):
         if t > 0:
             b.decode_token()
         b.stream.synchronize()
-        assert_close_bf16(b.logits, logits_eager[t], max_abs=2e-2, what=f"token {t} logits")
-        assert torch.equal(b.tok, toks_eager[t]), f"token {t}"
+        assert torch.equal(b.logits, want_logits[t]), f"token {t} logits"
+        assert torch.equal(b.tok, want_tok[t]), f"token {t}"
     assert b.kv_cache.gen_offset == 3
+    c = _build_model(2, B, ctx)
+    ids = c.generate(first, 3)
+    assert ids.shape == (B, 3) and torch.equal(ids[:, 2], want_tok[2])
 
 
 def test_epilogues_against_library_golden(cuda):

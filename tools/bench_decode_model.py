@@ -77,16 +77,18 @@ def op_table(m: Llama, B: int, stream, hbm_peak: float):
                       "library_us": us_l, "library_GBps": bytes_per_launch / us_l / 1e3, "weight_MB": bytes_per_launch / 1e6}
 
     nl = len(L)
+    npf = m.next_prefetch_bytes
+    nx = lambda i, name: (getattr(L[(i + 1) % nl], name), 0, npf) if npf else None    # noqa: E731
     add("qkv_rope", lambda: [m.pre_attention_compute(None, b, m.num_heads, m.num_key_value_heads, 128, position=1000,
                                                      normed=x, out=(m.q, m.k, m.v)) for b in L],
         lambda: [F.linear(x, b.wqkv) for b in L], L[0].wqkv.numel() * 2, nl)
-    add("o_proj_residual", lambda: [dense.linear(xa, b.wo, residual=res, out=res) for b in L],
+    add("o_proj_residual", lambda: [dense.linear(xa, b.wo, residual=res, out=res, static_weights=True, prefetch=nx(i, 'wo')) for i, b in enumerate(L)],
         lambda: [res.add_(F.linear(xa, b.wo)) for b in L], L[0].wo.numel() * 2, nl)
-    add("gate_up_silu_mul", lambda: [dense.linear_silu_mul(x, b.gate_up_proj, out=act) for b in L],
+    add("gate_up_silu_mul", lambda: [dense.linear_silu_mul(x, b.gate_up_proj, out=act, static_weights=True, prefetch=nx(i, 'gate_up_proj')) for i, b in enumerate(L)],
         lambda: [_lib_gate_up(x, b.gate_up_proj, ffn) for b in L], L[0].gate_up_proj.numel() * 2, nl)
-    add("down_residual", lambda: [dense.linear(xf, b.down_proj, residual=res, out=res) for b in L],
+    add("down_residual", lambda: [dense.linear(xf, b.down_proj, residual=res, out=res, static_weights=True, prefetch=nx(i, 'down_proj')) for i, b in enumerate(L)],
         lambda: [res.add_(F.linear(xf, b.down_proj)) for b in L], L[0].down_proj.numel() * 2, nl)
-    add("lm_head", lambda: dense.linear_f32(x, m.lm_head, out=m.logits), lambda: F.linear(x, m.lm_head).float(),
+    add("lm_head", lambda: dense.linear_f32(x, m.lm_head, out=m.logits, static_weights=True), lambda: F.linear(x, m.lm_head).float(),
         m.lm_head.numel() * 2, 1)
     us_norm = timed_graph(lambda: [dense.rmsnorm(x, b.input_layernorm_weight, 1e-5, out=m.h) for b in L], 5, stream) / nl
     rows["rmsnorm"] = {"us": us_norm}
@@ -96,6 +98,123 @@ def op_table(m: Llama, B: int, stream, hbm_peak: float):
 def _lib_gate_up(x, W, ffn):
     gu = F.linear(x, W)
     return F.silu(gu[:, :ffn]) * gu[:, ffn:]
+
+
+def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupled: bool = False,
+                modes=("hot", "native", "library"), ops: bool = True) -> dict:
+    """Time the token loop of `m` (cache state already installed) in the given modes; see the module docstring."""
+    dev, B = m.device, m.batch_size
+    shape = m.shape
+    L, Hq, H = m.num_layers, m.num_heads, m.num_key_value_heads
+    cache, cs = m.kv_cache, m.cos_sin_cache
+    hbm_peak = peaks()
+    stream = m.stream
+    torch.cuda.synchronize(dev)
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    total = warmup + steps
+    a = math.sqrt(1 - noise ** 2)
+    base = torch.randn(L, B, Hq, 1, 128, generator=g, device=dev)
+    qs = [(a * base + noise * torch.randn(L, B, Hq, 1, 128, generator=g, device=dev)).to(torch.bfloat16) for _ in range(total)]
+    kv = [torch.randn(L, B, H, 1, 128, generator=g, device=dev).to(torch.bfloat16) for _ in range(total)]
+    q_in, k_in = torch.zeros_like(qs[0]), torch.zeros_like(kv[0])
+    hid, ffn = m.hidden_size, shape.intermediate_size
+
+    def token(mode: str):
+        if mode == "native":
+            dense.embed_rmsnorm(m.tok, m.embed_tokens, m.layers[0].input_layernorm_weight, 1e-5, m.x, m.h)
+        elif mode == "library":
+            x = m.embed_tokens[m.tok]
+        for l, buf in enumerate(m.layers):
+            if mode == "native":
+                m._pre_attention_step(l)
+            elif mode == "library":
+                hh = F.rms_norm(x, (hid,), buf.input_layernorm_weight, 1e-5)
+                m.q.view(B, -1).copy_(F.linear(hh, buf.wqkv)[:, :Hq * 128])
+            hook = m._after_select_hook(l) if mode == "native" else None
+            if coupled and mode == "native":
+                cache.decode_layer(l, m.q, m.k, m.v, cs, out=m.attn, device_counters=True, after_select=hook)
+            else:
+                cache.decode_layer(l, q_in[l], k_in[l], k_in[l], cs, out=m.attn, device_counters=True, after_select=hook)
+            if mode == "native":
+                m._post_attention_step(l)
+            elif mode == "library":
+                x = x + F.linear(m.attn.view(B, -1), buf.wo)
+                h2 = F.rms_norm(x, (hid,), buf.post_attention_layernorm_weight, 1e-5)
+                x = x + F.linear(_lib_gate_up(h2, buf.gate_up_proj, ffn), buf.down_proj)
+        if mode == "native":
+            m._head_step()
+            if m.l2_prefetch_bytes:
+                torch.cuda.current_stream().wait_stream(m.prefetch_stream)
+        elif mode == "library":
+            logits = F.linear(F.rms_norm(x, (hid,), m.norm_weight, 1e-5), m.lm_head).float()
+            m.tok.copy_(logits.argmax(dim=-1))
+        cache.join_side_streams()
+        cache.advance_device_counters()
+
+    def run(mode: str):
+        cache.kv_offset -= cache.gen_offset
+        cache.gen_offset = 0
+        cache.reset_device_counters()
+        with torch.cuda.stream(stream):
+            q_in.copy_(qs[0]); k_in.copy_(kv[0]); token(mode)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            token(mode)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cap = cache.buf_len - cache.sparse_end - 2
+        with torch.cuda.stream(stream):
+            for t in range(total):
+                if t == warmup:
+                    e0.record()
+                if t % cap == cap - 1:
+                    cache._counters_dev.copy_(torch.tensor([0, cache.sparse_end + 1], dtype=torch.int32, device=dev))
+                q_in.copy_(qs[t]); k_in.copy_(kv[t]); graph.replay()
+            e1.record()
+        stream.synchronize()
+        hits = float(cache.cnts_all.float().mean()) / cache.select_sets
+        graph.reset()
+        return e0.elapsed_time(e1) / steps, hits
+
+    res = {mode: run(mode) for mode in modes}
+    wb = m.weight_bytes()
+    out = {
+        "what": f"{shape.name} decode, {m.max_length} ctx, batch {B}, {L} layers, whole layer stack + lm_head + greedy token, "
+                "one CUDA graph per token: 'native' = dense remainder (rmsnorm, QKV + RoPE, o_proj, gate/up + SiLU*mul, "
+                "down, lm_head, argmax) through this repo's kernels; 'library' = the same through torch / cuBLAS calls, as "
+                "the reference's model files do; the sparse-KV step is this repo's in both",
+        "batch": B, "layers": L, "coupled_qkv": bool(coupled), "hbm_store_ways": cache.hbm_store_ways,
+        "l2_prefetch_mb": m.l2_prefetch_bytes / 1e6, "next_prefetch_mb": m.next_prefetch_bytes / 1e6,
+        "dense_weight_GB": wb / 1e9, "hbm_peak_GBps": hbm_peak, "steps": steps, "warmup": warmup,
+        "dense_env": {k: os.environ.get(k) for k in ("SKV_DENSE_STAGES", "SKV_DENSE_CTAS_PER_SM", "SKV_DENSE_ORDER", "SKV_PDL")
+                      if os.environ.get(k)},
+    }
+    for mode, (ms, hit) in res.items():
+        out[f"{mode}_ms_per_token"] = ms
+        out[f"{mode}_tokens_per_s"] = B / ms * 1e3
+        out.setdefault("chunk_cache_hit_rate", {})[mode] = round(hit, 3)
+    if "hot" in res:
+        for mode in ("native", "library"):
+            if mode in res:
+                d = res[mode][0] - res["hot"][0]
+                out[f"{mode}_dense_ms"] = d
+                out[f"{mode}_dense_weight_stream_GBps"] = wb / (d * 1e-3) / 1e9
+                out[f"{mode}_dense_frac_hbm_peak"] = wb / (d * 1e-3) / 1e9 / hbm_peak
+    if ops:
+        out["ops"] = op_table(m, B, stream, hbm_peak)
+    return out
+
+
+def install_synthetic_state(m: Llama, ctx: int):
+    dev, cache, shape = m.device, m.kv_cache, m.shape
+    states = []
+    for l in range(m.num_layers):
+        st = synth.layer_state(shape, m.batch_size, ctx, seed=1000 + l, device=dev, cos_sin=None)
+        cache.v_cache_cpu[l][:, :, :st["v_chunks"].shape[2]].copy_(st["v_chunks"])
+        st["v_chunks"] = None
+        states.append(st)
+    synth.install(cache, states, skip_v_store=True)
 
 
 def main():
@@ -109,117 +228,16 @@ def main():
     ap.add_argument("--hbm-store-ways", type=int, default=0)
     ap.add_argument("--coupled", action="store_true", help="feed the QKV kernel's outputs to the sparse-KV step")
     ap.add_argument("--skip-ops", action="store_true")
+    ap.add_argument("--l2-prefetch-mb", type=float, default=96.0)
+    ap.add_argument("--next-prefetch-mb", type=float, default=32.0)
     ap.add_argument("--model", default="llama-3.1-8b")
     args = ap.parse_args()
-    dev = torch.device("cuda:0")
-    shape = synth.MODELS[args.model]
-    B = args.batch
-    m = Llama(args.model, batch_size=B, max_length=args.ctx, device="cuda:0", num_layers=args.layers or None,
-              hbm_store_ways=args.hbm_store_ways)
-    L, Hq, H = m.num_layers, m.num_heads, m.num_key_value_heads
-    cache, cs = m.kv_cache, m.cos_sin_cache
-    states = []
-    for l in range(L):
-        st = synth.layer_state(shape, B, args.ctx, seed=1000 + l, device=dev, cos_sin=None)
-        cache.v_cache_cpu[l][:, :, :st["v_chunks"].shape[2]].copy_(st["v_chunks"])
-        st["v_chunks"] = None
-        states.append(st)
-    synth.install(cache, states, skip_v_store=True)
-    del states
-    hbm_peak = peaks()
-    stream = m.stream
-
-    g = torch.Generator(device=dev).manual_seed(0)
-    total = args.warmup + args.steps
-    a = math.sqrt(1 - args.noise ** 2)
-    base = torch.randn(L, B, Hq, 1, 128, generator=g, device=dev)
-    qs = [(a * base + args.noise * torch.randn(L, B, Hq, 1, 128, generator=g, device=dev)).to(torch.bfloat16) for _ in range(total)]
-    kv = [torch.randn(L, B, H, 1, 128, generator=g, device=dev).to(torch.bfloat16) for _ in range(total)]
-    q_in, k_in = torch.zeros_like(qs[0]), torch.zeros_like(kv[0])
-    hid, ffn = m.hidden_size, shape.intermediate_size
-
-    def token(mode: str):
-        if mode == "native":
-            dense.embed_rmsnorm(m.tok, m.embed_tokens, m.layers[0].input_layernorm_weight, 1e-5, m.x, m.h)
-        elif mode == "library":
-            x = m.embed_tokens[m.tok]
-        for l, buf in enumerate(m.layers):
-            if mode == "native":
-                m.pre_attention_compute(None, buf, Hq, H, 128, position=cache.prefill, pos_dev=cache.gen_dev, normed=m.h,
-                                        out=(m.q, m.k, m.v))
-            elif mode == "library":
-                hh = F.rms_norm(x, (hid,), buf.input_layernorm_weight, 1e-5)
-                m.q.view(B, -1).copy_(F.linear(hh, buf.wqkv)[:, :Hq * 128])
-            if args.coupled and mode == "native":
-                cache.decode_layer(l, m.q, m.k, m.v, cs, out=m.attn, device_counters=True)
-            else:
-                cache.decode_layer(l, q_in[l], k_in[l], k_in[l], cs, out=m.attn, device_counters=True)
-            if mode == "native":
-                dense.linear(m.attn.view(B, -1), buf.wo, residual=m.x, out=m.x)
-                dense.rmsnorm(m.x, buf.post_attention_layernorm_weight, 1e-5, out=m.h)
-                dense.linear_silu_mul(m.h, buf.gate_up_proj, out=m.act)
-                dense.linear(m.act, buf.down_proj, residual=m.x, out=m.x)
-                nxt = m.layers[l + 1].input_layernorm_weight if l + 1 < L else m.norm_weight
-                dense.rmsnorm(m.x, nxt, 1e-5, out=m.h)
-            elif mode == "library":
-                x = x + F.linear(m.attn.view(B, -1), buf.wo)
-                h2 = F.rms_norm(x, (hid,), buf.post_attention_layernorm_weight, 1e-5)
-                x = x + F.linear(_lib_gate_up(h2, buf.gate_up_proj, ffn), buf.down_proj)
-        cache.join_side_streams()
-        cache.advance_device_counters()
-        if mode == "native":
-            dense.linear_f32(m.h, m.lm_head, out=m.logits)
-            dense.argmax(m.logits, out=m.tok)
-        elif mode == "library":
-            logits = F.linear(F.rms_norm(x, (hid,), m.norm_weight, 1e-5), m.lm_head).float()
-            m.tok.copy_(logits.argmax(dim=-1))
-
-    def run(mode: str):
-        cache.gen_offset = 0
-        cache.reset_device_counters()
-        with torch.cuda.stream(stream):
-            q_in.copy_(qs[0]); k_in.copy_(kv[0]); token(mode)
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            token(mode)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        cap = cache.buf_len - cache.sparse_end - 2
-        with torch.cuda.stream(stream):
-            for t in range(total):
-                if t == args.warmup:
-                    e0.record()
-                if t % cap == cap - 1:
-                    cache._counters_dev.copy_(torch.tensor([0, cache.sparse_end + 1], dtype=torch.int32, device=dev))
-                q_in.copy_(qs[t]); k_in.copy_(kv[t]); graph.replay()
-            e1.record()
-        stream.synchronize()
-        hits = float(cache.cnts_all.float().mean()) / cache.select_sets
-        return e0.elapsed_time(e1) / args.steps, hits
-
-    ms_hot, hit_hot = run("hot")
-    ms_nat, hit_nat = run("native")
-    ms_lib, _ = run("library")
-    wb = m.weight_bytes()
-    out = {
-        "what": f"{shape.name} decode, {args.ctx} ctx, batch {B}, {L} layers: sparse-KV hot path alone / + dense remainder "
-                "through this repo's kernels / + dense remainder through torch-cuBLAS library calls; one CUDA graph per token",
-        "batch": B, "layers": L, "coupled_qkv": bool(args.coupled), "hbm_store_ways": args.hbm_store_ways,
-        "hot_path_ms_per_token": ms_hot, "native_ms_per_token": ms_nat, "library_ms_per_token": ms_lib,
-        "hot_path_tokens_per_s": B / ms_hot * 1e3, "native_tokens_per_s": B / ms_nat * 1e3,
-        "library_tokens_per_s": B / ms_lib * 1e3,
-        "dense_weight_GB": wb / 1e9,
-        "native_dense_ms": ms_nat - ms_hot, "library_dense_ms": ms_lib - ms_hot,
-        "native_dense_weight_stream_GBps": wb / ((ms_nat - ms_hot) * 1e-3) / 1e9,
-        "library_dense_weight_stream_GBps": wb / ((ms_lib - ms_hot) * 1e-3) / 1e9,
-        "native_dense_frac_hbm_peak": wb / ((ms_nat - ms_hot) * 1e-3) / 1e9 / hbm_peak,
-        "hbm_peak_GBps": hbm_peak,
-        "chunk_cache_hit_rate": {"hot": round(hit_hot, 3), "native": round(hit_nat, 3)},
-        "dense_env": {k: os.environ.get(k) for k in ("SKV_DENSE_STAGES", "SKV_DENSE_CTAS_PER_SM", "SKV_PDL") if os.environ.get(k)},
-    }
-    if not args.skip_ops:
-        out["ops"] = op_table(m, B, stream, hbm_peak)
-    print(json.dumps(out))
+    m = Llama(args.model, batch_size=args.batch, max_length=args.ctx, device="cuda:0", num_layers=args.layers or None,
+              hbm_store_ways=args.hbm_store_ways, l2_prefetch_mb=args.l2_prefetch_mb,
+              next_prefetch_mb=args.next_prefetch_mb)
+    install_synthetic_state(m, args.ctx)
+    print(json.dumps(whole_model(m, steps=args.steps, warmup=args.warmup, noise=args.noise, coupled=args.coupled,
+                                 ops=not args.skip_ops)))
 
 
 if __name__ == "__main__":
