@@ -236,7 +236,7 @@ def workload_config(args, shape, L, *, hit_rate, n_gpus, heads_mode=False):
     lay = synth.layout(args.ctx, args.budget)
     return {"workload": f"{shape.name} random-init decode state, {args.ctx} ctx ('122K', test/e2e.py shape), "
                         f"batch {args.batch}/GPU, sparse budget {args.budget}, rank {args.rank}, chunk 8, {L} layers",
-            "scope": "sparse-KV decode step of every layer; dense QKV/o_proj/MLP not included (SURVEY.md 8 f2)",
+            "scope": "sparse-KV decode step of every layer; the dense QKV/o_proj/MLP of the layers is timed around it in `whole_model` (SURVEY.md 8 f2), not in value / e2e",
             "batch_per_gpu": args.batch, "global_batch": args.batch * (1 if heads_mode else n_gpus), "ctx": args.ctx,
             "layers": L,
             "landmarks": lay.n_landmarks, "select_chunks": lay.select, "kv_rows_attended": lay.sparse_end + 1,
@@ -431,7 +431,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
             model = Llama(full_shape, batch_size=B, max_length=args.ctx, device=f"cuda:{local_rank}", num_layers=L,
                           kv_cache=cache)
             whole = whole_model(model, steps=args.whole_model_steps, warmup=4, noise=args.noise,
-                                modes=("hot", "native", "library"), ops=True)
+                                modes=("hot", "native", "library"), ops=True, store_ways=args.hbm_store_ways)
             whole["note"] = ("context for the headline, not part of value / e2e: decode tokens/s of the whole model with "
                              "random-init weights; the sparse-KV step consumes the same synthetic q/k/v as the headline")
             del model

@@ -20,6 +20,6 @@ bool pdl_enabled() {
 }  // namespace skv
 
 extern "C" {
-const char *skv_version(void) { return "shadowkv_b200 0.1 (sm_100a; tcgen05 K rebuild, TMA bulk compaction)"; }
+const char *skv_version(void) { return "shadowkv_b200 0.2 (sm_100a; tcgen05 scoring / K rebuild / dense stream-K linears, TMA rings)"; }
 const char *skv_last_error(void) { return skv::g_err; }
 }

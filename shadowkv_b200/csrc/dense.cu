@@ -97,11 +97,16 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int 
     const int n = t * 128 + row;
     if (n < p.Nout) {
       const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+      // all residual loads first: out may alias resid (same element, same thread), so the compiler cannot hoist them
+      // over the stores by itself and the batch rows would pay one L2 round trip each
+      float rr[NPAD];
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b) rr[b] = (p.resid && b < p.B) ? __bfloat162float(p.resid[size_t(b) * p.Nout + n]) : 0.f;
 #pragma unroll
       for (int b = 0; b < NPAD; ++b)
         if (b < p.B) {
           float y = bfr(v[b] + bias);
-          if (p.resid) y = bfr(__bfloat162float(p.resid[size_t(b) * p.Nout + n]) + y);
+          if (p.resid) y = bfr(rr[b] + y);
           p.out[size_t(b) * p.Nout + n] = __float2bfloat16_rn(y);
         }
     }

@@ -101,7 +101,7 @@ def _lib_gate_up(x, W, ffn):
 
 
 def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupled: bool = False,
-                modes=("hot", "native", "library"), ops: bool = True) -> dict:
+                modes=("hot", "native", "library"), ops: bool = True, store_ways: int = 0) -> dict:
     """Time the token loop of `m` (cache state already installed) in the given modes; see the module docstring."""
     dev, B = m.device, m.batch_size
     shape = m.shape
@@ -152,7 +152,7 @@ def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupl
         cache.join_side_streams()
         cache.advance_device_counters()
 
-    def run(mode: str):
+    def run(mode: str, fill: int = 0):
         cache.kv_offset -= cache.gen_offset
         cache.gen_offset = 0
         cache.reset_device_counters()
@@ -165,6 +165,10 @@ def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupl
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cap = cache.buf_len - cache.sparse_end - 2
         with torch.cuda.stream(stream):
+            for t in range(fill):                       # tokens that warm the HBM chunk store before timing
+                if t % cap == cap - 1:
+                    cache._counters_dev.copy_(torch.tensor([0, cache.sparse_end + 1], dtype=torch.int32, device=dev))
+                q_in.copy_(qs[t % total]); k_in.copy_(kv[t % total]); graph.replay()
             for t in range(total):
                 if t == warmup:
                     e0.record()
@@ -203,6 +207,15 @@ def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupl
                 out[f"{mode}_dense_frac_hbm_peak"] = wb / (d * 1e-3) / 1e9 / hbm_peak
     if ops:
         out["ops"] = op_table(m, B, stream, hbm_peak)
+    if store_ways and not cache.hbm_store_ways:
+        # same token loop with the HBM chunk store between the sparse slots and the pinned host store (byte-identical
+        # results; most missed chunks stop crossing PCIe)
+        cache.enable_hbm_store(store_ways)
+        ms, hit = run("native", fill=32)
+        ms_hot_s, _ = run("hot", fill=8)
+        cache.enable_hbm_store(0)
+        out["hbm_chunk_store"] = {"ways": store_ways, "native_ms_per_token": ms, "native_tokens_per_s": B / ms * 1e3,
+                                  "hot_ms_per_token": ms_hot_s, "store_fill_tokens": 32}
     return out
 
 
@@ -231,13 +244,14 @@ def main():
     ap.add_argument("--l2-prefetch-mb", type=float, default=96.0)
     ap.add_argument("--next-prefetch-mb", type=float, default=32.0)
     ap.add_argument("--model", default="llama-3.1-8b")
+    ap.add_argument("--store-ways", type=int, default=0, help="also time the native loop with an HBM chunk store")
     args = ap.parse_args()
     m = Llama(args.model, batch_size=args.batch, max_length=args.ctx, device="cuda:0", num_layers=args.layers or None,
               hbm_store_ways=args.hbm_store_ways, l2_prefetch_mb=args.l2_prefetch_mb,
               next_prefetch_mb=args.next_prefetch_mb)
     install_synthetic_state(m, args.ctx)
     print(json.dumps(whole_model(m, steps=args.steps, warmup=args.warmup, noise=args.noise, coupled=args.coupled,
-                                 ops=not args.skip_ops)))
+                                 ops=not args.skip_ops, store_ways=args.store_ways)))
 
 
 if __name__ == "__main__":
