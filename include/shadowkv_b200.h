@@ -318,6 +318,12 @@ int skv_gather_chunks(const skv_bf16 *src, int64_t src_stride, skv_bf16 *dst, in
                               * [B,kv_heads,128] bf16 with the rotary embedding of vllm rotary_embedding applied to
                               * q and k at the token's position (llama.py:296, 377-385; glm.py:344, 421)         */
 
+#define SKV_DENSE_PARTIAL 4  /* out f32 [planes][B][out_features]: every CTA stores the partial sums of its slab range of a
+                              * tile as plane (CTA - first CTA of the tile); nothing is reduced inside the kernel.  The
+                              * consumer, skv_dense_finish_rmsnorm, adds the planes in the same order the other modes
+                              * use, so the result is bit-identical to SKV_DENSE_RESID + skv_rmsnorm, without the
+                              * cross-CTA fix-up (fence, arrival counter, re-read) at the end of the linear.           */
+
 typedef struct skv_dense_epilogue {
   int32_t mode;          /* SKV_DENSE_*                                                         */
   int32_t q_heads;       /* QKV_ROPE                                                            */
@@ -351,6 +357,15 @@ int64_t skv_dense_workspace_bytes(void);
  * (torch Linear layout), fp32 accumulation, epilogue per `epi`.  in_features % 64 == 0. */
 int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_features, int out_features,
                      const skv_dense_epilogue *epi, void *workspace, skv_stream_t stream);
+
+/* Bytes of the plane buffer SKV_DENSE_PARTIAL needs for this problem (depends on how the slabs split over the SMs). */
+int64_t skv_dense_partial_bytes(int batch, int in_features, int out_features);
+
+/* Consumer of SKV_DENSE_PARTIAL for the two places a linear feeds a residual add and a norm (o_proj, down_proj;
+ * llama.py:408-413, 424-426 + the next layer_norm):  y = bf16(sum of planes (+ bias));  x = bf16(x + y) in place;
+ * h = rmsnorm(x, w, eps).  `in_features` / `out_features` are those of the linear that wrote the planes. */
+int skv_dense_finish_rmsnorm(const float *planes, int batch, int in_features, int out_features, const skv_bf16 *bias,
+                             skv_bf16 *x_inout, const skv_bf16 *w, float eps, skv_bf16 *h_out, skv_stream_t stream);
 
 /* h[b,:] = bf16(x[b,:] * rsqrt(mean(x^2) + eps) * w) (flashinfer rmsnorm, tensor_op.py:34-39).  With tok != NULL the
  * row is first looked up, x[b,:] = emb[tok[b],:] (F.embedding, base.py:141), and written to x_out (the residual

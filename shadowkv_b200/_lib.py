@@ -79,11 +79,13 @@ _SIGS = {
     "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
     "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "skv_argmax": [_p, _p, _i, _i, _p],
+    "skv_dense_finish_rmsnorm": [_p, _i, _i, _i, _p, _p, _p, _f, _p, _p],
     "skv_l2_prefetch": [_p, _l, _p],
 }
 # every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
 EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",
-                                "skv_attention_workspace_bytes", "skv_dense_workspace_bytes"])
+                                "skv_attention_workspace_bytes", "skv_dense_workspace_bytes",
+                                "skv_dense_partial_bytes"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -97,6 +99,8 @@ lib.skv_attention_workspace_bytes.argtypes = [_i] * 5
 lib.skv_attention_workspace_bytes.restype = C.c_int64
 lib.skv_dense_workspace_bytes.argtypes = []
 lib.skv_dense_workspace_bytes.restype = C.c_int64
+lib.skv_dense_partial_bytes.argtypes = [_i, _i, _i]
+lib.skv_dense_partial_bytes.restype = C.c_int64
 
 
 def check(rc: int, what: str) -> None:

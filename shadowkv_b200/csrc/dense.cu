@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(kDnThreads, 1)
       __syncwarp();
       if (lane == 0) mbarrier_arrive(&acc_empty[acc]);
 
+      if (p.mode == SKV_DENSE_PARTIAL) {
+        // no reduction here: plane (this CTA - first CTA of the tile); the consumer adds the planes in CTA order
+        const int j = c - dn_cta_of(t * p.KS, p.total, nc);
+        const int n = t * 128 + row;
+        if (n < p.Nout) {
+#pragma unroll
+          for (int b = 0; b < NPAD; ++b)
+            if (b < p.B) p.out_f32[(size_t(j) * p.B + b) * p.Nout + n] = v[b];
+        }
+        continue;
+      }
       if (!(s0 == 0 && s1 == p.KS)) {
         // split tile: park the partial sums; the CTA that arrives last adds them up in CTA order
         const int slot = (t * p.KS < w0) ? 0 : 1;
@@ -448,6 +459,87 @@ __global__ void __launch_bounds__(kNormThreads)
   }
 }
 
+// ---- consumer of SKV_DENSE_PARTIAL: planes -> (+bias) -> bf16 -> + residual -> rmsnorm ------------------------------
+// One CTA per sequence; a thread owns 8 consecutive features (one tile, so one plane count).  The planes are added in
+// CTA order, exactly like the in-kernel fix-up of the other modes.
+__global__ void __launch_bounds__(kNormThreads)
+    finish_rmsnorm_kernel(const float *planes, int B, int Nout, int KS, int total, int nc, const __nv_bfloat16 *bias,
+                          __nv_bfloat16 *x, const __nv_bfloat16 *w, float eps, __nv_bfloat16 *h_out) {
+  __shared__ float s_part[kNormThreads / 32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = Nout >> 3;
+  float xv[2][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    if (j < nvec) {
+      const int n0 = j * 8, t = n0 >> 7;
+      const int cf = dn_cta_of(t * KS, total, nc), cl = dn_cta_of(t * KS + KS - 1, total, nc);
+      const int nseg = cl - cf + 1;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      const int4 rv = reinterpret_cast<const int4 *>(x + size_t(b) * Nout)[j];
+      for (int s0 = 0; s0 < nseg; s0 += 8) {
+        float4 tmp[8][2];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int sj = min(s0 + g, nseg - 1);
+          const float4 *src = reinterpret_cast<const float4 *>(planes + (size_t(sj) * B + b) * Nout + n0);
+          tmp[g][0] = __ldcg(src); tmp[g][1] = __ldcg(src + 1);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (s0 + g < nseg) {
+            acc[0] += tmp[g][0].x; acc[1] += tmp[g][0].y; acc[2] += tmp[g][0].z; acc[3] += tmp[g][0].w;
+            acc[4] += tmp[g][1].x; acc[5] += tmp[g][1].y; acc[6] += tmp[g][1].z; acc[7] += tmp[g][1].w;
+          }
+        }
+      }
+      const uint32_t *ur = reinterpret_cast<const uint32_t *>(&rv);
+      int4 bv = make_int4(0, 0, 0, 0);
+      if (bias) bv = reinterpret_cast<const int4 *>(bias)[j];
+      const uint32_t *ub = reinterpret_cast<const uint32_t *>(&bv);
+      int4 o;
+      uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float y0 = bfr(acc[2 * k] + bf16_lo(ub[k])), y1 = bfr(acc[2 * k + 1] + bf16_hi(ub[k]));
+        const float x0 = bfr(bf16_lo(ur[k]) + y0), x1 = bfr(bf16_hi(ur[k]) + y1);
+        xv[i][2 * k] = x0; xv[i][2 * k + 1] = x1;
+        ss += x0 * x0; ss += x1 * x1;
+        uo[k] = pack_bf16(__float2bfloat16_rn(x0), __float2bfloat16_rn(x1));
+      }
+      reinterpret_cast<int4 *>(x + size_t(b) * Nout)[j] = o;
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_part[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormThreads / 32; ++i) tot += s_part[i];
+  const float r = rsqrtf(tot / float(Nout) + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + i * kNormThreads;
+    if (j < nvec) {
+      const int4 wv = reinterpret_cast<const int4 *>(w)[j];
+      const uint32_t *uw = reinterpret_cast<const uint32_t *>(&wv);
+      int4 o;
+      uint32_t *uo = reinterpret_cast<uint32_t *>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        uo[k] = pack_bf16(__float2bfloat16_rn(xv[i][2 * k] * r * bf16_lo(uw[k])),
+                          __float2bfloat16_rn(xv[i][2 * k + 1] * r * bf16_hi(uw[k])));
+      reinterpret_cast<int4 *>(h_out + size_t(b) * Nout)[j] = o;
+    }
+  }
+}
+
 // ---- greedy token ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) argmax_kernel(const float *logits, int64_t *tok, int vocab) {
   __shared__ float s_v[32];
@@ -495,6 +587,21 @@ __global__ void __launch_bounds__(128) l2_prefetch_kernel(const unsigned char *b
 static int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
+}
+
+// How a plain [out, in] linear splits over the SMs: shared by the launcher and by the consumer of SKV_DENSE_PARTIAL.
+struct DenseSched { int T, KS, total, ctas, max_planes; };
+static DenseSched dense_sched(int in_features, int out_features, int T) {
+  DenseSched d{};
+  d.T = T; d.KS = in_features / 64; d.total = d.T * d.KS;
+  int ctas = kNumSMs * env_int("SKV_DENSE_CTAS_PER_SM", 1);
+  if (ctas > kDnMaxCtas) ctas = kDnMaxCtas;
+  if (ctas < 1) ctas = 1;
+  if (ctas > d.total) ctas = d.total;
+  d.ctas = ctas;
+  const int share = d.total / ctas;                       // shortest slab range of a CTA
+  d.max_planes = (d.KS + share - 1) / share + 1;          // CTAs that can touch one tile
+  return d;
 }
 
 template <int NPAD>
@@ -556,6 +663,7 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
   switch (epi->mode) {
     case SKV_DENSE_F32:
     case SKV_DENSE_RESID:
+    case SKV_DENSE_PARTIAL:
       p.T = (out_features + 127) / 128;
       break;
     case SKV_DENSE_SILU_MUL:
@@ -581,11 +689,9 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
       return SKV_ERR_ARGUMENT;
   }
   if (p.T > kDnMaxTiles) { set_error("dense_linear: more than %d row tiles", kDnMaxTiles); return SKV_ERR_UNSUPPORTED; }
-  p.total = p.T * p.KS;
-  int ctas = kNumSMs * env_int("SKV_DENSE_CTAS_PER_SM", 1);
-  if (ctas > kDnMaxCtas) ctas = kDnMaxCtas;
-  if (ctas < 1) ctas = 1;
-  if (ctas > p.total) ctas = p.total;
+  const DenseSched sched = dense_sched(in_features, out_features, p.T);
+  p.total = sched.total;
+  const int ctas = sched.ctas;
   const int npad = batch <= 16 ? 16 : 32;
   CUtensorMap mw, mx;
   int rc = make_tensor_map_2d(&mw, W, uint64_t(out_features), uint64_t(in_features), 64, 64);
@@ -593,6 +699,30 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
   rc = make_tensor_map_2d(&mx, x, uint64_t(batch), uint64_t(in_features), uint32_t(npad), 64);
   if (rc) return rc;
   return npad == 16 ? launch_dense<16>(mw, mx, p, ctas, as_stream(stream)) : launch_dense<32>(mw, mx, p, ctas, as_stream(stream));
+}
+
+int64_t skv_dense_partial_bytes(int batch, int in_features, int out_features) {
+  if (batch < 1 || in_features < 64 || in_features % 64 || out_features < 1) return 0;
+  const DenseSched d = dense_sched(in_features, out_features, (out_features + 127) / 128);
+  return int64_t(d.max_planes) * batch * out_features * 4;
+}
+
+int skv_dense_finish_rmsnorm(const float *planes, int batch, int in_features, int out_features, const skv_bf16 *bias,
+                             skv_bf16 *x_inout, const skv_bf16 *w, float eps, skv_bf16 *h_out, skv_stream_t stream) {
+  if (!planes || !x_inout || !w || !h_out) { set_error("dense_finish_rmsnorm: null pointer"); return SKV_ERR_ARGUMENT; }
+  if (batch < 1 || in_features < 64 || in_features % 64 || out_features < 8 || out_features % 8 ||
+      out_features > 2 * kNormThreads * 8) {
+    set_error("dense_finish_rmsnorm: in_features %d (multiple of 64), out_features %d (multiple of 8, <= %d)", in_features,
+              out_features, 2 * kNormThreads * 8);
+    return SKV_ERR_UNSUPPORTED;
+  }
+  const DenseSched d = dense_sched(in_features, out_features, (out_features + 127) / 128);
+  cudaError_t e = launch_kernel(finish_rmsnorm_kernel, dim3(batch), dim3(kNormThreads), 0, as_stream(stream), true, planes,
+                                batch, out_features, d.KS, d.total, d.ctas, reinterpret_cast<const __nv_bfloat16 *>(bias),
+                                reinterpret_cast<__nv_bfloat16 *>(x_inout), reinterpret_cast<const __nv_bfloat16 *>(w), eps,
+                                reinterpret_cast<__nv_bfloat16 *>(h_out));
+  if (e != cudaSuccess) { set_error("finish_rmsnorm_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("finish_rmsnorm_kernel");
 }
 
 int skv_rmsnorm(const skv_bf16 *x, const int64_t *tok, const skv_bf16 *emb, const skv_bf16 *w, float eps, skv_bf16 *x_out,

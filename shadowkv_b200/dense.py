@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import lib, check
 
-F32, RESID, SILU_MUL, QKV_ROPE = 0, 1, 2, 3
+F32, RESID, SILU_MUL, QKV_ROPE, PARTIAL = 0, 1, 2, 3, 4
 MAX_BATCH = 32
 
 _workspaces: dict = {}
@@ -89,6 +89,38 @@ def linear(x: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None = None, r
                              static_weights=int(static_weights))
     _launch(x, W, epi, "dense_linear", prefetch)
     return out
+
+
+_planes: dict = {}
+
+
+def linear_partial(x: torch.Tensor, W: torch.Tensor, static_weights: bool = False, prefetch=None) -> torch.Tensor:
+    """First half of ``residual + F.linear(x, W)`` followed by a ``layer_norm`` (o_proj / down_proj, reference
+    models/llama.py:408-413, 424-426): the partial sums of every CTA as fp32 planes, consumed by ``finish_rmsnorm``.
+    Same result as ``linear(..., residual=)`` + ``rmsnorm``, bit for bit, without the cross-CTA fix-up inside the
+    linear.  The plane buffer is cached per shape: consume it before the next ``linear_partial`` of that shape."""
+    _check_x(x, W)
+    key = (x.device, x.shape[0], x.shape[1], W.shape[0])
+    planes = _planes.get(key)
+    if planes is None:
+        n = lib.skv_dense_partial_bytes(x.shape[0], x.shape[1], W.shape[0])
+        planes = torch.zeros(n // 4, dtype=torch.float32, device=x.device)
+        _planes[key] = planes
+    _launch(x, W, _lib.DenseEpilogue(mode=PARTIAL, out=planes.data_ptr(), static_weights=int(static_weights)),
+            "dense_linear_partial", prefetch)
+    return planes
+
+
+def finish_rmsnorm(planes: torch.Tensor, in_features: int, x_inout: torch.Tensor, w: torch.Tensor, eps: float,
+                   h_out: torch.Tensor | None = None, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """Second half: x_inout <- bf16(x_inout + bf16(sum of planes (+ bias))), returns rmsnorm(x_inout, w, eps)."""
+    if x_inout.dim() != 2 or not x_inout.is_contiguous() or x_inout.dtype != torch.bfloat16:
+        raise ValueError("finish_rmsnorm takes a contiguous [batch, hidden] bfloat16 residual stream")
+    h_out = torch.empty_like(x_inout) if h_out is None else h_out
+    check(lib.skv_dense_finish_rmsnorm(planes.data_ptr(), x_inout.shape[0], in_features, x_inout.shape[1],
+                                       bias.data_ptr() if bias is not None else None, x_inout.data_ptr(), w.data_ptr(),
+                                       float(eps), h_out.data_ptr(), _cs()), "dense_finish_rmsnorm")
+    return h_out
 
 
 def linear_f32(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor | None = None,

@@ -54,10 +54,13 @@ class Llama:
     def __init__(self, model: str | synth.ModelShape = "llama-3.1-8b", batch_size: int = 1, max_length: int = 124928,
                  device: str = "cuda:0", sparse_budget: int = 2048, rank: int = 160, chunk_size: int = 8,
                  num_layers: int | None = None, seed: int = 0, kv_cache: ShadowKVCache_CPU | None = None,
-                 hbm_store_ways: int = 0, l2_prefetch_mb: float = 96.0, next_prefetch_mb: float = 32.0) -> None:
+                 hbm_store_ways: int = 0, l2_prefetch_mb: float = 96.0, next_prefetch_mb: float = 32.0,
+                 fused_finish: bool = True) -> None:
         """l2_prefetch_mb: bytes of the layer's o_proj / gate_up weights pulled into L2 (126 MB on B200) on a side
         stream while the sparse-KV step of the same layer waits on its PCIe fetch (0 disables).
-        next_prefetch_mb: head of the next linear's weights each dense kernel pulls into L2 during its own tail."""
+        next_prefetch_mb: head of the next linear's weights each dense kernel pulls into L2 during its own tail.
+        fused_finish: o_proj / down_proj leave partial planes and the following norm kernel finishes them
+        (dense.linear_partial + dense.finish_rmsnorm) instead of linear(residual=) + rmsnorm; same bits."""
         self.shape = synth.MODELS[model] if isinstance(model, str) else model
         self.device = torch.device(device)
         self.batch_size, self.max_length = batch_size, max_length
@@ -90,6 +93,7 @@ class Llama:
         self.graph = None
         self.l2_prefetch_bytes = int(l2_prefetch_mb * 1e6)
         self.next_prefetch_bytes = int(next_prefetch_mb * 1e6) & ~15
+        self.fused_finish = fused_finish
         self.prefetch_stream = torch.cuda.Stream(device=dev)
         self._prepared = False
         self.stream = torch.cuda.Stream(device=dev)
@@ -177,15 +181,27 @@ class Llama:
         gu_done = max(0, self.l2_prefetch_bytes - buf.wo.numel() * 2)        # what the hot-path window already pulled
         nxt_w = L[l + 1].wqkv if l + 1 < len(L) else self.lm_head
         nxt_n = L[l + 1].input_layernorm_weight if l + 1 < len(L) else self.norm_weight
-        dense.linear(self.attn.view(self.batch_size, -1), buf.wo, residual=self.x, out=self.x, static_weights=True,
-                     prefetch=(buf.gate_up_proj, gu_done, n) if n else None)
-        dense.rmsnorm(self.x, buf.post_attention_layernorm_weight, buf.post_attention_layernorm_variance_epsilon,
-                      out=self.h)
+        if self.fused_finish:
+            # the linear leaves fp32 partial planes; the norm kernel that follows anyway adds them, the residual and the
+            # norm in one pass (no cross-CTA fix-up at the end of the linear); bit-identical to the branch below
+            pl = dense.linear_partial(self.attn.view(self.batch_size, -1), buf.wo, static_weights=True,
+                                      prefetch=(buf.gate_up_proj, gu_done, n) if n else None)
+            dense.finish_rmsnorm(pl, buf.wo.shape[1], self.x, buf.post_attention_layernorm_weight,
+                                 buf.post_attention_layernorm_variance_epsilon, h_out=self.h)
+        else:
+            dense.linear(self.attn.view(self.batch_size, -1), buf.wo, residual=self.x, out=self.x, static_weights=True,
+                         prefetch=(buf.gate_up_proj, gu_done, n) if n else None)
+            dense.rmsnorm(self.x, buf.post_attention_layernorm_weight, buf.post_attention_layernorm_variance_epsilon,
+                          out=self.h)
         dense.linear_silu_mul(self.h, buf.gate_up_proj, out=self.act, static_weights=True,
                               prefetch=(buf.down_proj, 0, n) if n else None)
-        dense.linear(self.act, buf.down_proj, residual=self.x, out=self.x, static_weights=True,
-                     prefetch=(nxt_w, 0, n) if n else None)
-        dense.rmsnorm(self.x, nxt_n, self.norm_variance_epsilon, out=self.h)
+        if self.fused_finish:
+            pl = dense.linear_partial(self.act, buf.down_proj, static_weights=True, prefetch=(nxt_w, 0, n) if n else None)
+            dense.finish_rmsnorm(pl, buf.down_proj.shape[1], self.x, nxt_n, self.norm_variance_epsilon, h_out=self.h)
+        else:
+            dense.linear(self.act, buf.down_proj, residual=self.x, out=self.x, static_weights=True,
+                         prefetch=(nxt_w, 0, n) if n else None)
+            dense.rmsnorm(self.x, nxt_n, self.norm_variance_epsilon, out=self.h)
 
     def _head_step(self):
         n = self.next_prefetch_bytes

@@ -80,6 +80,30 @@ def test_linear_residual(cuda, B, K, N, bias, resid):
         assert torch.equal(rr, got)
 
 
+@pytest.mark.parametrize("B,K,N,bias", [(1, 4096, 4096, False), (5, 14336, 4096, False), (17, 1024, 200, True),
+                                        (32, 4096, 4096, True), (2, 64, 128, False), (3, 4096, 8192, False)])
+def test_partial_planes_plus_finish_equal_the_unfused_path_bit_for_bit(cuda, B, K, N, bias):
+    """linear_partial + finish_rmsnorm (no cross-CTA fix-up inside the linear; the norm kernel adds the planes) against
+    linear(residual=) + rmsnorm: same summation order, so the same bits -- and both against the oracle."""
+    from shadowkv_b200 import dense
+    g = torch.Generator().manual_seed(B + K + N)
+    x, W = _rn(g, B, K), _rn(g, N, K, scale=0.02)
+    b = _rn(g, N, scale=0.5) if bias else None
+    r, w = _rn(g, B, N), (1.0 + 0.1 * torch.randn(N, generator=g)).to(BF16)
+    xd, Wd, bd, wd = x.to(cuda), W.to(cuda), (b.to(cuda) if bias else None), w.to(cuda)
+    x1 = dense.linear(xd, Wd, bias=bd, residual=r.to(cuda))
+    h1 = dense.rmsnorm(x1, wd, 1e-5)
+    x2 = r.to(cuda).clone()
+    planes = dense.linear_partial(xd, Wd, static_weights=True)
+    h2 = dense.finish_rmsnorm(planes, K, x2, wd, 1e-5, bias=bd)
+    assert torch.equal(x1, x2) and torch.equal(h1, h2)
+    y = DO.linear(x, W, b)
+    want_x = DO.add_bf16(r, y)
+    _assert_prop(x2, want_x, y, what="fused residual")
+    # the norm of a 1-ulp-different x: compare on the kernel's own x (the stage itself), then loosely end to end
+    assert_ulp_bf16(h2, DO.rmsnorm(x2.cpu(), w, 1e-5), ulps=1, frac_exact=0.99, what="fused rmsnorm")
+
+
 def test_linear_is_deterministic_and_leaves_the_counters_at_zero(cuda):
     from shadowkv_b200 import dense
     g = torch.Generator().manual_seed(1)

@@ -1,0 +1,18 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_dense.py -q -m gpu --no-header -p no:cacheprovider > gpurun_out/test_gpu_dense.log 2>&1; echo "dense rc=$?"; tail -4 gpurun_out/test_gpu_dense.log
+timeout 400 python tools/bench_decode_model.py --steps 32 2>gpurun_out/dm.err > gpurun_out/decode_model.json; tail -2 gpurun_out/dm.err
+python -c "
+import json
+d=json.load(open('gpurun_out/decode_model.json'))
+print('native %.3f ms lib %.3f ms hot %.3f' % (d['native_ms_per_token'], d['library_ms_per_token'], d['hot_ms_per_token']))
+for k,v in d['ops'].items(): print(k, {a:round(x,1) for a,x in v.items()})"
+for m in glm-4-9b-1m yi-9b-200k; do
+  echo "== $m (4 layers, batch 4)"
+  timeout 400 python tools/bench_decode_model.py --steps 16 --layers 4 --batch 4 --model $m --ctx 131072 2>gpurun_out/dm_$m.err > gpurun_out/decode_model_$m.json; tail -2 gpurun_out/dm_$m.err
+  python -c "
+import json
+d=json.load(open('gpurun_out/decode_model_$m.json'))
+print('native %.3f ms lib %.3f ms hot %.3f' % (d['native_ms_per_token'], d['library_ms_per_token'], d['hot_ms_per_token']))
+for k,v in d['ops'].items(): print(k, {a:round(x,1) for a,x in v.items()})"
+done

@@ -90,6 +90,18 @@ def op_table(m: Llama, B: int, stream, hbm_peak: float):
         lambda: [res.add_(F.linear(xf, b.down_proj)) for b in L], L[0].down_proj.numel() * 2, nl)
     add("lm_head", lambda: dense.linear_f32(x, m.lm_head, out=m.logits, static_weights=True), lambda: F.linear(x, m.lm_head).float(),
         m.lm_head.numel() * 2, 1)
+    # o_proj / down followed by the norm: partial planes + fused finish against linear(residual=) + rmsnorm
+    hn = torch.zeros(B, hid, dtype=torch.bfloat16, device=dev)
+    for name, xin, attr in (("o_proj", xa, "wo"), ("down", xf, "down_proj")):
+        fused = timed_graph(lambda: [dense.finish_rmsnorm(dense.linear_partial(xin, getattr(b, attr), static_weights=True,
+                                                                                prefetch=nx(i, attr)),
+                                                          getattr(b, attr).shape[1], res, b.input_layernorm_weight, 1e-5, h_out=hn)
+                                     for i, b in enumerate(L)], 5, stream) / nl
+        unfused = timed_graph(lambda: [(dense.linear(xin, getattr(b, attr), residual=res, out=res, static_weights=True,
+                                                     prefetch=nx(i, attr)),
+                                        dense.rmsnorm(res, b.input_layernorm_weight, 1e-5, out=hn)) for i, b in enumerate(L)],
+                              5, stream) / nl
+        rows[f"{name}+norm"] = {"fused_us": fused, "unfused_us": unfused}
     us_norm = timed_graph(lambda: [dense.rmsnorm(x, b.input_layernorm_weight, 1e-5, out=m.h) for b in L], 5, stream) / nl
     rows["rmsnorm"] = {"us": us_norm}
     return rows
