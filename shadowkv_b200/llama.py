@@ -94,6 +94,7 @@ class Llama:
         self.l2_prefetch_bytes = int(l2_prefetch_mb * 1e6)
         self.next_prefetch_bytes = int(next_prefetch_mb * 1e6) & ~15
         self.fused_finish = fused_finish
+        self.greedy = True                      # the token body ends in the argmax kernel (temperature 0)
         self.prefetch_stream = torch.cuda.Stream(device=dev)
         self._prepared = False
         self.stream = torch.cuda.Stream(device=dev)
@@ -207,7 +208,8 @@ class Llama:
         n = self.next_prefetch_bytes
         dense.linear_f32(self.h, self.lm_head, out=self.logits, static_weights=True,
                          prefetch=(self.layers[0].wqkv, 0, n) if n else None)      # the next token starts there
-        dense.argmax(self.logits, out=self.tok)
+        if self.greedy:
+            dense.argmax(self.logits, out=self.tok)
 
     def _token_body(self):
         c, L = self.kv_cache, self.layers
@@ -244,15 +246,22 @@ class Llama:
         self.kv_cache.reset_device_counters()
         self._prepared = True
 
-    def capture(self, warmup: int = 1):
-        """Warm up eagerly (real decode steps), then capture one token as a CUDA graph."""
+    def capture(self, warmup: int = 1, rewind: bool = False):
+        """Warm up eagerly (real decode steps: they allocate scratch, encode tensor maps, set kernel attributes), then
+        capture one token as a CUDA graph.  rewind=True puts the generation offset back afterwards, so the warm-up
+        tokens leave only cache-state effects behind (which chunks sit in the sparse slots), never results."""
         c = self.kv_cache
         self.prepare()
+        g0 = c.gen_offset
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 self._token_body()
                 c.note_replayed_steps(1)
         self.stream.synchronize()
+        if rewind and c.gen_offset != g0:
+            c.kv_offset -= c.gen_offset - g0
+            c.gen_offset = g0
+            c.reset_device_counters()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             self._token_body()
@@ -271,6 +280,36 @@ class Llama:
             else:
                 self._token_body()
         c.note_replayed_steps(1)
+
+    def batch_generate(self, next_token: torch.Tensor, gen_len: int = 256, temperature: float = 0.0, top_p: float = -1,
+                       top_k: int = 50, benchmark: bool = False):
+        """Decode loop of reference ``LLM.batch_generate`` (base.py:626-655) from the first sampled token on (the cache
+        already holds the prompt: prefill is outside this path).  Returns [B, gen_len] ids, and tokens/s when
+        ``benchmark``.  Temperature 0 keeps the argmax inside the captured graph; otherwise the graph ends at the
+        logits and ``tensor_op.sample_token`` (the reference's operator sequence) draws the token."""
+        import time
+        from .tensor_op import sample_token
+        greedy = temperature == 0.0
+        if self.graph is None or greedy != self.greedy:
+            self.greedy = greedy
+            self.capture(warmup=1, rewind=True)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.tok.copy_(next_token.reshape(-1))
+        out = []
+        self.stream.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(gen_len):
+            self.decode_token()
+            with torch.cuda.stream(self.stream):
+                if not greedy:
+                    self.tok.copy_(sample_token(self.logits.clone(), temperature=temperature, top_p=top_p, top_k=top_k)[:, 0])
+                out.append(self.tok.clone())
+        self.stream.synchronize()
+        ids = torch.stack(out, dim=1)
+        if benchmark:
+            return ids, self.batch_size * gen_len / (time.perf_counter() - t0)
+        return ids
 
     def generate(self, first_token: torch.Tensor, gen_len: int):
         """Greedy loop of base.py:626-640 (temperature 0): returns [B, gen_len] generated ids."""

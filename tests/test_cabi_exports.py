@@ -74,3 +74,31 @@ def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
     vs = _lib.VStore(tags=1, data=1, pcie_count=0, ways=100)
     assert lib.skv_fetch_misses(C.byref(g), 1, 0, 1, 1, 1, 1, C.byref(vs), 0) == -2  # ways not a power of two
     assert lib.skv_select_workspace_bytes(C.byref(g)) > 8 * 4 * 15560 * 2
+
+
+def test_dense_entry_points_reject_bad_arguments_without_a_gpu():
+    """Part 4 of the header (dense remainder of the decode layer): argument checks run before any launch."""
+    import ctypes as C
+    from shadowkv_b200 import _lib
+    lib = _lib.lib
+    epi = _lib.DenseEpilogue(mode=1, out=8)
+    one = 16                                               # any non-null "pointer": nothing is dereferenced
+    assert lib.skv_dense_linear(0, one, 1, 4096, 4096, C.byref(epi), one, 0) == -2          # null x
+    assert lib.skv_dense_linear(one, one, 33, 4096, 4096, C.byref(epi), one, 0) == -1       # batch > 32
+    assert lib.skv_dense_linear(one, one, 1, 100, 4096, C.byref(epi), one, 0) == -1         # in_features % 64
+    assert b"in_features" in lib.skv_last_error()
+    bad = _lib.DenseEpilogue(mode=9, out=8)
+    assert lib.skv_dense_linear(one, one, 1, 4096, 4096, C.byref(bad), one, 0) == -2        # unknown epilogue
+    qkv = _lib.DenseEpilogue(mode=3, out=8, q_heads=32, kv_heads=8, k_out=8, v_out=8)
+    assert lib.skv_dense_linear(one, one, 1, 4096, 4096, C.byref(qkv), one, 0) == -2        # out_features != 48 heads
+    silu = _lib.DenseEpilogue(mode=2, out=8)
+    assert lib.skv_dense_linear(one, one, 1, 4096, 200, C.byref(silu), one, 0) == -1        # 2F with F % 64 != 0
+    assert lib.skv_rmsnorm(0, 0, 0, one, 1e-5, 0, one, 1, 4096, 0) == -2                    # neither x nor tok
+    assert lib.skv_rmsnorm(one, 0, 0, one, 1e-5, 0, one, 1, 4100, 0) == -1                  # hidden % 8
+    assert lib.skv_argmax(0, one, 1, 10, 0) == -2
+    assert lib.skv_l2_prefetch(one + 1, 4096, 0) == -2                                      # not 16-byte aligned
+    assert lib.skv_dense_finish_rmsnorm(one, 1, 4096, 4100, 0, one, one, 1e-5, one, 0) == -1
+    assert lib.skv_dense_workspace_bytes() > 4096 * 4
+    # plane buffer: 4096 x 4096 splits into 32 tiles x 64 slabs over 148 CTAs -> at most 6 CTAs touch a tile
+    assert lib.skv_dense_partial_bytes(1, 4096, 4096) == 6 * 4096 * 4
+    assert lib.skv_dense_partial_bytes(2, 64, 128) == 2 * 2 * 128 * 4

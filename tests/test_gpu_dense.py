@@ -285,6 +285,17 @@ def test_whole_token_graph_replay_is_bit_identical_to_eager_launches(cuda):
     c = _build_model(2, B, ctx)
     ids = c.generate(first, 3)
     assert ids.shape == (B, 3) and torch.equal(ids[:, 2], want_tok[2])
+    # the reference's batch_generate loop (base.py:626-655): greedy = the same tokens; with a temperature the graph
+    # ends at the logits and sample_token draws from the top-k set
+    d = _build_model(2, B, ctx)
+    ids_g, tps = d.batch_generate(first, gen_len=3, temperature=0.0, benchmark=True)
+    assert torch.equal(ids_g, torch.stack(want_tok, dim=1)) and tps > 0
+    e = _build_model(2, B, ctx)
+    torch.manual_seed(0)
+    ids_s = e.batch_generate(first, gen_len=2, temperature=0.8, top_k=5, top_p=-1)
+    assert ids_s.shape == (B, 2)
+    kth = want_logits[0].topk(5, dim=-1).values[:, -1]
+    assert bool((want_logits[0].gather(1, ids_s[:, :1]).squeeze(1) >= kth).all()), "sampled token outside the top-k set"
 
 
 def test_epilogues_against_library_golden(cuda):

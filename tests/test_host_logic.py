@@ -35,3 +35,24 @@ def test_model_shapes():
     assert cfg.num_attention_heads // cfg.num_key_value_heads == 4
     assert cfg.hidden_size // cfg.num_attention_heads == 128
     assert synth.MODELS["glm-4-9b-1m"].glm_rope
+
+
+def test_sampling_mirrors_follow_the_reference_semantics():
+    """tensor_op.top_k_top_p_filter / norm_logits / sample_token (reference models/tensor_op.py:242-297) on CPU."""
+    import torch
+    from shadowkv_b200 import tensor_op as T
+    logits = torch.tensor([[1.0, 3.0, 2.0, 0.5, -1.0], [0.0, 0.0, 5.0, 4.0, 4.5]])
+    f = T.top_k_top_p_filter(logits.clone(), top_k=2)
+    assert torch.isinf(f[0, [0, 3, 4]]).all() and torch.isfinite(f[0, [1, 2]]).all()
+    assert torch.isinf(f[1, [0, 1, 3]]).all() and torch.isfinite(f[1, [2, 4]]).all()
+    # nucleus: the token that crosses top_p is kept (shifted mask), everything after it is dropped
+    p = T.top_k_top_p_filter(torch.tensor([[2.0, 1.0, 0.0, -1.0]]), top_p=0.7)
+    probs = torch.softmax(torch.tensor([2.0, 1.0, 0.0, -1.0]), -1)
+    assert probs[0] < 0.7 < probs[0] + probs[1]
+    assert torch.isfinite(p[0, :2]).all() and torch.isinf(p[0, 2:]).all()
+    pr = T.norm_logits(logits.clone(), temperature=0.5, top_k=3, top_p=-1)
+    assert torch.allclose(pr.sum(-1), torch.ones(2)) and (pr[0, [3, 4]] == 0).all()
+    assert T.sample_token(logits, temperature=0).tolist() == [[1], [2]]
+    g = torch.manual_seed(0)
+    tok = T.sample_token(logits.clone(), temperature=0.7, top_k=2, top_p=-1)
+    assert tok.shape == (2, 1) and int(tok[0]) in (1, 2) and int(tok[1]) in (2, 4)
