@@ -27,11 +27,15 @@ def _cs() -> int:
 
 
 def workspace(device) -> torch.Tensor:
-    """Scratch of skv_dense_linear (zero-filled once; the kernel keeps its counters at zero), one per device."""
-    key = torch.device(device)
+    """Scratch of skv_dense_linear (zero-filled once; the kernel keeps its counters at zero): one per (device, stream),
+    because launches of one stream run in order and may share it, launches of different streams may not."""
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None:
-        ws = torch.zeros(lib.skv_dense_workspace_bytes(), dtype=torch.uint8, device=key)
+        ws = torch.zeros(lib.skv_dense_workspace_bytes(), dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
     return ws
 
@@ -100,7 +104,7 @@ def linear_partial(x: torch.Tensor, W: torch.Tensor, static_weights: bool = Fals
     Same result as ``linear(..., residual=)`` + ``rmsnorm``, bit for bit, without the cross-CTA fix-up inside the
     linear.  The plane buffer is cached per shape: consume it before the next ``linear_partial`` of that shape."""
     _check_x(x, W)
-    key = (x.device, x.shape[0], x.shape[1], W.shape[0])
+    key = (x.device, torch.cuda.current_stream(x.device).cuda_stream, x.shape[0], x.shape[1], W.shape[0])
     planes = _planes.get(key)
     if planes is None:
         n = lib.skv_dense_partial_bytes(x.shape[0], x.shape[1], W.shape[0])

@@ -116,6 +116,10 @@ def test_linear_is_deterministic_and_leaves_the_counters_at_zero(cuda):
     torch.cuda.synchronize()
     ws = dense.workspace(cuda)
     assert int(ws[:16384].view(torch.int32).abs().sum()) == 0
+    # another stream gets its own scratch
+    with torch.cuda.stream(torch.cuda.Stream()):
+        assert dense.workspace(cuda).data_ptr() != ws.data_ptr()
+        assert torch.equal(dense.linear(x, W), a)
 
 
 @pytest.mark.parametrize("B,vocab", [(1, 128256), (4, 64000)])

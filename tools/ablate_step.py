@@ -55,17 +55,24 @@ def main():
             else:
                 pid = c.get_retrieval_position_ids(l, q_in[l], append=ap)
             cur, side = torch.cuda.current_stream(), c.copy_stream
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
+            if "nofork" in skip:                 # everything on one stream: what the side-stream fork / join costs
                 if "rebuild" not in skip:
                     c.get_key_cache(l, pid, None, cs)
-                c._k_done.record(side)
-            if "fetch" not in skip:
-                c.get_value_cache(l, pid)
-            cur.wait_event(c._k_done)
+                if "fetch" not in skip:
+                    c.get_value_cache(l, pid)
+            else:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    if "rebuild" not in skip:
+                        c.get_key_cache(l, pid, None, cs)
+                    c._k_done.record(side)
+                if "fetch" not in skip:
+                    c.get_value_cache(l, pid)
+                cur.wait_event(c._k_done)
             if "attention" not in skip:
                 c.attention(l, q_in[l], None, out[l], True)
-        c.join_side_streams()
+        if "nofork" not in skip:
+            c.join_side_streams()
 
     def run(skip):
         cache.reset_device_counters()
@@ -89,7 +96,7 @@ def main():
 
     full = run(set())
     print(f"full step              {full:7.2f} us/layer   (hits {float(cache.cnts_all.float().mean()):.0f}/256)")
-    for skip in (["attention"], ["fetch"], ["rebuild"], ["fetch", "rebuild"], ["fetch", "rebuild", "attention"],
+    for skip in (["nofork"], ["rebuild", "nofork"], ["attention"], ["fetch"], ["rebuild"], ["fetch", "rebuild"], ["fetch", "rebuild", "attention"],
                  ["select", "fetch", "rebuild", "attention"], ["score", "select", "rebuild", "attention"],
                  ["score", "select", "fetch", "rebuild"]):
         t = run(set(skip))
