@@ -35,7 +35,7 @@ constexpr int64_t kDnPartBytes = int64_t(kDnMaxCtas) * 2 * kDnMaxBatch * 128 * 4
 
 struct DenseParams {
   int B, K, KS, Nout, T, mode, stages, total;
-  float *part;            // [ctas][2][128 rows][NPAD] fp32 partial tiles
+  float *part;            // [ctas][2][NPAD][128 rows] fp32 partial tiles
   int *tile_cnt;          // [T] arrivals per split tile; zero between launches
   const __nv_bfloat16 *resid, *bias, *cos_sin;
   __nv_bfloat16 *out, *k_out, *v_out;
@@ -350,11 +350,12 @@ __global__ void __launch_bounds__(kDnThreads, 1)
       if (!(s0 == 0 && s1 == p.KS)) {
         // split tile: park the partial sums; the CTA that arrives last adds them up in CTA order
         const int slot = (t * p.KS < w0) ? 0 : 1;
-        constexpr int kPartFloats = 128 * NPAD;        // one partial tile: [row][NPAD] fp32, a thread's row contiguous
-        float4 *mine = reinterpret_cast<float4 *>(p.part + (size_t(c) * 2 + slot) * kPartFloats + row * NPAD);
+        constexpr int kPartFloats = 128 * NPAD;        // one partial tile: [batch column][row] fp32 -- a warp's 32 rows
+                                                       // of one column are one 128-byte line (coalesced both ways)
+        float *mine = p.part + (size_t(c) * 2 + slot) * kPartFloats + row;
 #pragma unroll
-        for (int j = 0; j < NPAD / 4; ++j)
-          if (4 * j < p.B) __stcg(mine + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        for (int b = 0; b < NPAD; ++b)
+          if (b < p.B) __stcg(mine + b * 128, v[b]);
         __threadfence();
         if (leader && final_seg) SKV_STAMP_NS(trow, 7);
         epi_bar();
@@ -376,24 +377,22 @@ __global__ void __launch_bounds__(kDnThreads, 1)
         // sum in CTA order (deterministic); the loads of kGroup contributors are in flight together
         constexpr int kGroup = NPAD == 16 ? 8 : 4;
         for (int c0 = cf; c0 <= cl; c0 += kGroup) {
-          float4 tmp[kGroup][NPAD / 4];
+          float tmp[kGroup][NPAD];
 #pragma unroll
           for (int g = 0; g < kGroup; ++g) {
             const int cc = min(c0 + g, cl);
             const int sl = (t * p.KS < dn_begin(cc, p.total, nc)) ? 0 : 1;
-            const float4 *src = reinterpret_cast<const float4 *>(p.part + (size_t(cc) * 2 + sl) * kPartFloats + row * NPAD);
+            const float *src = p.part + (size_t(cc) * 2 + sl) * kPartFloats + row;
 #pragma unroll
-            for (int j = 0; j < NPAD / 4; ++j)
-              if (4 * j < p.B) tmp[g][j] = __ldcg(src + j);
+            for (int b = 0; b < NPAD; ++b)
+              if (b < p.B) tmp[g][b] = __ldcg(src + b * 128);
           }
 #pragma unroll
           for (int g = 0; g < kGroup; ++g) {
             if (c0 + g <= cl) {
 #pragma unroll
-              for (int j = 0; j < NPAD / 4; ++j) {
-                if (4 * j >= p.B) continue;
-                v[4 * j] += tmp[g][j].x; v[4 * j + 1] += tmp[g][j].y; v[4 * j + 2] += tmp[g][j].z; v[4 * j + 3] += tmp[g][j].w;
-              }
+              for (int b = 0; b < NPAD; ++b)
+                if (b < p.B) v[b] += tmp[g][b];
             }
           }
         }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel tuning aid: wall-clock (%globaltimer) phase timeline of dense_streamk_kernel over a chain of back-to-back
 launches (the o_proj / QKV / gate-up / down shapes over distinct weights, captured in a CUDA graph).  Needs the trace
-build:  make trace && python tools/trace_dense.py [o|qkv|gu|down]   Not part of the product path or of bench.py."""
+build:  make trace && python tools/trace_dense.py [o|qkv|gu|down] [batch]   Not part of the product path or of bench.py."""
 import ctypes as C
 import os
 import sys
@@ -18,14 +18,15 @@ LABELS = ["start", "prefill", "pdl_wait", "setup", "mma0", "mma_end", "acc_last"
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "o"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     shapes = {"o": (4096, 4096), "qkv": (6144, 4096), "gu": (28672, 4096), "down": (4096, 14336)}
     N, K = shapes[which]
     dev = torch.device("cuda:0")
     n = 12
     g = torch.Generator(device=dev).manual_seed(0)
     Ws = [(torch.randn(N, K, generator=g, device=dev) * 0.02).to(torch.bfloat16) for _ in range(n)]
-    x = torch.randn(1, K, generator=g, device=dev).to(torch.bfloat16)
-    out = torch.zeros(1, N // 2 if which == "gu" else N, dtype=torch.bfloat16, device=dev)
+    x = torch.randn(B, K, generator=g, device=dev).to(torch.bfloat16)
+    out = torch.zeros(B, N // 2 if which == "gu" else N, dtype=torch.bfloat16, device=dev)
 
     def chain():
         for W in Ws:
