@@ -13,6 +13,8 @@
 // SM (3 x 32 KiB ring each).
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
+
 namespace skv {
 
 constexpr int kSmTileRows = 128;                 // landmarks per tile = UMMA M
@@ -221,7 +223,8 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
   if (append) p.ap = *append;
   // two CTAs per SM; every CTA of a row strides over that row's tiles
-  int cpr = (2 * kNumSMs + BH - 1) / BH;
+  static const int target = [] { const char *e = getenv("SKV_SCORE_CTAS"); return (e && *e) ? atoi(e) : 2 * kNumSMs; }();
+  int cpr = (target + BH - 1) / BH;
   if (cpr > T) cpr = T;
   if (cpr < 1) cpr = 1;
   p.ctas_per_row = cpr;
