@@ -344,6 +344,15 @@ typedef struct skv_dense_epilogue {
   void *out;             /* F32: float*; RESID / SILU_MUL: bf16*; QKV_ROPE: q                   */
   skv_bf16 *k_out;       /* QKV_ROPE                                                            */
   skv_bf16 *v_out;       /* QKV_ROPE                                                            */
+  /* QKV_ROPE, optional (all zero: the whole fused wqkv, k / v written as [B,kv_heads,128]): */
+  int32_t head0;         /* W holds only the heads [head0, head0 + head_count) of the fused wqkv numbering
+                          * (q heads, then k heads, then v heads); out_features = 128 * head_count.  Lets the q
+                          * projection run on the critical path and the k / v projection beside it.           */
+  int32_t head_count;    /* 0: all heads from head0 on                                                       */
+  int32_t kv_row;        /* with kv_stride_h != 0: k / v are APPENDED in place (update_kv_cache,              */
+  int32_t reserved2;     /* kv_cache.py:1227-1271): element [b, head, kv_row + *pos_dev, :] of the cache      */
+  int64_t kv_stride_b;   /* buffers k_out / v_out with these element strides                                  */
+  int64_t kv_stride_h;
   const void *prefetch_next; /* optional hint: the weights the NEXT linear of the stream will read (16-byte aligned).   */
   int64_t prefetch_bytes;    /* Every CTA pulls its share of the first prefetch_bytes into L2 once it has issued its own
                               * last load, so HBM keeps streaming through the kernel's tail and the hand-over.         */

@@ -38,7 +38,9 @@ class DenseEpilogue(C.Structure):
                 ("cos_sin_rows", C.c_int32), ("pos", C.c_int32), ("static_weights", C.c_int32), ("reserved", C.c_int32),
                 ("pos_dev", C.c_void_p), ("bias", C.c_void_p),
                 ("resid", C.c_void_p), ("cos_sin", C.c_void_p), ("out", C.c_void_p), ("k_out", C.c_void_p),
-                ("v_out", C.c_void_p), ("prefetch_next", C.c_void_p), ("prefetch_bytes", C.c_int64)]
+                ("v_out", C.c_void_p), ("head0", C.c_int32), ("head_count", C.c_int32), ("kv_row", C.c_int32),
+                ("reserved2", C.c_int32), ("kv_stride_b", C.c_int64), ("kv_stride_h", C.c_int64),
+                ("prefetch_next", C.c_void_p), ("prefetch_bytes", C.c_int64)]
 
 
 if not os.path.exists(LIB_PATH):

@@ -42,6 +42,9 @@ struct DenseParams {
   float *out_f32;
   int up_row0;            // SILU_MUL: first "up" row of W (= F); tile t = gate rows [64t, 64t+64) + up rows [F+64t, ..)
   int q_heads, kv_heads, rope_mode, cos_sin_rows, pos;
+  int head0;              // QKV_ROPE: W holds the heads [head0, head0 + T) of the fused wqkv
+  int kv_row;             // QKV_ROPE with kv_stride_h != 0: k / v go to row kv_row (+ *pos_dev) of a cache buffer
+  long long kv_stride_b, kv_stride_h;
   int static_w;           // W may be read before griddepcontrol.wait
   int trace_id;           // SKV_TRACE builds: launch counter
   int reorder;            // split tiles first (SegOrder)
@@ -131,9 +134,10 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int 
     }
     epi_bar();
   } else {  // SKV_DENSE_QKV_ROPE: tile = head
-    const int n = t * 128 + row;
+    const int th = t + p.head0;                                    // head index in the fused wqkv numbering
+    const int n = th * 128 + row;
     const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
-    const bool is_q = t < p.q_heads, is_k = !is_q && t < p.q_heads + p.kv_heads;
+    const bool is_q = th < p.q_heads, is_k = !is_q && th < p.q_heads + p.kv_heads;
     const bool rope = p.rope_mode != 0 && (is_q || is_k);          // uniform over the tile
 #pragma unroll
     for (int b = 0; b < NPAD; ++b) v[b] = bfr(v[b] + bias);
@@ -170,14 +174,24 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int 
       }
       epi_bar();
     }
-    __nv_bfloat16 *dst;
-    int heads, head;
-    if (is_q) { dst = p.out; heads = p.q_heads; head = t; }
-    else if (is_k) { dst = p.k_out; heads = p.kv_heads; head = t - p.q_heads; }
-    else { dst = p.v_out; heads = p.kv_heads; head = t - p.q_heads - p.kv_heads; }
+    if (is_q || p.kv_stride_h == 0) {
+      __nv_bfloat16 *dst;
+      int heads, head;
+      if (is_q) { dst = p.out; heads = p.q_heads; head = th; }
+      else if (is_k) { dst = p.k_out; heads = p.kv_heads; head = th - p.q_heads; }
+      else { dst = p.v_out; heads = p.kv_heads; head = th - p.q_heads - p.kv_heads; }
 #pragma unroll
-    for (int b = 0; b < NPAD; ++b)
-      if (b < p.B) dst[(size_t(b) * heads + head) * 128 + row] = __float2bfloat16_rn(v[b]);
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) dst[(size_t(b) * heads + head) * 128 + row] = __float2bfloat16_rn(v[b]);
+    } else {
+      // append in place: row kv_row (+ the device-side generation counter) of the layer's K / V buffer [B,H,rows,128]
+      __nv_bfloat16 *dst = is_k ? p.k_out : p.v_out;
+      const int head = is_k ? th - p.q_heads : th - p.q_heads - p.kv_heads;
+      const long long r = (long long)p.kv_row + (p.pos_dev ? *p.pos_dev : 0);
+#pragma unroll
+      for (int b = 0; b < NPAD; ++b)
+        if (b < p.B) dst[b * p.kv_stride_b + head * p.kv_stride_h + r * 128 + row] = __float2bfloat16_rn(v[b]);
+    }
   }
 }
 
@@ -671,12 +685,21 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
       p.T = p.up_row0 / 64;
       break;
     case SKV_DENSE_QKV_ROPE:
-      if (epi->q_heads < 1 || epi->kv_heads < 1 || out_features != (epi->q_heads + 2 * epi->kv_heads) * 128 || !epi->k_out ||
-          !epi->v_out || epi->rope_mode < 0 || epi->rope_mode > 2 || (epi->rope_mode && (!epi->cos_sin || epi->cos_sin_rows < 1))) {
-        set_error("dense_linear: qkv_rope needs out_features = (q_heads + 2 kv_heads) * 128, k_out, v_out and a cos_sin table");
-        return SKV_ERR_ARGUMENT;
+      {
+        const int all = epi->q_heads + 2 * epi->kv_heads;
+        const int n_heads = epi->head_count > 0 ? epi->head_count : all - epi->head0;
+        const bool has_kv = epi->head0 + n_heads > epi->q_heads;
+        if (epi->q_heads < 1 || epi->kv_heads < 1 || epi->head0 < 0 || n_heads < 1 || epi->head0 + n_heads > all ||
+            out_features != n_heads * 128 || (has_kv && (!epi->k_out || !epi->v_out)) || epi->rope_mode < 0 ||
+            epi->rope_mode > 2 || (epi->rope_mode && (!epi->cos_sin || epi->cos_sin_rows < 1))) {
+          set_error("dense_linear: qkv_rope needs out_features = 128 x (heads of the launch), k_out / v_out when the launch "
+                    "covers k / v heads, and a cos_sin table");
+          return SKV_ERR_ARGUMENT;
+        }
+        p.T = n_heads;
+        p.head0 = epi->head0;
+        p.kv_row = epi->kv_row; p.kv_stride_b = epi->kv_stride_b; p.kv_stride_h = epi->kv_stride_h;
       }
-      p.T = epi->q_heads + 2 * epi->kv_heads;
       p.q_heads = epi->q_heads; p.kv_heads = epi->kv_heads; p.rope_mode = epi->rope_mode;
       p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(epi->cos_sin);
       p.cos_sin_rows = epi->cos_sin_rows; p.pos = epi->pos; p.pos_dev = epi->pos_dev;

@@ -149,24 +149,45 @@ def linear_silu_mul(x: torch.Tensor, W_gate_up: torch.Tensor, out: torch.Tensor 
 
 def linear_qkv_rope(x: torch.Tensor, wqkv: torch.Tensor, q_heads: int, kv_heads: int, cos_sin: torch.Tensor | None,
                     pos: int, *, bias: torch.Tensor | None = None, glm: bool = False, pos_dev: torch.Tensor | None = None,
-                    q_out=None, k_out=None, v_out=None, static_weights: bool = False, prefetch=None):
+                    q_out=None, k_out=None, v_out=None, static_weights: bool = False, prefetch=None,
+                    heads: tuple[int, int] | None = None, kv_cache=None):
     """``F.linear(h, wqkv[, bqkv])`` + split + ``vllm._custom_ops.rotary_embedding`` on q and k (reference
     models/llama.py:377-385 + 296; models/glm.py:344-357 + 421).  Returns q [B,q_heads,1,128], k, v [B,kv_heads,1,128]
     -- the layout ``ShadowKVCache_CPU.decode_layer`` takes.  cos_sin None: no rotary embedding.  The token position is
-    ``pos`` (+ ``pos_dev[0]``, an int32 device counter, when given)."""
+    ``pos`` (+ ``pos_dev[0]``, an int32 device counter, when given).
+
+    heads=(first, count): ``wqkv`` holds only those heads of the fused matrix (q heads, then k, then v; pass the row
+    slice ``wqkv_full[first*128:(first+count)*128]``; ``bias`` stays the full vector), so the q projection can run on the
+    critical path and the k / v projection beside it.  kv_cache=(k_buf, v_buf, row): k and v are appended IN PLACE at
+    row ``row`` (+ ``pos_dev[0]``) of the layer's cache buffers [B,H,rows,128] (``update_kv_cache``,
+    kv_cache.py:1227-1271) instead of being returned."""
     _check_x(x, wqkv)
     B, dev = x.shape[0], x.device
-    q = torch.empty(B, q_heads, 1, 128, dtype=torch.bfloat16, device=dev) if q_out is None else q_out
-    k = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if k_out is None else k_out
-    v = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if v_out is None else v_out
+    h0, cnt = heads if heads is not None else (0, q_heads + 2 * kv_heads)
+    has_q, has_kv = h0 < q_heads, h0 + cnt > q_heads
+    q = k = v = None
+    if has_q:
+        q = torch.empty(B, q_heads, 1, 128, dtype=torch.bfloat16, device=dev) if q_out is None else q_out
+    kv_row = kv_sb = kv_sh = 0
+    if has_kv:
+        if kv_cache is not None:
+            k, v, kv_row = kv_cache
+            if k.dim() != 4 or k.stride(3) != 1 or k.stride(2) != 128 or k.stride() != v.stride():
+                raise ValueError("kv_cache buffers must be [B, H, rows, 128] with contiguous rows")
+            kv_sb, kv_sh = k.stride(0), k.stride(1)
+        else:
+            k = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if k_out is None else k_out
+            v = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if v_out is None else v_out
     epi = _lib.DenseEpilogue(mode=QKV_ROPE, q_heads=q_heads, kv_heads=kv_heads,
                              rope_mode=0 if cos_sin is None else (2 if glm else 1),
                              cos_sin_rows=0 if cos_sin is None else cos_sin.shape[0], pos=int(pos),
                              pos_dev=pos_dev.data_ptr() if pos_dev is not None else None,
                              bias=bias.data_ptr() if bias is not None else None,
                              cos_sin=cos_sin.data_ptr() if cos_sin is not None else None,
-                             out=q.data_ptr(), k_out=k.data_ptr(), v_out=v.data_ptr(),
-                             static_weights=int(static_weights))
+                             out=q.data_ptr() if q is not None else k.data_ptr(),
+                             k_out=k.data_ptr() if k is not None else None, v_out=v.data_ptr() if v is not None else None,
+                             static_weights=int(static_weights), head0=h0, head_count=cnt, kv_row=int(kv_row),
+                             kv_stride_b=kv_sb, kv_stride_h=kv_sh)
     _launch(x, wqkv, epi, "dense_linear_qkv_rope", prefetch)
     return q, k, v
 

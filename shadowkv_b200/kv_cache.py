@@ -485,7 +485,7 @@ class ShadowKVCache_CPU:
         return out
 
     def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
-                     device_counters=False, after_select=None):
+                     device_counters=False, after_select=None, before_attention=None):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
         query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
@@ -493,14 +493,18 @@ class ShadowKVCache_CPU:
         captured in a CUDA graph and replayed (see reset/advance_device_counters)."""
         self.incoming_q_len = 1
         g = self._geometry(cos_sin_cache)
-        # (a2) fused into the scoring launch: same rows, same position as update_kv_cache
-        kc, vc = key_states.contiguous(), value_states.contiguous()
+        # (a2) fused into the scoring launch: same rows, same position as update_kv_cache.  key_states None: the caller
+        # appends the token's K / V rows itself before the attention (the whole-model runner's K/V projection writes
+        # them in place from a side stream and joins through `before_attention`)
         pos = self.sparse_end + (0 if device_counters else self.gen_offset)
         if pos >= self.buf_len:
             raise RuntimeError(f"generation buffer full ({self.buf_len - self.sparse_end} tokens)")
-        ap = _lib.Append(k_new=kc.data_ptr(), v_new=vc.data_ptr(), k_buf=self.k_cache_buffer[layer_idx].data_ptr(),
-                         v_buf=self.v_cache_buffer[layer_idx].data_ptr(),
-                         pos_dev=self.gen_dev.data_ptr() if device_counters else None, pos=pos)
+        ap = None
+        if key_states is not None:
+            kc, vc = key_states.contiguous(), value_states.contiguous()
+            ap = _lib.Append(k_new=kc.data_ptr(), v_new=vc.data_ptr(), k_buf=self.k_cache_buffer[layer_idx].data_ptr(),
+                             v_buf=self.v_cache_buffer[layer_idx].data_ptr(),
+                             pos_dev=self.gen_dev.data_ptr() if device_counters else None, pos=pos)
         pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
         if after_select is not None:
             # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
@@ -529,6 +533,8 @@ class ShadowKVCache_CPU:
                 side.wait_event(self._fetch_done)
                 self.fill_value_store(layer_idx)
         cur.wait_event(self._k_done)
+        if before_attention is not None:
+            before_attention()
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
         return self.attention(layer_idx, query_states, kv_len, out, device_counters)
 

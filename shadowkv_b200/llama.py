@@ -55,12 +55,14 @@ class Llama:
                  device: str = "cuda:0", sparse_budget: int = 2048, rank: int = 160, chunk_size: int = 8,
                  num_layers: int | None = None, seed: int = 0, kv_cache: ShadowKVCache_CPU | None = None,
                  hbm_store_ways: int = 0, l2_prefetch_mb: float = 96.0, next_prefetch_mb: float = 32.0,
-                 fused_finish: bool = True) -> None:
+                 fused_finish: bool = True, split_qkv: bool = True) -> None:
         """l2_prefetch_mb: bytes of the layer's o_proj / gate_up weights pulled into L2 (126 MB on B200) on a side
         stream while the sparse-KV step of the same layer waits on its PCIe fetch (0 disables).
         next_prefetch_mb: head of the next linear's weights each dense kernel pulls into L2 during its own tail.
         fused_finish: o_proj / down_proj leave partial planes and the following norm kernel finishes them
-        (dense.linear_partial + dense.finish_rmsnorm) instead of linear(residual=) + rmsnorm; same bits."""
+        (dense.linear_partial + dense.finish_rmsnorm) instead of linear(residual=) + rmsnorm; same bits.
+        split_qkv: only the q projection runs on the critical path; the k / v projection of the layer runs on a side
+        stream in the PCIe window of the sparse-KV step and appends its rows in place."""
         self.shape = synth.MODELS[model] if isinstance(model, str) else model
         self.device = torch.device(device)
         self.batch_size, self.max_length = batch_size, max_length
@@ -94,6 +96,8 @@ class Llama:
         self.l2_prefetch_bytes = int(l2_prefetch_mb * 1e6)
         self.next_prefetch_bytes = int(next_prefetch_mb * 1e6) & ~15
         self.fused_finish = fused_finish
+        self.split_qkv = split_qkv
+        self.kv_stream = torch.cuda.Stream(device=dev)
         self.greedy = True                      # the token body ends in the argmax kernel (temperature 0)
         self.prefetch_stream = torch.cuda.Stream(device=dev)
         self._prepared = False
@@ -167,13 +171,44 @@ class Llama:
 
     # ---- one decode token with device-side counters: the body of the CUDA graph ---------------------------------
     def _pre_attention_step(self, l: int):
-        """Fused QKV + RoPE of layer l from the already normalised self.h (device-side position counter)."""
+        """Fused QKV + RoPE of layer l from the already normalised self.h (device-side position counter).  With
+        split_qkv only the q heads are projected here, on the critical path; k and v follow in `_after_select_hook`."""
         c, buf = self.kv_cache, self.layers[l]
-        self.pre_attention_compute(None, buf, self.num_heads, self.num_key_value_heads, 128, position=c.prefill,
-                                   pos_dev=c.gen_dev, normed=self.h, out=(self.q, self.k, self.v))
+        if not self.split_qkv:
+            self.pre_attention_compute(None, buf, self.num_heads, self.num_key_value_heads, 128, position=c.prefill,
+                                       pos_dev=c.gen_dev, normed=self.h, out=(self.q, self.k, self.v))
+            return
+        Hq = self.num_heads
+        dense.linear_qkv_rope(self.h, buf.wqkv[:Hq * 128], Hq, self.num_key_value_heads, self.cos_sin_cache, c.prefill,
+                              bias=buf.bqkv, glm=self.shape.glm_rope, pos_dev=c.gen_dev, q_out=self.q,
+                              static_weights=True, heads=(0, Hq))
+
+    def _project_kv_in_place(self, l: int):
+        """k / v projection + RoPE(k) of layer l on `kv_stream`, appended in place to the layer's cache buffers
+        (update_kv_cache, kv_cache.py:1227-1271).  Runs while the sparse-KV step waits on its PCIe fetch; the attention
+        joins it through `_before_attention_hook`."""
+        c, buf = self.kv_cache, self.layers[l]
+        Hq, H = self.num_heads, self.num_key_value_heads
+        cur, side = torch.cuda.current_stream(), self.kv_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            dense.linear_qkv_rope(self.h, buf.wqkv[Hq * 128:], Hq, H, self.cos_sin_cache, c.prefill, bias=buf.bqkv,
+                                  glm=self.shape.glm_rope, pos_dev=c.gen_dev, static_weights=True, heads=(Hq, 2 * H),
+                                  kv_cache=(c.k_cache_buffer[l], c.v_cache_buffer[l], c.sparse_end))
 
     def _after_select_hook(self, l: int):
-        return (lambda b=self.layers[l]: self._prefetch_post_attention_weights(b)) if self.l2_prefetch_bytes else None
+        if not (self.l2_prefetch_bytes or self.split_qkv):
+            return None
+
+        def hook(l=l, b=self.layers[l]):
+            if self.split_qkv:
+                self._project_kv_in_place(l)
+            if self.l2_prefetch_bytes:
+                self._prefetch_post_attention_weights(b)
+        return hook
+
+    def _before_attention_hook(self):
+        return (lambda: torch.cuda.current_stream().wait_stream(self.kv_stream)) if self.split_qkv else None
 
     def _post_attention_step(self, l: int):
         """o_proj + residual, norm, gate/up + SiLU*mul, down + residual, next norm -- in place on self.x / self.h.
@@ -217,8 +252,9 @@ class Llama:
                             L[0].input_layernorm_variance_epsilon, self.x, self.h)
         for l in range(len(L)):
             self._pre_attention_step(l)
-            c.decode_layer(l, self.q, self.k, self.v, self.cos_sin_cache, out=self.attn, device_counters=True,
-                           after_select=self._after_select_hook(l))
+            kv = (None, None) if self.split_qkv else (self.k, self.v)
+            c.decode_layer(l, self.q, kv[0], kv[1], self.cos_sin_cache, out=self.attn, device_counters=True,
+                           after_select=self._after_select_hook(l), before_attention=self._before_attention_hook())
             self._post_attention_step(l)
         self._head_step()
         if self.l2_prefetch_bytes:

@@ -187,6 +187,42 @@ def test_qkv_rope(cuda, model, B, use_dev_pos):
     assert torch.equal(v0, v)
 
 
+@pytest.mark.parametrize("model,B", [("llama-3.1-8b", 2), ("glm-4-9b-1m", 3)])
+def test_qkv_head_ranges_and_in_place_append(cuda, model, B):
+    """The q heads and the k / v heads projected by two launches (row slices of the fused wqkv), k / v appended in
+    place at row `row + *pos_dev` of strided [B,H,rows,128] cache buffers: same values as the oracle's fused call."""
+    from shadowkv_b200 import dense
+    sh = synth.MODELS[model]
+    Hq, H, hid = sh.num_attention_heads, sh.num_key_value_heads, sh.hidden_size
+    g = torch.Generator().manual_seed(B + H)
+    h = _rn(g, B, hid)
+    Wqkv = _rn(g, (Hq + 2 * H) * 128, hid, scale=0.03)
+    bias = _rn(g, (Hq + 2 * H) * 128, scale=0.5) if sh.glm_rope else None
+    cs = synth.cos_sin_table(9000, theta=sh.rope_theta, glm=sh.glm_rope)
+    pos, gen, row0, rows = 8100, 37, 2496, 2592
+    qkv = DO.linear(h, Wqkv, bias)
+    wq, wk, wv = qkv.split([Hq * 128, H * 128, H * 128], dim=-1)
+    wq = DO.rotary_vllm(wq.reshape(B, Hq, 128), cs[pos + gen], neox=not sh.glm_rope)
+    wk = DO.rotary_vllm(wk.reshape(B, H, 128), cs[pos + gen], neox=not sh.glm_rope)
+    wv = wv.reshape(B, H, 128)
+    dev_h, dev_W, dev_cs = h.to(cuda), Wqkv.to(cuda), cs.to(cuda)
+    dev_b = bias.to(cuda) if bias is not None else None
+    pos_dev = torch.tensor([gen], dtype=torch.int32, device=cuda)
+    q, k0, v0 = dense.linear_qkv_rope(dev_h, dev_W[:Hq * 128], Hq, H, dev_cs, pos, bias=dev_b, glm=sh.glm_rope,
+                                      pos_dev=pos_dev, heads=(0, Hq))
+    assert k0 is None and v0 is None
+    assert_rope_rows_close(q.view(B, Hq, 128), wq, glm=sh.glm_rope, ulps_in=1, frac_exact=0.93, what="q heads")
+    kbuf = torch.full((B, H, rows, 128), 7.0, dtype=BF16, device=cuda)
+    vbuf = torch.full((B, H, rows, 128), 7.0, dtype=BF16, device=cuda)
+    dense.linear_qkv_rope(dev_h, dev_W[Hq * 128:], Hq, H, dev_cs, pos, bias=dev_b, glm=sh.glm_rope, pos_dev=pos_dev,
+                          heads=(Hq, 2 * H), kv_cache=(kbuf, vbuf, row0))
+    assert_rope_rows_close(kbuf[:, :, row0 + gen], wk, glm=sh.glm_rope, ulps_in=1, frac_exact=0.93, what="k row")
+    assert_ulp_bf16(vbuf[:, :, row0 + gen], wv, ulps=1, frac_exact=0.97, what="v row")
+    kbuf[:, :, row0 + gen] = 7.0
+    vbuf[:, :, row0 + gen] = 7.0
+    assert bool((kbuf == 7.0).all()) and bool((vbuf == 7.0).all()), "only the appended row may be written"
+
+
 def test_argument_errors(cuda):
     from shadowkv_b200 import dense
     x = torch.zeros(33, 4096, dtype=BF16, device=cuda)
@@ -228,11 +264,11 @@ def test_layer_methods_against_oracle(cuda, model):
     assert exact > 0.75, exact
 
 
-def _build_model(layers, B, ctx, hbm_store_ways=0):
+def _build_model(layers, B, ctx, hbm_store_ways=0, split_qkv=True):
     from shadowkv_b200.llama import Llama
     sh = synth.MODELS["llama-3.1-8b"]
     m = Llama("llama-3.1-8b", batch_size=B, max_length=ctx, device="cuda:0", num_layers=layers, seed=7,
-              hbm_store_ways=hbm_store_ways)
+              hbm_store_ways=hbm_store_ways, split_qkv=split_qkv)
     states = [synth.layer_state(sh, B, ctx, seed=100 + l, device="cuda:0", cos_sin=m.cos_sin_cache) for l in range(layers)]
     synth.install(m.kv_cache, states)
     torch.cuda.synchronize()
@@ -244,9 +280,13 @@ def test_token_runner_matches_the_reference_named_call_chain(cuda):
     fused into the previous step, in-place residual stream) against the eager reference-named chain
     inference -> layer_compute -> pre/post_attention_compute, token after token on the same token ids.  (One layer:
     the two paths split the attention differently, and with more layers a last-bit difference can flip a chunk of the
-    next layer's top-S selection, which is a discontinuity, not an error.)"""
+    next layer's top-S selection, which is a discontinuity, not an error.  For the same reason the runner projects
+    q, k, v in ONE launch here, like the eager chain: the two-launch split of the default runner sums the same products
+    in another order, and a last-bit difference in q can flip a borderline chunk of this layer's own selection; the
+    split launches are checked against the oracle in test_qkv_head_ranges_and_in_place_append and, end to end, in the
+    graph-replay test below.)"""
     B, ctx = 2, 8192
-    a, b = _build_model(1, B, ctx), _build_model(1, B, ctx)
+    a, b = _build_model(1, B, ctx), _build_model(1, B, ctx, split_qkv=False)
     tok = torch.tensor([11, 4242], dtype=torch.int64, device=cuda)
     for t in range(3):
         pos = torch.full((B, 1), ctx + t, dtype=torch.int64, device=cuda)

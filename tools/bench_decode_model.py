@@ -144,10 +144,14 @@ def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupl
                 hh = F.rms_norm(x, (hid,), buf.input_layernorm_weight, 1e-5)
                 m.q.view(B, -1).copy_(F.linear(hh, buf.wqkv)[:, :Hq * 128])
             hook = m._after_select_hook(l) if mode == "native" else None
+            pre = m._before_attention_hook() if mode == "native" else None
+            split = mode == "native" and m.split_qkv             # k / v rows are then appended by the side-stream projection
             if coupled and mode == "native":
-                cache.decode_layer(l, m.q, m.k, m.v, cs, out=m.attn, device_counters=True, after_select=hook)
+                cache.decode_layer(l, m.q, None if split else m.k, None if split else m.v, cs, out=m.attn,
+                                   device_counters=True, after_select=hook, before_attention=pre)
             else:
-                cache.decode_layer(l, q_in[l], k_in[l], k_in[l], cs, out=m.attn, device_counters=True, after_select=hook)
+                cache.decode_layer(l, q_in[l], None if split else k_in[l], None if split else k_in[l], cs, out=m.attn,
+                                   device_counters=True, after_select=hook, before_attention=pre)
             if mode == "native":
                 m._post_attention_step(l)
             elif mode == "library":
@@ -201,7 +205,7 @@ def whole_model(m: Llama, *, steps: int, warmup: int, noise: float = 0.28, coupl
                 "down, lm_head, argmax) through this repo's kernels; 'library' = the same through torch / cuBLAS calls, as "
                 "the reference's model files do; the sparse-KV step is this repo's in both",
         "batch": B, "layers": L, "coupled_qkv": bool(coupled), "hbm_store_ways": cache.hbm_store_ways,
-        "l2_prefetch_mb": m.l2_prefetch_bytes / 1e6, "next_prefetch_mb": m.next_prefetch_bytes / 1e6,
+        "split_qkv": bool(m.split_qkv), "l2_prefetch_mb": m.l2_prefetch_bytes / 1e6, "next_prefetch_mb": m.next_prefetch_bytes / 1e6,
         "dense_weight_GB": wb / 1e9, "hbm_peak_GBps": hbm_peak, "steps": steps, "warmup": warmup,
         "dense_env": {k: os.environ.get(k) for k in ("SKV_DENSE_STAGES", "SKV_DENSE_CTAS_PER_SM", "SKV_DENSE_ORDER", "SKV_PDL")
                       if os.environ.get(k)},
@@ -256,11 +260,12 @@ def main():
     ap.add_argument("--l2-prefetch-mb", type=float, default=96.0)
     ap.add_argument("--next-prefetch-mb", type=float, default=32.0)
     ap.add_argument("--model", default="llama-3.1-8b")
+    ap.add_argument("--no-split-qkv", action="store_true")
     ap.add_argument("--store-ways", type=int, default=0, help="also time the native loop with an HBM chunk store")
     args = ap.parse_args()
     m = Llama(args.model, batch_size=args.batch, max_length=args.ctx, device="cuda:0", num_layers=args.layers or None,
               hbm_store_ways=args.hbm_store_ways, l2_prefetch_mb=args.l2_prefetch_mb,
-              next_prefetch_mb=args.next_prefetch_mb)
+              next_prefetch_mb=args.next_prefetch_mb, split_qkv=not args.no_split_qkv)
     install_synthetic_state(m, args.ctx)
     print(json.dumps(whole_model(m, steps=args.steps, warmup=args.warmup, noise=args.noise, coupled=args.coupled,
                                  ops=not args.skip_ops, store_ways=args.store_ways)))
