@@ -102,3 +102,29 @@ def test_dense_entry_points_reject_bad_arguments_without_a_gpu():
     # plane buffer: 4096 x 4096 splits into 32 tiles x 64 slabs over 148 CTAs -> at most 6 CTAs touch a tile
     assert lib.skv_dense_partial_bytes(1, 4096, 4096) == 6 * 4096 * 4
     assert lib.skv_dense_partial_bytes(2, 64, 128) == 2 * 2 * 128 * 4
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/shadowkv_b200.h is the boundary a cgo / JNI / ctypes binding would consume: it has to compile as C99
+    (no C++ in the signatures) and a C program has to link against the library and get the documented error codes."""
+    import shutil
+    import subprocess
+    import pytest
+    from shadowkv_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(
+        '#include "shadowkv_b200.h"\n#include <string.h>\n'
+        "int main(void) {\n"
+        '  if (!strstr(skv_version(), "sm_100a")) return 2;\n'
+        "  if (skv_reorder_keys_and_compute_offsets(0, 0, 0, 0, 1, 1, 256, 0) != SKV_ERR_ARGUMENT) return 3;\n"
+        '  if (!strstr(skv_last_error(), "null")) return 4;\n'
+        "  if (skv_gather_copy((const skv_bf16 *)16, (skv_bf16 *)16, (const int64_t *)16, 1, 8, 100, 100, 200, 0)"
+        " != SKV_ERR_UNSUPPORTED) return 5;\n"
+        "  return 0;\n}\n")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "caller"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lshadowkv_b200", f"-Wl,-rpath,{libdir}"])
+    assert subprocess.call([str(exe)]) == 0
