@@ -241,6 +241,7 @@ def workload_config(args, shape, L, *, hit_rate, n_gpus, heads_mode=False):
             "layers": L,
             "landmarks": lay.n_landmarks, "select_chunks": lay.select, "kv_rows_attended": lay.sparse_end + 1,
             "chunk_cache_hit_rate": round(hit_rate, 4), "query_noise": args.noise, "table_mode": args.table_mode,
+            "fetch_rebuild_launch": "two launches, two streams" if os.environ.get("SKV_FUSED_FETCH") == "0" else "one launch",
             "l2_policy": "inputs larger than L2: per token the step streams every layer's landmarks, "
                          f"{L} x {lay.n_landmarks * shape.num_key_value_heads * 256 / 1e6:.1f} MB per sequence",
             "parallelism": (f"kv heads split x{n_gpus}, one all-gather of the attention output per layer" if heads_mode
@@ -586,10 +587,20 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
                                        res.data_ptr(), cache.cnts.data_ptr(), cache.offsets.data_ptr(), cache.k_cache_buffer[l].data_ptr(), 0, cur()),
                   "rebuild")
 
+        def fetch_rebuild(l):            # the launch the step uses: both transfers of the missed chunks in one grid
+            vh = cache.v_cache_cpu[l]
+            check(lib.skv_fetch_and_rebuild(C.byref(g), vh.data_ptr(), vh.stride(1), cache.v_cache_buffer[l].data_ptr(),
+                                            cache.U[l].data_ptr(), cache.SV[l].data_ptr(), cs.data_ptr(),
+                                            cache.k_cache_buffer[l].data_ptr(), res.data_ptr(), cache.cnts.data_ptr(),
+                                            cache.offsets.data_ptr(), None, cur()), "fetch_and_rebuild")
+
         row = {}
         if miss:
-            t = timed(fetch, 2 * L)
             by = B * H * miss * 2048
+            t = timed(fetch_rebuild, 2 * L)
+            row["fetch_rebuild_us"] = t
+            row["fetch_rebuild_GBps_pcie"] = by / t * 1e-3
+            t = timed(fetch, 2 * L)
             row["fetch_us"] = t
             row["fetch_GBps_pcie"] = by / t * 1e-3
             t = timed(rebuild, 2 * L)
@@ -623,6 +634,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, *, full=True):
     for label in ("h0", "h60"):
         if "fetch_GBps_pcie" in kernels.get(label, {}):
             kernels[label]["fetch_frac_pcie"] = kernels[label]["fetch_GBps_pcie"] / pcie["h2d_memcpy_GBps"]
+            kernels[label]["fetch_rebuild_frac_pcie"] = kernels[label]["fetch_rebuild_GBps_pcie"] / pcie["h2d_memcpy_GBps"]
     return kernels, roofline, pcie
 
 

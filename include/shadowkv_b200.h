@@ -274,6 +274,27 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
                          int64_t stride_h, int64_t stride_row, float scale, int num_splits, void *workspace,
                          const int32_t *kv_len_dev, skv_stream_t stream);
 
+/* skv_attention_decode with launch flags.  SKV_ATTN_PROGRAMMATIC: launch with programmatic stream serialization,
+ * i.e. the kernel may be scheduled while the preceding kernel of the stream still runs and waits on the device
+ * (griddepcontrol.wait) before it reads q, K, V or kv_len_dev.  Only for a caller whose preceding operation in
+ * `stream` is the single kernel that produced the last of those inputs (skv_fetch_and_rebuild in the decode step). */
+#define SKV_ATTN_PROGRAMMATIC 1
+int skv_attention_decode_ex(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch,
+                            int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b,
+                            int64_t stride_h, int64_t stride_row, float scale, int num_splits, void *workspace,
+                            const int32_t *kv_len_dev, int flags, skv_stream_t stream);
+
+/* (a6) + (a7) in ONE launch (reference models/base.py:326-338 runs them on two streams and joins before the
+ * attention): the missed chunks' V rows come from the pinned host store (or the HBM chunk store) exactly as in
+ * skv_fetch_misses, their K rows are rebuilt exactly as in skv_rebuild_keys (tcgen05 path), by different CTAs of the
+ * same grid.  With a single predecessor the attention that follows can be launched programmatically
+ * (SKV_ATTN_PROGRAMMATIC).  Same arguments and table modes as the two calls it replaces; in the reference table
+ * mode the caller compacts the hits of both buffers first (skv_compact_hits). */
+int skv_fetch_and_rebuild(const skv_geom *geom, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
+                          const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
+                          const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
+                          const skv_vstore *vstore, skv_stream_t stream);
+
 /* ======================================================================
  * Part 3 -- prefill-side state build (reference models/kv_cache.py:788-980, ShadowKVCache_CPU.prefill_kv_cache)
  * ====================================================================== */

@@ -78,6 +78,8 @@ _SIGS = {
     "skv_gather_chunks": [_p, _l, _p, _l, _l, _p, _i, _i, _p],
     "skv_append_kv": [C.POINTER(Geom)] + [_p] * 4 + [_i, _p, _p],
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
+    "skv_attention_decode_ex": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _i, _p],
+    "skv_fetch_and_rebuild": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(VStore), _p],
     "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
     "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "skv_argmax": [_p, _p, _i, _i, _p],

@@ -10,7 +10,7 @@ namespace skv {
 // attention_mma.cu: TMA ring + tensor-core attention (product path)
 int launch_attention_mma(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch, int kv_heads,
                          int q_groups, int kv_len, int64_t stride_b, int64_t stride_h, int64_t stride_row, float scale,
-                         int num_splits, void *workspace, const int32_t *kv_len_dev, cudaStream_t st);
+                         int num_splits, void *workspace, const int32_t *kv_len_dev, bool pdl, cudaStream_t st);
 
 constexpr int kAttnMinWarps = 8;              // 256 threads: the combine maps 128 dims x 2 head pairs onto them
 constexpr int kAttnMaxWarps = 12;             // block size is chosen per launch (see plan_splits)
@@ -344,6 +344,14 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
                          int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b, int64_t stride_h,
                          int64_t stride_row, float scale, int num_splits, void *workspace,
                          const int32_t *kv_len_dev, skv_stream_t stream) {
+  return skv_attention_decode_ex(q, k, v, out, batch, kv_heads, q_groups, head_dim, kv_len, stride_b, stride_h, stride_row,
+                                 scale, num_splits, workspace, kv_len_dev, 0, stream);
+}
+
+int skv_attention_decode_ex(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch,
+                            int kv_heads, int q_groups, int head_dim, int kv_len, int64_t stride_b, int64_t stride_h,
+                            int64_t stride_row, float scale, int num_splits, void *workspace,
+                            const int32_t *kv_len_dev, int flags, skv_stream_t stream) {
   if (!q || !k || !v || !out || !workspace) { set_error("attention_decode: null pointer"); return SKV_ERR_ARGUMENT; }
   if (head_dim != kHeadDim || q_groups < 1 || kv_len < 1 || (stride_row % 8) || (stride_h % 8) || (stride_b % 8)) {
     set_error("attention_decode: need head_dim=128 and 16-byte aligned strides"); return SKV_ERR_UNSUPPORTED;
@@ -351,7 +359,7 @@ int skv_attention_decode(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
   static const bool simt = [] { const char *e = getenv("SKV_ATTN_IMPL"); return e && e[0] == '1'; }();
   if (!simt && q_groups <= 16)   // product path; SKV_ATTN_IMPL=1 selects the SIMT kernel below (cross-check)
     return launch_attention_mma(q, k, v, out, batch, kv_heads, q_groups, kv_len, stride_b, stride_h, stride_row, scale,
-                                num_splits, workspace, kv_len_dev, as_stream(stream));
+                                num_splits, workspace, kv_len_dev, (flags & SKV_ATTN_PROGRAMMATIC) != 0, as_stream(stream));
   AttnParams p{};
   p.q = q; p.k = k; p.v = v; p.out = out; p.kv_len_dev = kv_len_dev;
   p.B = batch; p.H = kv_heads; p.G = q_groups; p.ngz = (q_groups + kAttnGT - 1) / kAttnGT; p.kv_len = kv_len;

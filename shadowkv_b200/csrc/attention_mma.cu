@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(kAmThreads, 1)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
   }
   __syncthreads();
+  // under a programmatic launch everything above overlapped the predecessor's tail; q, the K / V buffers and the
+  // length counter are (transitively) the predecessors' outputs
+  pdl_wait();
 
   const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
   const int k_begin = split * p.keys_per_split;
@@ -309,7 +312,7 @@ int make_tensor_map_kv(CUtensorMap *out, const void *base, uint64_t rows, uint64
 
 int launch_attention_mma(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v, skv_bf16 *out, int batch, int kv_heads,
                          int q_groups, int kv_len, int64_t stride_b, int64_t stride_h, int64_t stride_row, float scale,
-                         int num_splits, void *workspace, const int32_t *kv_len_dev, cudaStream_t st) {
+                         int num_splits, void *workspace, const int32_t *kv_len_dev, bool pdl, cudaStream_t st) {
   CUtensorMap map_k, map_v;
   int rc = make_tensor_map_kv(&map_k, k, kv_len, kv_heads, batch, stride_row, stride_h, stride_b);
   if (rc) return rc;
@@ -356,7 +359,7 @@ int launch_attention_mma(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
     cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = smem;
   }
-  cudaError_t e = launch_kernel(attention_mma_kernel, dim3(ns, kv_heads, batch), dim3(kAmThreads), smem, st, /*pdl=*/false,
+  cudaError_t e = launch_kernel(attention_mma_kernel, dim3(ns, kv_heads, batch), dim3(kAmThreads), smem, st, pdl,
                                 map_k, map_v, p);
   if (e != cudaSuccess) { set_error("attention_mma_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("attention_mma_kernel");

@@ -38,9 +38,14 @@ struct RebuildParams {
   int tile_skip;             // 1: skip by whole tiles like the reference and write every row of a kept tile
 };
 
-__global__ void __launch_bounds__(128, 2)
-    rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_sv, RebuildParams p) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+// One 128-row tile (16 missed chunks) of one (b,h), worked on by threads 0..127 of the CTA.  Shared by the stand-alone
+// rebuild kernel and by the rebuild warps of fetch_rebuild_kernel.
+// barrier of the 128 threads that work on a tile (the whole CTA of rebuild_tcgen05_kernel, the first four warps of
+// fetch_rebuild_kernel)
+__device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void rebuild_tile(const CUtensorMap *map_sv_ptr, const RebuildParams &p, const int tile,
+                                             const int bh, unsigned char *smem) {
   unsigned char *sA = smem;                                   // n_slabs x 16 KiB
   // sized by the slabs the rank needs (rank 160 -> 3 slabs -> 96 KiB, two CTAs per SM), not by the maximum
   unsigned char *sB = smem + p.n_slabs * kSlabBytesA;         // n_slabs x 16 KiB
@@ -50,8 +55,8 @@ __global__ void __launch_bounds__(128, 2)
   int *s_ids = reinterpret_cast<int *>(tmem_slot + 2);        // [16] chunk id per tile row group (-1: skip)
   int *s_slots = s_ids + kTileChunks;                         // [16] destination slot
 
-  const int tile = blockIdx.x, bh = blockIdx.y, b = bh / p.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = bh / p.H;
+  const int warp = threadIdx.x >> 5;
   const int cnt = p.cnts ? p.cnts[bh] : 0;
   const int first_slot = tile * kTileChunks;
   if (p.miss_slots) {
@@ -78,11 +83,11 @@ __global__ void __launch_bounds__(128, 2)
     for (int s = 0; s < p.n_slabs; ++s) mbarrier_init(&full_bar[s], 1);
     mbarrier_init(mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_sv) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_sv_ptr) : "memory");
   }
   if (warp == 0) tcgen05_alloc(tmem_slot, 128);
   tcgen05_fence_before();
-  __syncthreads();
+  tile_sync();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -112,12 +117,12 @@ __global__ void __launch_bounds__(128, 2)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_slabs; ++s) {
       mbarrier_expect_tx(&full_bar[s], kSlabBytesB);
-      tma_load_2d(sB + s * kSlabBytesB, &map_sv, s * kSlabCols, bh * kHeadDim, &full_bar[s]);
+      tma_load_2d(sB + s * kSlabBytesB, map_sv_ptr, s * kSlabCols, bh * kHeadDim, &full_bar[s]);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   fence_proxy_async_smem();                                    // cp.async wrote through the generic proxy
-  __syncthreads();
+  tile_sync();
   if (threadIdx.x == 0) {
     // MMA issuer
     int step = 0;
@@ -222,8 +227,120 @@ __global__ void __launch_bounds__(128, 2)
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  tile_sync();
   if (warp == 0) tcgen05_dealloc(tmem_base, 128);
+}
+
+__global__ void __launch_bounds__(128, 2)
+    rebuild_tcgen05_kernel(const __grid_constant__ CUtensorMap map_sv, RebuildParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  rebuild_tile(&map_sv, p, blockIdx.x, blockIdx.y, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The two transfers a missed chunk needs, in ONE launch: its V rows from the pinned host store (PCIe, or the HBM
+// chunk store) and its K rows rebuilt from the low-rank factors.  A CTA owns 16 entries of the miss list (one rebuild
+// tile): warps 0-3 rebuild their K rows exactly as rebuild_tcgen05_kernel does, warps 4-7 fetch their V chunks, four
+// chunks per warp with all 16 x 16-byte loads of a lane in flight before the first store.  Grid, shared memory and
+// TMEM footprint are those of the rebuild kernel alone; the fetch warps only add registers.
+// Why one launch: with two launches on two streams the attention that follows has two predecessors and cannot be
+// launched programmatically; here the chain select -> fetch+rebuild -> attention -> next scoring has single
+// predecessors all the way (reference stream choreography: models/base.py:326-338).
+// ------------------------------------------------------------------------------------------------
+struct FetchParams {
+  const skv_bf16 *src;       // pinned host (or device) chunk-major store
+  int64_t src_stride_bh;     // elements
+  skv_bf16 *dst;             // V buffer
+  int64_t dst_stride_bh, dst_base_off;
+  const int32_t *offsets;    // reference table: chunk id of slot i >= cnt; in-place table: slot of the i-th miss
+  const int64_t *resident;   // in-place table only: chunk id per slot
+  skv_vstore vs;
+};
+
+constexpr int kFetchPerWarp = 4;
+
+__device__ __forceinline__ void fetch_entries(const FetchParams &f, const int32_t *cnts, const int S, const int block,
+                                              const int bh, const int warp) {
+  const int lane = threadIdx.x & 31;
+  const int i = (block * 4 + warp) * kFetchPerWarp;   // i + kFetchPerWarp <= S: the grid covers S entries exactly
+  const int32_t *off = f.offsets + size_t(bh) * S;
+  // The index chain (hit count | miss list -> slot -> chunk id -> store tag) for all four chunks at once: every level
+  // is one batch of independent loads, so its latency is paid once per warp and not once per chunk.  The list entries
+  // are read before the hit count is known (entries beyond the misses hold stale but in-range values).
+  int raw[kFetchPerWarp];
+#pragma unroll
+  for (int u = 0; u < kFetchPerWarp; ++u) raw[u] = off[i + u];
+  const int cnt = cnts[bh];
+  if (f.resident) {
+    if (i >= S - cnt) return;
+  } else if (i + kFetchPerWarp <= cnt) {
+    return;
+  }
+  const int4 *sbase = reinterpret_cast<const int4 *>(f.src + size_t(bh) * f.src_stride_bh);
+  int4 *dbase = reinterpret_cast<int4 *>(f.dst + size_t(bh) * f.dst_stride_bh + f.dst_base_off);
+  bool on[kFetchPerWarp];
+  int slot[kFetchPerWarp];
+  long long chunk[kFetchPerWarp];
+  if (f.resident) {
+#pragma unroll
+    for (int u = 0; u < kFetchPerWarp; ++u) {
+      on[u] = (i + u) < S - cnt;
+      slot[u] = raw[u] & (S - 1);                     // S is a power of two; a no-op for the entries that count
+      chunk[u] = f.resident[size_t(bh) * S + slot[u]];
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kFetchPerWarp; ++u) {
+      on[u] = (i + u) >= cnt;
+      slot[u] = i + u;
+      chunk[u] = raw[u];
+    }
+  }
+  const int4 *src[kFetchPerWarp];
+#pragma unroll
+  for (int u = 0; u < kFetchPerWarp; ++u) src[u] = sbase + size_t(chunk[u]) * (kChunkBytes / 16) + lane;
+  if (f.vs.tags) {                                    // HBM chunk store: read-only here (skv_vstore_fill updates it)
+    int tag[kFetchPerWarp];
+#pragma unroll
+    for (int u = 0; u < kFetchPerWarp; ++u) {
+      const size_t w = size_t(bh) * f.vs.ways + (static_cast<int>(chunk[u]) & (f.vs.ways - 1));
+      tag[u] = on[u] ? f.vs.tags[w] : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < kFetchPerWarp; ++u) {
+      if (!on[u]) continue;
+      const size_t w = size_t(bh) * f.vs.ways + (static_cast<int>(chunk[u]) & (f.vs.ways - 1));
+      if (tag[u] == static_cast<int>(chunk[u]))       // warp uniform
+        src[u] = reinterpret_cast<const int4 *>(f.vs.data) + w * (kChunkBytes / 16) + lane;
+      else if (f.vs.pcie_count && lane == 0)
+        atomicAdd(f.vs.pcie_count + bh, 1);
+    }
+  }
+  int4 v[kFetchPerWarp][4];
+#pragma unroll
+  for (int u = 0; u < kFetchPerWarp; ++u) {
+    if (on[u]) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[u][k] = ld_stream(src[u] + k * 32);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kFetchPerWarp; ++u) {
+    if (on[u]) {
+      int4 *d = dbase + size_t(slot[u]) * (kChunkBytes / 16) + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d[k * 32] = v[u][k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+    fetch_rebuild_kernel(const __grid_constant__ CUtensorMap map_sv, RebuildParams p, FetchParams f) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_launch_dependents();
+  pdl_wait();                                         // offsets / cnts / resident come from the selection kernel
+  if (threadIdx.x < 128) rebuild_tile(&map_sv, p, blockIdx.x, blockIdx.y, smem);
+  else fetch_entries(f, p.cnts, p.S, blockIdx.x, blockIdx.y, int(threadIdx.x >> 5) - 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,11 +491,61 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
   return launch_status("rebuild_tcgen05_kernel");
 }
 
+static int launch_fetch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p, FetchParams f, int B, cudaStream_t st) {
+  const int BH = B * p.H;
+  if (p.R % 8 || p.R < 8 || p.R > kMaxSlabs * kSlabCols) { set_error("fetch_and_rebuild: rank %d unsupported", p.R); return SKV_ERR_UNSUPPORTED; }
+  p.n_slabs = (p.R + kSlabCols - 1) / kSlabCols;
+  p.k_steps = (p.R + 15) / 16;
+  CUtensorMap map_sv;
+  int rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, p.R, kHeadDim, kSlabCols);
+  if (rc) return rc;
+  p.U = reinterpret_cast<const __nv_bfloat16 *>(U);
+  const int smem = p.n_slabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
+  static int attr = 0;
+  if (smem > attr) { cudaFuncSetAttribute(fetch_rebuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
+  static_assert(kTileChunks == 4 * kFetchPerWarp, "a CTA fetches the V chunks of the tile it rebuilds");
+  const int n_tiles = (p.S + kTileChunks - 1) / kTileChunks;
+  cudaError_t e = launch_kernel(fetch_rebuild_kernel, dim3(n_tiles, BH), dim3(256), smem, st, /*pdl=*/true, map_sv, p, f);
+  if (e != cudaSuccess) { set_error("fetch_rebuild_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("fetch_rebuild_kernel");
+}
+
 }  // namespace skv
 
 using namespace skv;
 
 extern "C" {
+
+int skv_fetch_and_rebuild(const skv_geom *g, const skv_bf16 *v_host, int64_t host_stride, skv_bf16 *v_buf,
+                          const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
+                          const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
+                          const skv_vstore *vstore, skv_stream_t stream) {
+  if (!g || !v_host || !v_buf || !U || !SV || !cos_sin || !k_buf || !resident || !cnts || !offsets) {
+    set_error("fetch_and_rebuild: null pointer"); return SKV_ERR_ARGUMENT;
+  }
+  if (vstore && (!vstore->tags || !vstore->data || vstore->ways < 1 || (vstore->ways & (vstore->ways - 1)))) {
+    set_error("fetch_and_rebuild: chunk store needs tags, data and a power-of-two way count"); return SKV_ERR_ARGUMENT;
+  }
+  if (g->head_dim != kHeadDim || g->chunk != kChunkTokens || !valid_map_size(g->select)) {
+    set_error("fetch_and_rebuild: unsupported geometry"); return SKV_ERR_UNSUPPORTED;
+  }
+  RebuildParams p{};
+  p.resident = resident; p.cnts = cnts; p.miss_slots = g->table_mode ? offsets : nullptr;
+  p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(cos_sin);
+  p.out = reinterpret_cast<__nv_bfloat16 *>(k_buf);
+  p.out_stride_bh = int64_t(g->buf_len) * g->head_dim;
+  p.out_row0 = g->sparse_start;
+  p.H = g->kv_heads; p.S = g->select; p.L = g->seq_len; p.R = g->rank;
+  p.rope = g->rope_glm ? 2 : 1;
+  p.tile_skip = 0;
+  FetchParams f{};
+  f.src = v_host; f.src_stride_bh = host_stride; f.dst = v_buf;
+  f.dst_stride_bh = int64_t(g->buf_len) * g->head_dim;
+  f.dst_base_off = int64_t(g->sparse_start) * g->head_dim;
+  f.offsets = offsets; f.resident = g->table_mode ? resident : nullptr;
+  if (vstore) f.vs = *vstore;
+  return launch_fetch_rebuild(U, SV, p, f, g->batch, as_stream(stream));
+}
 
 int skv_rebuild_keys(const skv_geom *g, const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin,
                      const int64_t *resident, const int32_t *cnts, const int32_t *offsets, skv_bf16 *k_buf, int impl,

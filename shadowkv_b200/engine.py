@@ -10,9 +10,9 @@ Two public entry points:
   the device INSIDE the replayed graph, and the attention outputs are copied back to pinned host memory
   inside the same graph.  This is the call ``bench.py`` times as ``e2e``.
 
-The graph holds, per layer: score (+ fused append) -> select -> {V miss fetch || tcgen05 K rebuild on the side
-stream} -> split-K attention, i.e. 5 kernels (7 with table_mode="reference": two hit compactions more; +1 with
-the HBM chunk store: its fill), plus one counter-advance kernel per token.  The generation offset lives on the
+The graph holds, per layer: score (+ fused append) -> select -> V miss fetch + tcgen05 K rebuild (one launch) ->
+split-K attention, i.e. 4 kernels chained by programmatic dependent launches (5 with table_mode="reference": one hit
+compaction more; +1 with the HBM chunk store: its fill), plus one counter-advance kernel per token.  The generation offset lives on the
 device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the same graph is valid for every token.
 """
 from __future__ import annotations
@@ -51,9 +51,12 @@ class DecodeStepGraph:
                           else torch.zeros(L, B, 1, Hq, D, dtype=dt)).pin_memory()
         self.h2d_bytes = (self.q_d.numel() + self.k_d.numel() + self.v_d.numel()) * 2
         self.d2h_bytes = (self.out_all if gather_heads else self.out_d).numel() * 2
-        # kernels of libshadowkv_b200.so per token: score(+append), select, fetch(V), rebuild(K), attention
-        # (+ the two hit compactions when the table keeps the reference's slot order)
-        self.launches_per_step = L * ((5 if cache.table_mode == "inplace" else 7) + (1 if cache.hbm_store_ways else 0))
+        # kernels of libshadowkv_b200.so per token: score(+append), select, fetch(V) + rebuild(K) (one launch, or two
+        # with SKV_FUSED_FETCH=0), attention (+ the hit compactions when the table keeps the reference's slot order:
+        # one launch for both buffers in front of the fused launch, one per buffer otherwise)
+        fused = cache.fused_fetch_rebuild and cache.rebuild_impl == 0
+        per_layer = (4 if fused else 5) + (0 if cache.table_mode == "inplace" else (1 if fused else 2))
+        self.launches_per_step = L * (per_layer + (1 if cache.hbm_store_ways else 0))
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0

@@ -17,14 +17,16 @@ get_key_cache    (:1108-1176)   ``skv_rebuild_keys`` (tcgen05, RoPE in the epilo
 (base.py:341 flash-attn call)   ``attention`` / ``shadowkv_b200.attention.flash_attn_with_kvcache``
 =============================  =====================================================================
 
-``decode_layer`` runs the whole per-layer step (score+append -> select -> {V fetch || K rebuild on the side
-stream} -> attention).  The prefill-side methods (``get_svd``, ``prefill_kv_cache``) build the state with torch
+``decode_layer`` runs the whole per-layer step: score+append -> select -> V fetch + K rebuild of the missed chunks
+(ONE launch, ``skv_fetch_and_rebuild``; ``SKV_FUSED_FETCH=0``: two launches on two streams as in base.py:326-338)
+-> attention, every kernel launched programmatically behind its single predecessor.  The prefill-side methods (``get_svd``, ``prefill_kv_cache``) build the state with torch
 ops; they are outside the hot path and kept only so the class is usable end to end.
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -121,6 +123,11 @@ class ShadowKVCache_CPU:
         self._sel_ws = None
         self._attn_ws = None
         self.rebuild_impl = 0      # 0: tcgen05 (product); 1: SIMT cross-check (tests only)
+        # decode_layer: V fetch and K rebuild of the missed chunks as ONE launch (default) or as two launches on two
+        # streams like the reference's choreography (SKV_FUSED_FETCH=0; kept for A/B measurements)
+        self.fused_fetch_rebuild = os.environ.get("SKV_FUSED_FETCH", "1") != "0"
+        self.programmatic_attention = os.environ.get("SKV_ATTN_PDL", "1") != "0"     # A/B knob, single-launch path only
+        self._side_used = False
         self.rope_glm = False
         # device-side copies of the generation counters, so a captured CUDA graph of the step can be replayed
         # while the cache grows (decode_layer(..., device_counters=True) + advance_device_counters())
@@ -447,7 +454,9 @@ class ShadowKVCache_CPU:
     def join_side_streams(self):
         """Make the current stream wait for everything queued on the copy stream (the store fill of the last
         layer runs behind the attention that did not have to wait for it)."""
-        torch.cuda.current_stream().wait_stream(self.copy_stream)
+        if self._side_used:                   # nothing to join when every layer took the single-launch path
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
+            self._side_used = False
 
     def get_key_cache(self, layer_idx, position_ids, rope_func, cos_sin_cache):
         """Compact the hit chunks, rebuild + RoPE the missed ones from U.SV (kv_cache.py:1108-1176).
@@ -465,8 +474,27 @@ class ShadowKVCache_CPU:
               "rebuild_keys")
         return kb[:, :, :self._view_len(layer_idx)]
 
-    def attention(self, layer_idx, query_states, kv_len=None, out=None, device_counters=False):
-        """softmax(q K^T / sqrt(D)) V over rows [0, kv_len) of this layer's buffers (base.py:341)."""
+    def fetch_and_rebuild(self, layer_idx, cos_sin_cache):
+        """get_value_cache + get_key_cache of one layer in ONE launch (the V fetch and the K rebuild of the missed
+        chunks run in different CTAs of the same grid), so the attention behind it has a single predecessor."""
+        g = self._geometry(cos_sin_cache)
+        st = _cs()
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
+        kb, vb = self.k_cache_buffer[layer_idx], self.v_cache_buffer[layer_idx]
+        if not g.table_mode:
+            check(lib.skv_compact_hits(C.byref(g), kb.data_ptr(), vb.data_ptr(), self.offsets.data_ptr(),
+                                       self.cnts.data_ptr(), st), "compact_hits(K,V)")
+        vh = self.v_cache_cpu[layer_idx]
+        vs = self._vstore(layer_idx)
+        check(lib.skv_fetch_and_rebuild(C.byref(g), vh.data_ptr(), vh.stride(1), vb.data_ptr(),
+                                        self.U[layer_idx].data_ptr(), self.SV[layer_idx].data_ptr(),
+                                        cos_sin_cache.data_ptr(), kb.data_ptr(), self.position_ids[layer_idx].data_ptr(),
+                                        self.cnts.data_ptr(), self.offsets.data_ptr(),
+                                        C.byref(vs) if vs is not None else None, st), "fetch_and_rebuild")
+
+    def attention(self, layer_idx, query_states, kv_len=None, out=None, device_counters=False, programmatic=False):
+        """softmax(q K^T / sqrt(D)) V over rows [0, kv_len) of this layer's buffers (base.py:341).
+        programmatic=True: programmatic dependent launch behind the single kernel that precedes it in the stream."""
         g = self._geometry()
         if device_counters:
             kv_len = self.buf_len                    # sizes the grid; the kernel reads the real length
@@ -477,10 +505,11 @@ class ShadowKVCache_CPU:
         if out is None:
             out = torch.empty(B, 1, Hq, self.head_dim, dtype=self.dtype, device=self.device)
         kb, vb = self.k_cache_buffer[layer_idx], self.v_cache_buffer[layer_idx]
-        check(lib.skv_attention_decode(q.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), B,
-                                       g.kv_heads, g.q_groups, g.head_dim, kv_len, kb.stride(0), kb.stride(1),
-                                       kb.stride(2), 1.0 / math.sqrt(self.head_dim), 0, self._attn_ws.data_ptr(),
-                                       self.kv_len_dev.data_ptr() if device_counters else 0, _cs()),
+        check(lib.skv_attention_decode_ex(q.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), B,
+                                          g.kv_heads, g.q_groups, g.head_dim, kv_len, kb.stride(0), kb.stride(1),
+                                          kb.stride(2), 1.0 / math.sqrt(self.head_dim), 0, self._attn_ws.data_ptr(),
+                                          self.kv_len_dev.data_ptr() if device_counters else 0,
+                                          1 if programmatic else 0, _cs()),
               "attention_decode")
         return out
 
@@ -517,26 +546,38 @@ class ShadowKVCache_CPU:
         # (programmatic launch: no launch gap); the short K rebuild runs beside it on the side stream.  base.py's
         # choreography (:326-338) has the two swapped, which only matters for who pays the fork/join.
         cur, side = torch.cuda.current_stream(), self.copy_stream
-        if self.hbm_store_ways and self.num_layers == 1 and not torch.cuda.is_current_stream_capturing():
-            # a single-layer cache driven eagerly: the store fill of the previous token (side stream) must be done
-            # before this token's fetch reads the store; with more layers, or inside a replayed graph, the joins
-            # below and the graph boundary already order them
+        if self.hbm_store_ways and not torch.cuda.is_current_stream_capturing() and \
+                (self.num_layers == 1 or self.fused_fetch_rebuild):
+            # driven eagerly, the store fill of this layer's previous token (side stream) must be done before this
+            # token's fetch reads the store.  With two streams and more than one layer the fork / join below already
+            # orders them, and so does the graph boundary of a replayed graph.
             cur.wait_stream(side)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
-            self._k_done.record(side)
-        self.get_value_cache(layer_idx, pid)
+        if self.fused_fetch_rebuild and self.rebuild_impl == 0:
+            # one launch for both transfers of the missed chunks: select -> fetch+rebuild -> attention is a chain of
+            # single predecessors, each launched programmatically (no fork / join, no launch gap before the attention)
+            self.fetch_and_rebuild(layer_idx, cos_sin_cache)
+            single_predecessor = self.programmatic_attention
+        else:
+            side.wait_stream(cur)
+            self._side_used = True
+            with torch.cuda.stream(side):
+                self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
+                self._k_done.record(side)
+            self.get_value_cache(layer_idx, pid)
+            single_predecessor = False
         if self.hbm_store_ways:               # the store fill runs behind the attention, on the side stream
+            self._side_used = True
             self._fetch_done.record(cur)
             with torch.cuda.stream(side):
                 side.wait_event(self._fetch_done)
                 self.fill_value_store(layer_idx)
-        cur.wait_event(self._k_done)
+        if not single_predecessor:
+            cur.wait_event(self._k_done)
         if before_attention is not None:
             before_attention()
+            single_predecessor = False        # the hook may have joined other streams in front of the attention
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
-        return self.attention(layer_idx, query_states, kv_len, out, device_counters)
+        return self.attention(layer_idx, query_states, kv_len, out, device_counters, programmatic=single_predecessor)
 
 
 class ShadowKVCache(ShadowKVCache_CPU):

@@ -74,6 +74,14 @@ def test_fused_entry_points_reject_bad_arguments_without_a_gpu():
     vs = _lib.VStore(tags=1, data=1, pcie_count=0, ways=100)
     assert lib.skv_fetch_misses(C.byref(g), 1, 0, 1, 1, 1, 1, C.byref(vs), 0) == -2  # ways not a power of two
     assert lib.skv_select_workspace_bytes(C.byref(g)) > 8 * 4 * 15560 * 2
+    # the single-launch V fetch + K rebuild and the attention variant with launch flags
+    assert lib.skv_fetch_and_rebuild(C.byref(g), 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, None, 0) == -2      # null offsets
+    assert lib.skv_fetch_and_rebuild(C.byref(bad_s), 1, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, 0) == -1  # select 200
+    assert lib.skv_fetch_and_rebuild(C.byref(g), 1, 0, 1, 1, 1, 1, 1, 1, 1, 1, C.byref(vs), 0) == -2
+    bad_r = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=128, chunk=8, select=256, n_landmarks=15560, rank=164,
+                      seq_len=124928, buf_len=2592, sparse_start=448)
+    assert lib.skv_fetch_and_rebuild(C.byref(bad_r), 1, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, 0) == -1  # rank % 8
+    assert lib.skv_attention_decode_ex(1, 1, 1, 1, 1, 8, 4, 64, 100, 8, 8, 8, 0.1, 0, 1, 0, 1, 0) == -1
 
 
 def test_dense_entry_points_reject_bad_arguments_without_a_gpu():

@@ -107,6 +107,40 @@ def test_decode_layer_fused_equals_stepwise(cuda):
             assert_close_bf16(o1, o2, max_abs=4e-3, what="fused vs stepwise")
 
 
+@pytest.mark.parametrize("model,table_mode,ways", [("llama-3.1-8b", "inplace", 0), ("llama-3.1-8b", "reference", 0),
+                                                   ("glm-4-9b-1m", "inplace", 0), ("llama-3.1-8b", "inplace", 128)])
+def test_single_launch_fetch_and_rebuild_equals_the_two_stream_path(cuda, model, table_mode, ways):
+    """skv_fetch_and_rebuild (V fetch and K rebuild of the missed chunks as CTAs of ONE grid, attention launched
+    programmatically behind it) against the two launches on two streams it replaces: same chunk table, same K / V
+    bytes, same attention output, bit for bit, in both table modes and with the HBM chunk store."""
+    B = 2
+    shape, c1, _, _, cs, lay = _build(cuda, model, B, 8192, 1024, 2, table_mode=table_mode)
+    _, c2, _, _, _, _ = _build(cuda, model, B, 8192, 1024, 2, table_mode=table_mode)
+    c1.fused_fetch_rebuild, c2.fused_fetch_rebuild = True, False
+    if ways:
+        c1.enable_hbm_store(ways)
+        c2.enable_hbm_store(ways)
+    d_cs = cs.to(cuda)
+    base = None
+    for step in range(6):
+        for l in range(2):
+            q, kn, vn = synth.queries(shape, B, seed=13 * step + l, base=base, noise=0.4)
+            base = q if base is None else base
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            o1 = c1.decode_layer(l, dq, dk, dv, d_cs)
+            o2 = c2.decode_layer(l, dq, dk, dv, d_cs)
+            torch.cuda.synchronize()
+            assert 0 < int(c1.cnts.sum()) < B * shape.num_key_value_heads * lay.select or step == 0
+            assert torch.equal(c1.cnts, c2.cnts)
+            assert torch.equal(c1.position_ids[l], c2.position_ids[l])
+            assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l]), f"K bytes differ at step {step} layer {l}"
+            assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l]), f"V bytes differ at step {step} layer {l}"
+            assert torch.equal(o1, o2)
+    if ways:
+        assert torch.equal(c1.vstore_tags, c2.vstore_tags)
+        assert int(c1.pcie_count.sum()) == int(c2.pcie_count.sum()) > 0
+
+
 def test_uncached_variant_token_ids(cuda):
     """ShadowKVCache (batch 1, no chunk cache; reference kv_cache.py:421-470) returns token-level ids and
     rebuilds every chunk each step."""

@@ -62,6 +62,7 @@ def main():
                     c.get_value_cache(l, pid)
             else:
                 side.wait_stream(cur)
+                c._side_used = True
                 with torch.cuda.stream(side):
                     if "rebuild" not in skip:
                         c.get_key_cache(l, pid, None, cs)
