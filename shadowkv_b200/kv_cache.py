@@ -542,42 +542,45 @@ class ShadowKVCache_CPU:
         if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += 1
             self.gen_offset += 1
-        # The V fetch is the long pole (PCIe), so it stays on the current stream right behind the selection kernel
-        # (programmatic launch: no launch gap); the short K rebuild runs beside it on the side stream.  base.py's
-        # choreography (:326-338) has the two swapped, which only matters for who pays the fork/join.
         cur, side = torch.cuda.current_stream(), self.copy_stream
-        if self.hbm_store_ways and not torch.cuda.is_current_stream_capturing() and \
-                (self.num_layers == 1 or self.fused_fetch_rebuild):
+        hooks = after_select is not None or before_attention is not None
+        single = self.fused_fetch_rebuild and self.rebuild_impl == 0 and not hooks
+        if self.hbm_store_ways and not torch.cuda.is_current_stream_capturing() and (self.num_layers == 1 or single):
             # driven eagerly, the store fill of this layer's previous token (side stream) must be done before this
             # token's fetch reads the store.  With two streams and more than one layer the fork / join below already
             # orders them, and so does the graph boundary of a replayed graph.
             cur.wait_stream(side)
-        if self.fused_fetch_rebuild and self.rebuild_impl == 0:
+        if single:
             # one launch for both transfers of the missed chunks: select -> fetch+rebuild -> attention is a chain of
             # single predecessors, each launched programmatically (no fork / join, no launch gap before the attention)
             self.fetch_and_rebuild(layer_idx, cos_sin_cache)
-            single_predecessor = self.programmatic_attention
         else:
+            # two launches on two streams (the reference's choreography).  Also what a caller with hooks gets: it runs
+            # its own kernels in the PCIe window and joins them in front of the attention, so the attention has several
+            # predecessors anyway, and the rebuild CTAs (96 KiB of shared memory each) leave their SMs after ~9 us
+            # instead of staying for the whole transfer as the CTAs of the single launch do.  The V fetch is the long
+            # pole (PCIe), so it stays on the current stream right behind the selection kernel; the short K rebuild runs
+            # beside it on the side stream (base.py:326-338 has the two swapped, which only matters for who pays the
+            # fork / join)
             side.wait_stream(cur)
             self._side_used = True
             with torch.cuda.stream(side):
                 self.get_key_cache(layer_idx, pid, None, cos_sin_cache)
                 self._k_done.record(side)
             self.get_value_cache(layer_idx, pid)
-            single_predecessor = False
         if self.hbm_store_ways:               # the store fill runs behind the attention, on the side stream
             self._side_used = True
             self._fetch_done.record(cur)
             with torch.cuda.stream(side):
                 side.wait_event(self._fetch_done)
                 self.fill_value_store(layer_idx)
-        if not single_predecessor:
+        if not single:
             cur.wait_event(self._k_done)
         if before_attention is not None:
             before_attention()
-            single_predecessor = False        # the hook may have joined other streams in front of the attention
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
-        return self.attention(layer_idx, query_states, kv_len, out, device_counters, programmatic=single_predecessor)
+        return self.attention(layer_idx, query_states, kv_len, out, device_counters,
+                              programmatic=single and self.programmatic_attention)
 
 
 class ShadowKVCache(ShadowKVCache_CPU):
