@@ -18,7 +18,8 @@
 namespace skv {
 
 constexpr int kSmTileRows = 128;                 // landmarks per tile = UMMA M
-constexpr int kSmStages = 3;                     // 3 x 32 KiB ring per CTA
+constexpr int kSmMaxStages = 3;                  // ring depth is a template parameter: 3 x 32 KiB, two CTAs per SM
+                                                 // (default) or 2 x 32 KiB, three CTAs per SM (SKV_SCORE_STAGES=2)
 constexpr int kSmSlabBytes = kSmTileRows * 128;  // one 64-column (128 B) swizzle slab of a tile
 constexpr int kSmTileBytes = 2 * kSmSlabBytes;   // 32 KiB
 constexpr int kSmQSlabBytes = 16 * 128;          // B operand: 16 rows (heads, zero padded) x 64 columns
@@ -36,7 +37,8 @@ struct ScoreMmaParams {
   int64_t buf_rows;
 };
 
-__global__ void __launch_bounds__(kSmThreads, 2)
+template <int kSmStages, int kCtasPerSm>
+__global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
     score_tcgen05_kernel(const __grid_constant__ CUtensorMap map_lm, ScoreMmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sA = smem;                                          // kSmStages x 32 KiB
@@ -222,19 +224,26 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   p.q = q; p.scores = scores; p.part_max = pmax; p.part_sum = psum;
   p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
   if (append) p.ap = *append;
-  // two CTAs per SM; every CTA of a row strides over that row's tiles
-  static const int target = [] { const char *e = getenv("SKV_SCORE_CTAS"); return (e && *e) ? atoi(e) : 2 * kNumSMs; }();
+  // two (or three) CTAs per SM; every CTA of a row strides over that row's tiles
+  static const int stages = [] { const char *e = getenv("SKV_SCORE_STAGES"); return (e && e[0] == '2') ? 2 : 3; }();
+  static const int target = [] {
+    const char *e = getenv("SKV_SCORE_CTAS");
+    return (e && *e) ? atoi(e) : (stages == 2 ? 3 : 2) * kNumSMs;
+  }();
   int cpr = (target + BH - 1) / BH;
   if (cpr > T) cpr = T;
   if (cpr < 1) cpr = 1;
   p.ctas_per_row = cpr;
-  const int smem = kSmStages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmStages + 4) * 8 + 8 + 2 * 4 * 32 * 4 + 64;
+  const int smem = stages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmMaxStages + 4) * 8 + 8 + 2 * 4 * 32 * 4 + 64;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(score_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(score_tcgen05_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(score_tcgen05_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr = true;
   }
-  cudaError_t e = launch_kernel(score_tcgen05_kernel, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p);
+  cudaError_t e = stages == 2
+      ? launch_kernel(score_tcgen05_kernel<2, 3>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p)
+      : launch_kernel(score_tcgen05_kernel<3, 2>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p);
   if (e != cudaSuccess) { set_error("score_tcgen05_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("score_tcgen05_kernel");
 }
