@@ -107,15 +107,19 @@ def test_decode_layer_fused_equals_stepwise(cuda):
             assert_close_bf16(o1, o2, max_abs=4e-3, what="fused vs stepwise")
 
 
-@pytest.mark.parametrize("model,table_mode,ways", [("llama-3.1-8b", "inplace", 0), ("llama-3.1-8b", "reference", 0),
-                                                   ("glm-4-9b-1m", "inplace", 0), ("llama-3.1-8b", "inplace", 128)])
-def test_single_launch_fetch_and_rebuild_equals_the_two_stream_path(cuda, model, table_mode, ways):
+@pytest.mark.parametrize("model,table_mode,ways,prompt_len,budget", [
+    ("llama-3.1-8b", "inplace", 0, 8192, 1024), ("llama-3.1-8b", "reference", 0, 8192, 1024),
+    ("glm-4-9b-1m", "inplace", 0, 8192, 1024), ("llama-3.1-8b", "inplace", 128, 8192, 1024),
+    ("llama-3.1-8b", "inplace", 0, 32768, 8192),        # S = 1024 chunks: the largest table the kernels take
+    ("yi-9b-200k", "reference", 0, 16384, 4096)])       # S = 512, 4 kv heads x 8 query heads
+def test_single_launch_fetch_and_rebuild_equals_the_two_stream_path(cuda, model, table_mode, ways, prompt_len, budget):
     """skv_fetch_and_rebuild (V fetch and K rebuild of the missed chunks as CTAs of ONE grid, attention launched
     programmatically behind it) against the two launches on two streams it replaces: same chunk table, same K / V
     bytes, same attention output, bit for bit, in both table modes and with the HBM chunk store."""
     B = 2
-    shape, c1, _, _, cs, lay = _build(cuda, model, B, 8192, 1024, 2, table_mode=table_mode)
-    _, c2, _, _, _, _ = _build(cuda, model, B, 8192, 1024, 2, table_mode=table_mode)
+    shape, c1, _, _, cs, lay = _build(cuda, model, B, prompt_len, budget, 2, table_mode=table_mode)
+    _, c2, _, _, _, _ = _build(cuda, model, B, prompt_len, budget, 2, table_mode=table_mode)
+    assert lay.select == budget // 8
     c1.fused_fetch_rebuild, c2.fused_fetch_rebuild = True, False
     if ways:
         c1.enable_hbm_store(ways)
