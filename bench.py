@@ -12,9 +12,9 @@ is outside this path and is NOT in the timed region -- 
 
   value  : tokens/s with the per-token inputs (q, k_new, v_new of every layer) already resident in HBM,
            all layers replayed as one CUDA graph, timed with CUDA events on the launching stream.
-  e2e    : the same tokens/s through the public host API (DecodeStepGraph.step_host): HOST tensors in, pinned
-           staging, H2D inside the timed region, attention outputs of every layer copied back D2H, one host
-           synchronisation per token.
+  e2e    : the same tokens/s through the public host API (DecodeStepGraph.step_host): HOST tensors in (pinned host
+           memory, copied to the device inside the timed region every step), attention outputs of every layer copied
+           back D2H, one host synchronisation per token.
   roofline : the landmark-scoring kernel (the dominant HBM kernel), timed alone with CUDA events, cycling through
            the landmark matrices of all layers (1 GB > L2) -- algorithmic bytes H*N*D*2 (+q) per (b) launch.
   cpu_baseline : the oracle's restatement of the reference PyTorch path (kv_cache.py:421-470) on the host cores,
@@ -313,7 +313,7 @@ def run_ours(args, rank, world, local_rank, n_gpus):
         return q, k, v
 
     dev_inputs = [inputs(t) for t in range(total)]
-    host_inputs = [tuple(x.cpu() for x in dev_inputs[t]) for t in range(total)]
+    host_inputs = [tuple(x.cpu().pin_memory() for x in dev_inputs[t]) for t in range(total)]    # pinned host memory
 
     def barrier():
         torch.cuda.synchronize()

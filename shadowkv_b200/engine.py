@@ -6,9 +6,10 @@ Two public entry points:
 
 * ``step_device(q, k, v)``  -- inputs already on the GPU ([layers,B,Hq,1,D] / [layers,B,H,1,D] bf16);
   returns the device tensor of attention outputs [layers,B,1,Hq,D].
-* ``step_host(q, k, v)``    -- inputs are HOST tensors; they are staged through pinned memory, copied to
-  the device INSIDE the replayed graph, and the attention outputs are copied back to pinned host memory
-  inside the same graph.  This is the call ``bench.py`` times as ``e2e``.
+* ``step_host(q, k, v)``    -- inputs are HOST tensors; pinned tensors are copied to the device as they are,
+  pageable ones are staged through the runner's pinned buffers first; the graph is replayed behind the three
+  copies and ends with the copy of the attention outputs back to pinned host memory.  This is the call
+  ``bench.py`` times as ``e2e``.
 
 The graph holds, per layer: score (+ fused append) -> select -> V miss fetch + tcgen05 K rebuild (one launch) ->
 split-K attention, i.e. 4 kernels chained by programmatic dependent launches (5 with table_mode="reference": one hit
@@ -68,12 +69,14 @@ class DecodeStepGraph:
         return self.cache.cnts_all
 
     # ----------------------------------------------------------------------------------------------
+    def _h2d(self, q=None, k=None, v=None):
+        """Host -> device copies of one token's inputs on the current stream (sources must be pinned)."""
+        self.q_d.copy_(self.q_h if q is None else q, non_blocking=True)
+        self.k_d.copy_(self.k_h if k is None else k, non_blocking=True)
+        self.v_d.copy_(self.v_h if v is None else v, non_blocking=True)
+
     def _body(self):
         c = self.cache
-        if self.host_io:
-            self.q_d.copy_(self.q_h, non_blocking=True)
-            self.k_d.copy_(self.k_h, non_blocking=True)
-            self.v_d.copy_(self.v_h, non_blocking=True)
         for l in range(c.num_layers):
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
                            device_counters=True)
@@ -91,6 +94,8 @@ class DecodeStepGraph:
         c.reset_device_counters()
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
+                if self.host_io:
+                    self._h2d()                  # the warm-up token's inputs are what the caller left in q_h / k_h / v_h
                 self._body()
                 c.note_replayed_steps(1)
         self.stream.synchronize()
@@ -126,11 +131,14 @@ class DecodeStepGraph:
         """Host tensors in, pinned host tensor out; synchronises on the result (a user needs it to sample)."""
         if not self.host_io:
             raise RuntimeError("runner was built with host_io=False")
-        self.q_h.copy_(q)
-        self.k_h.copy_(k)
-        self.v_h.copy_(v)
+        srcs = []
+        for t, stage in ((q, self.q_h), (k, self.k_h), (v, self.v_h)):
+            direct = t.dtype == stage.dtype and t.shape == stage.shape and t.is_contiguous() and t.is_pinned()
+            srcs.append(t if direct else stage.copy_(t))      # pageable / strided inputs go through the pinned stage
+        with torch.cuda.stream(self.stream):
+            self._h2d(*srcs)
         self.replay()
-        self.stream.synchronize()
+        self.stream.synchronize()                 # also covers the reads of the caller's pinned tensors
         return self.out_h
 
     def rewind_async(self, gen_offset: int = 0):
