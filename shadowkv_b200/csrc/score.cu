@@ -325,6 +325,15 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   pdl_wait();                                   // scores, partials and the chunk table are the predecessors' outputs
   int old_id = 0;
   if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
+  // the scores of this thread's first 8 landmarks for the first four heads, requested together with the partial
+  // statistics below: one L2 round trip instead of two in front of the first histogram pass
+  const skv_bf16 *sc = scores + size_t(bh) * G * ldn;
+  int4 w0[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+  if (tid * 8 < count) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < G) w0[g] = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n_begin + tid * 8);
+  }
 
   // 0. final softmax statistics per head (every CTA redundantly: G x T floats)
   for (int g = warp; g < G; g += kWarps) {
@@ -337,7 +346,6 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
 
   // 1. p = bf16(exp(s - max) * inv); key = max over heads (bf16 bits are monotone for p >= 0);
   //    first-level histogram on the high byte.  8 consecutive landmarks per thread: 16-byte loads.
-  const skv_bf16 *sc = scores + size_t(bh) * G * ldn;
   int *my_h1 = whist1 + warp * 256, *my_h2 = whist2 + warp * 256;
   for (int base = 0; base < count; base += kThreads * 8) {
     const int off = base + tid * 8;
@@ -345,9 +353,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
     uint16_t best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (on) {
       const int n = n_begin + off;
-#pragma unroll 4
-      for (int g = 0; g < G; ++g) {
-        const int4 w = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n);
+      auto fold = [&](const int4 &w, const int g) {
         const uint32_t u[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
         const float m = s_m[g], inv = s_inv[g];
 #pragma unroll
@@ -357,7 +363,12 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
           best[2 * e] = b0 > best[2 * e] ? b0 : best[2 * e];
           best[2 * e + 1] = b1 > best[2 * e + 1] ? b1 : best[2 * e + 1];
         }
-      }
+      };
+#pragma unroll
+      for (int g = 0; g < 4; ++g)                          // the first round's loads are already in registers
+        if (g < G) fold(base == 0 ? w0[g] : *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n), g);
+#pragma unroll 4
+      for (int g = 4; g < G; ++g) fold(*reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n), g);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         if (off + e >= count) best[e] = 0;                    // ragged tail: never selected (p > 0 for real keys)

@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
       if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
     }
   }
+  // TMEM does not depend on the predecessor either (attention and selection hold none; a rebuild CTA that is still
+  // resident keeps 128 of the 512 columns)
+  if (warp == 1) tcgen05_alloc(tmem_slot, 32);
   // everything below touches data of the predecessor (q, the K/V buffers, the score scratch)
   pdl_wait();
 
@@ -95,7 +98,6 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
     *reinterpret_cast<int4 *>(sQ + slab * kSmQSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
   }
   fence_proxy_async_smem();
-  if (warp == 1) tcgen05_alloc(tmem_slot, 32);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
