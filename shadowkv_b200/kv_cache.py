@@ -38,6 +38,21 @@ def _cs() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def hbm_store_ways_for(free_bytes: int, layers: int, rows: int, chunks_per_row: int, fraction: float = 0.5,
+                       chunk_bytes: int = 2048) -> int:
+    """Ways per (layer, b, h) of the HBM chunk store: the largest power of two whose store (2 KiB of V + a 4-byte tag
+    per way) fits in `fraction` of `free_bytes`, capped at the first power of two that holds every chunk of a row
+    (a direct-mapped store of that size never evicts).  0 when not even 128 ways fit."""
+    budget = int(free_bytes * fraction) // max(1, layers * rows * (chunk_bytes + 4))
+    cap = 1 << max(0, (max(1, chunks_per_row) - 1).bit_length())
+    ways = 128
+    if budget < ways:
+        return 0
+    while ways * 2 <= budget and ways * 2 <= cap:
+        ways *= 2
+    return min(ways, cap)
+
+
 class ShadowKVCache_CPU:
     """Batched ShadowKV cache: V chunked in pinned host memory, sparse K/V ring on the GPU, low-rank
     K factors and landmarks on the GPU after ``H2D``.  Reference: models/kv_cache.py:509-1319."""
@@ -419,9 +434,16 @@ class ShadowKVCache_CPU:
                                    C.byref(vs) if vs is not None else None, st), "fetch_misses")
         return vb[:, :, :self._view_len(layer_idx)]
 
-    def enable_hbm_store(self, ways: int):
+    def enable_hbm_store(self, ways, fraction: float = 0.5):
         """(Re)allocate the HBM chunk store with `ways` ways per (layer, b, h); 0 removes it.  Any captured
-        CUDA graph of the step must be re-captured afterwards."""
+        CUDA graph of the step must be re-captured afterwards.  ways="auto": the largest power of two that fits in
+        `fraction` of the HBM that is free right now (`hbm_store_ways_for`)."""
+        if ways == "auto":
+            self.vstore_tags = self.vstore_data = None          # what an earlier store held counts as free
+            free, _ = torch.cuda.mem_get_info(self.device)
+            ways = hbm_store_ways_for(free, self.num_layers, self.batch_size * self.num_key_value_heads,
+                                      chunks_per_row=self.max_length // self.chunk_size, fraction=fraction,
+                                      chunk_bytes=self.head_dim * self.chunk_size * 2)
         if ways & (ways - 1):
             raise ValueError("ways must be 0 or a power of two")
         self.hbm_store_ways = int(ways)

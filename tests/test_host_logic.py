@@ -56,3 +56,17 @@ def test_sampling_mirrors_follow_the_reference_semantics():
     g = torch.manual_seed(0)
     tok = T.sample_token(logits.clone(), temperature=0.7, top_k=2, top_p=-1)
     assert tok.shape == (2, 1) and int(tok[0]) in (1, 2) and int(tok[1]) in (2, 4)
+
+
+def test_hbm_store_sizing():
+    """enable_hbm_store("auto"): ways from the free HBM (pure arithmetic, no GPU needed)."""
+    from shadowkv_b200.kv_cache import hbm_store_ways_for
+    per_way = 2048 + 4
+    # Llama-3.1-8B, 122K, batch 1: 32 layers x 8 rows; 100 GB free, half of it for the store
+    w = hbm_store_ways_for(100 << 30, 32, 8, 15616)
+    assert w == 16384 and w * 32 * 8 * per_way <= 50 << 30          # capped: 16384 ways hold all 15616 chunks of a row
+    # batch 32 of the same shape: the budget decides
+    w = hbm_store_ways_for(100 << 30, 32, 8 * 32, 15616)
+    assert w & (w - 1) == 0 and w * 32 * 256 * per_way <= 50 << 30 < 2 * w * 32 * 256 * per_way
+    assert hbm_store_ways_for(1 << 20, 32, 8, 15616) == 0               # nothing fits
+    assert hbm_store_ways_for(1 << 40, 1, 1, 100) == 128                # never fewer than the kernels' smallest table
