@@ -176,7 +176,15 @@ typedef struct skv_geom {
   int32_t cos_sin_rows; /* rows of the cos_sin table           */
   int32_t table_mode;   /* 0: reference slot order (hits compacted to the front, needs skv_compact_hits);
                          * 1: in-place table (hits keep their slots; offsets[i] = slot of the i-th miss) */
+  int32_t flags;        /* SKV_GEOM_* bits                     */
 } skv_geom;
+
+/* The scoring launch is a programmatic dependent launch that streams the landmarks into shared memory BEFORE it
+ * waits for the preceding kernel of the stream.  That is only valid when `landmarks` was completely written before
+ * that preceding kernel STARTED (decode: the landmarks are static state built at prefill time).  A caller whose
+ * landmarks are produced by the preceding kernel of the same stream (prefill: skv_gather_rows -> skv_select_chunks)
+ * sets this flag; the kernel then loads nothing ahead of griddepcontrol.wait. */
+#define SKV_GEOM_DYNAMIC_LANDMARKS 1
 
 /* Optional fused append (a2) for the scoring launch: the new token's K and V rows [B,H,D] are written at
  * buffer row pos (+ *pos_dev when pos_dev != NULL) of every (b,h) by the first CTA of each row, which saves
@@ -198,7 +206,8 @@ int64_t skv_select_workspace_bytes(const skv_geom *geom);
  * skv_reorder_keys_and_compute_offsets.  q [B, H*G, D] bf16 (post-RoPE); landmarks [B,H,N,D];
  * landmark_idx [B,H,N] int64; resident [B,H,S] int64 in/out; offsets [B*H*S], cnts [B*H] out.
  * selected_out (optional, may be NULL) receives the S selected chunk ids per (b,h) in ascending
- * landmark order; score_out (optional) the bf16 max-over-groups softmax [B,H,N]; append (optional) fuses (a2). */
+ * landmark order; score_out (optional) the bf16 max-over-groups softmax [B,H,N]; append (optional) fuses (a2).
+ * Precondition on `landmarks`: see SKV_GEOM_DYNAMIC_LANDMARKS. */
 int skv_select_chunks(const skv_geom *geom, const skv_bf16 *q, const skv_bf16 *landmarks,
                       const int64_t *landmark_idx, int64_t *resident, int32_t *offsets, int32_t *cnts,
                       int64_t *selected_out, skv_bf16 *score_out, void *workspace, const skv_append *append,
@@ -371,8 +380,9 @@ typedef struct skv_dense_epilogue {
                           * projection run on the critical path and the k / v projection beside it.           */
   int32_t head_count;    /* 0: all heads from head0 on                                                       */
   int32_t kv_row;        /* with kv_stride_h != 0: k / v are APPENDED in place (update_kv_cache,              */
-  int32_t reserved2;     /* kv_cache.py:1227-1271): element [b, head, kv_row + *pos_dev, :] of the cache      */
-  int64_t kv_stride_b;   /* buffers k_out / v_out with these element strides                                  */
+  int32_t kv_rows;       /* kv_cache.py:1227-1271): element [b, head, kv_row + *pos_dev, :] of the cache      */
+  int64_t kv_stride_b;   /* buffers k_out / v_out with these element strides; kv_rows = rows of those buffers: */
+                         /* a row at or beyond kv_rows is dropped on the device, never written                 */
   int64_t kv_stride_h;
   const void *prefetch_next; /* optional hint: the weights the NEXT linear of the stream will read (16-byte aligned).   */
   int64_t prefetch_bytes;    /* Every CTA pulls its share of the first prefetch_bytes into L2 once it has issued its own

@@ -15,6 +15,12 @@ TORCH="$SITE/torch"
 PYINC="$($PY -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
 mkdir -p "$OUT/kernels"
 if [ ! -d "$REF/kernels" ]; then echo "reference not present at $REF; keeping prebuilt files" ; exit 0; fi
+# The reference's own Python for this path (models/kv_cache.py: ShadowKVCache_CPU; models/tensor_op.py: the
+# stride-marshalling wrappers), verbatim, so tests can run it UNMODIFIED on top of either native module
+# (tests/refpy.py).  oracle/_ref is git-ignored: nothing of the reference enters the history.
+mkdir -p "$OUT/models"
+cp "$REF/models/kv_cache.py" "$REF/models/tensor_op.py" "$OUT/models/"
+: > "$OUT/models/__init__.py"
 pids=()
 for f in main rope rope_new gather_copy batch_gather_gemm batch_gemm_softmax; do
   if [ "$OUT/$f.o" -nt "$REF/kernels/$f.cu" ]; then continue; fi

@@ -17,7 +17,10 @@ class Geom(C.Structure):
     """struct skv_geom (include/shadowkv_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "kv_heads", "q_groups", "head_dim", "chunk", "select", "n_landmarks", "rank", "seq_len",
-        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode")]
+        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode", "flags")]
+
+
+GEOM_DYNAMIC_LANDMARKS = 1   # SKV_GEOM_DYNAMIC_LANDMARKS
 
 
 class Append(C.Structure):
@@ -39,7 +42,7 @@ class DenseEpilogue(C.Structure):
                 ("pos_dev", C.c_void_p), ("bias", C.c_void_p),
                 ("resid", C.c_void_p), ("cos_sin", C.c_void_p), ("out", C.c_void_p), ("k_out", C.c_void_p),
                 ("v_out", C.c_void_p), ("head0", C.c_int32), ("head_count", C.c_int32), ("kv_row", C.c_int32),
-                ("reserved2", C.c_int32), ("kv_stride_b", C.c_int64), ("kv_stride_h", C.c_int64),
+                ("kv_rows", C.c_int32), ("kv_stride_b", C.c_int64), ("kv_stride_h", C.c_int64),
                 ("prefetch_next", C.c_void_p), ("prefetch_bytes", C.c_int64)]
 
 

@@ -2,6 +2,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -12,6 +15,23 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+// Opt-in for more than 48 KiB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device, so the
+// largest size already granted is remembered per (kernel, device); thread safe.
+int ensure_dynamic_smem(const void *kernel, int bytes, const char *what) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, int> granted;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("%s: cudaGetDevice: %s", what, cudaGetErrorString(e)); return int(e); }
+  std::lock_guard<std::mutex> lock(mu);
+  int &cur = granted[std::make_pair(kernel, dev)];
+  if (bytes > cur) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_error("%s: %d bytes of dynamic shared memory: %s", what, bytes, cudaGetErrorString(e)); return int(e); }
+    cur = bytes;
+  }
+  return SKV_OK;
 }
 bool pdl_enabled() {
   static const bool on = [] { const char *e = getenv("SKV_PDL"); return !(e && e[0] == '0'); }();

@@ -354,11 +354,7 @@ int launch_attention_mma(const skv_bf16 *q, const skv_bf16 *k, const skv_bf16 *v
   p.o_rows = q_groups <= 8 ? 8 : 16;
   const int smem = p.stages * kAmTileBytes + (kAmConsumers * p.o_rows * kAmOStride + kAmConsumers * kAmHeads * 2 +
                                              kAmMaxSplits * kAmHeads + kAmHeads) * 4 + 2 * kAmMaxStages * 8 + 16 + 64;
-  static int attr = 0;
-  if (smem > attr) {
-    cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = smem;
-  }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void *>(attention_mma_kernel), smem, "attention_mma_kernel")) return rc2;
   cudaError_t e = launch_kernel(attention_mma_kernel, dim3(ns, kv_heads, batch), dim3(kAmThreads), smem, st, pdl,
                                 map_k, map_v, p);
   if (e != cudaSuccess) { set_error("attention_mma_kernel: %s", cudaGetErrorString(e)); return int(e); }

@@ -81,6 +81,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 bool pdl_enabled();
 
+// Opt-in for > 48 KiB of dynamic shared memory, remembered per (kernel, device).  Returns SKV_OK or the CUDA error.
+int ensure_dynamic_smem(const void *kernel, int bytes, const char *what);
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
                                  Args... args) {

@@ -44,6 +44,7 @@ struct DenseParams {
   int q_heads, kv_heads, rope_mode, cos_sin_rows, pos;
   int head0;              // QKV_ROPE: W holds the heads [head0, head0 + T) of the fused wqkv
   int kv_row;             // QKV_ROPE with kv_stride_h != 0: k / v go to row kv_row (+ *pos_dev) of a cache buffer
+  int kv_rows;            // rows of that buffer: a row at or beyond it is dropped (as append_kv_kernel does)
   long long kv_stride_b, kv_stride_h;
   int static_w;           // W may be read before griddepcontrol.wait
   int trace_id;           // SKV_TRACE builds: launch counter
@@ -188,9 +189,10 @@ __device__ __forceinline__ void dense_epilogue(const DenseParams &p, int t, int 
       __nv_bfloat16 *dst = is_k ? p.k_out : p.v_out;
       const int head = is_k ? th - p.q_heads : th - p.q_heads - p.kv_heads;
       const long long r = (long long)p.kv_row + (p.pos_dev ? *p.pos_dev : 0);
+      const bool in_range = r >= 0 && r < p.kv_rows;       // generation region full: drop the row, never write past it
 #pragma unroll
       for (int b = 0; b < NPAD; ++b)
-        if (b < p.B) dst[b * p.kv_stride_b + head * p.kv_stride_h + r * 128 + row] = __float2bfloat16_rn(v[b]);
+        if (b < p.B && in_range) dst[b * p.kv_stride_b + head * p.kv_stride_h + r * 128 + row] = __float2bfloat16_rn(v[b]);
     }
   }
 }
@@ -633,12 +635,7 @@ static int launch_dense(const CUtensorMap &mw, const CUtensorMap &mx, DenseParam
   static int launches = 0;
   p.trace_id = launches++;
   const int smem = stages * kStageBytes + fixed;
-  static int attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(dense_streamk_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { set_error("dense_streamk_kernel: smem attribute: %s", cudaGetErrorString(e)); return int(e); }
-    attr = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(dense_streamk_kernel<NPAD>), smem, "dense_streamk_kernel")) return rc;
   cudaError_t e = launch_kernel(dense_streamk_kernel<NPAD>, dim3(ctas), dim3(kDnThreads), smem, st, /*pdl=*/true, mw, mx, p);
   if (e != cudaSuccess) { set_error("dense_streamk_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("dense_streamk_kernel");
@@ -699,6 +696,12 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
         p.T = n_heads;
         p.head0 = epi->head0;
         p.kv_row = epi->kv_row; p.kv_stride_b = epi->kv_stride_b; p.kv_stride_h = epi->kv_stride_h;
+        p.kv_rows = epi->kv_rows;
+        if (has_kv && epi->kv_stride_h != 0 && (epi->kv_rows < 1 || epi->kv_row < 0 || epi->kv_row >= epi->kv_rows)) {
+          set_error("dense_linear: in-place k / v append needs kv_rows (rows of the cache buffer) and 0 <= kv_row < kv_rows "
+                    "(got row %d of %d)", epi->kv_row, epi->kv_rows);
+          return SKV_ERR_ARGUMENT;
+        }
       }
       p.q_heads = epi->q_heads; p.kv_heads = epi->kv_heads; p.rope_mode = epi->rope_mode;
       p.cos_sin = reinterpret_cast<const __nv_bfloat16 *>(epi->cos_sin);

@@ -135,11 +135,7 @@ static int launch_compact(skv_bf16 *buf0, skv_bf16 *buf1, const int32_t *offsets
   if (!buf0 && !buf1) return SKV_OK;
   if (!buf0) { buf0 = buf1; buf1 = nullptr; }
   const int smem = kCompactPerCta * kChunkBytes + 8 + kCompactPerCta * 4 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(compact_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(compact_hits_kernel), smem, "compact_hits_kernel")) return rc;
   dim3 grid(kCompactCluster, BH, buf1 ? 2 : 1);
   compact_hits_kernel<<<grid, 128, smem, st>>>(buf0, buf1, offsets, cnts, S, stride_bh, base_off);
   return launch_status("compact_hits_kernel");

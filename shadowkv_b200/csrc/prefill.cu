@@ -203,8 +203,7 @@ int skv_select_outliers(const skv_bf16 *mincos, int rows, int chunks, int n_outl
     return SKV_ERR_UNSUPPORTED;
   }
   const int smem = (chunks * 2 + 15) / 16 * 16;
-  static int cur = 0;
-  if (smem > cur) { cudaFuncSetAttribute(outlier_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cur = smem; }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(outlier_select_kernel), smem, "outlier_select_kernel")) return rc;
   outlier_select_kernel<<<rows, kOutThreads, smem, as_stream(stream)>>>(mincos, chunks, n_outliers, outliers, rest_idx);
   return launch_status("outlier_select_kernel");
 }

@@ -484,8 +484,7 @@ static int launch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildParams p
   if (rc) return rc;
   p.U = reinterpret_cast<const __nv_bfloat16 *>(U);
   const int smem = p.n_slabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
-  static int attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(rebuild_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void *>(rebuild_tcgen05_kernel), smem, "rebuild_tcgen05_kernel")) return rc2;
   dim3 grid((p.S + kTileChunks - 1) / kTileChunks, BH);
   rebuild_tcgen05_kernel<<<grid, 128, smem, st>>>(map_sv, p);
   return launch_status("rebuild_tcgen05_kernel");
@@ -501,8 +500,7 @@ static int launch_fetch_rebuild(const skv_bf16 *U, const skv_bf16 *SV, RebuildPa
   if (rc) return rc;
   p.U = reinterpret_cast<const __nv_bfloat16 *>(U);
   const int smem = p.n_slabs * (kSlabBytesA + kSlabBytesB) + (kMaxSlabs + 1) * 8 + 8 + 2 * 16 * 4 + 64;
-  static int attr = 0;
-  if (smem > attr) { cudaFuncSetAttribute(fetch_rebuild_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = smem; }
+  if (int rc2 = ensure_dynamic_smem(reinterpret_cast<const void *>(fetch_rebuild_kernel), smem, "fetch_rebuild_kernel")) return rc2;
   static_assert(kTileChunks == 4 * kFetchPerWarp, "a CTA fetches the V chunks of the tile it rebuilds");
   const int n_tiles = (p.S + kTileChunks - 1) / kTileChunks;
   cudaError_t e = launch_kernel(fetch_rebuild_kernel, dim3(n_tiles, BH), dim3(256), smem, st, /*pdl=*/true, map_sv, p, f);

@@ -21,7 +21,7 @@ namespace skv {
 // score_mma.cu: TMA + tcgen05 scoring (product path)
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
-                          int64_t buf_rows);
+                          int64_t buf_rows, bool dynamic_landmarks);
 
 constexpr int kScoreThreads = 256;   // 8 warps
 
@@ -358,8 +358,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
         const float m = s_m[g], inv = s_inv[g];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint16_t b0 = f32_to_bf16_bits(__expf(bf16_lo(u[e]) - m) * inv);
-          const uint16_t b1 = f32_to_bf16_bits(__expf(bf16_hi(u[e]) - m) * inv);
+          // expf, not __expf: the oracle (and the tile partials of the scoring kernel) use the IEEE-accurate exponential,
+          // and a 2-ulp fp32 difference here flips bf16 roundings at the selection threshold
+          const uint16_t b0 = f32_to_bf16_bits(expf(bf16_lo(u[e]) - m) * inv);
+          const uint16_t b1 = f32_to_bf16_bits(expf(bf16_hi(u[e]) - m) * inv);
           best[2 * e] = b0 > best[2 * e] ? b0 : best[2 * e];
           best[2 * e + 1] = b1 > best[2 * e + 1] ? b1 : best[2 * e + 1];
         }
@@ -605,7 +607,7 @@ int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
   if (!simt)   // product path: TMA ring + tcgen05 (score_mma.cu); SKV_SCORE_IMPL=1 selects the SIMT cross-check
     return launch_scores_tcgen05(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                                  g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append,
-                                 g->buf_len);
+                                 g->buf_len, (g->flags & SKV_GEOM_DYNAMIC_LANDMARKS) != 0);
   return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                            g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append, g->buf_len);
 }
@@ -623,8 +625,7 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
 #define SKV_SEL_LAUNCH(SV, IP)                                                                                    \
   {                                                                                                              \
-    static int cur = 0;                                                                                          \
-    if (smem > cur) { cudaFuncSetAttribute(select_kernel<SV, IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cur = smem; } \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP>), smem, "select_kernel")) return rc; \
     cudaError_t e = launch_kernel(select_kernel<SV, IP>, dim3(kSelCluster, BH), dim3(kThreads), smem, st, true,     \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
                                   score_out, G, N, w.ldn, w.T, per);                                              \

@@ -32,6 +32,7 @@ struct ScoreMmaParams {
   skv_bf16 *scores;         // [BH, G, ldn]
   float *part_max, *part_sum;   // [BH, G, T]
   int G, N, ldn, T, ctas_per_row;
+  int dynamic_lm;           // landmarks may be the previous kernel's output: nothing is loaded ahead of griddepcontrol.wait
   float alpha;
   skv_append ap;
   int64_t buf_rows;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
     // the ring is empty: fill it right away.  The landmarks are static, so under a programmatic launch this
     // runs while the previous kernel of the stream (the previous layer's attention) is still finishing.
     const uint64_t pol = l2_policy_evict_first();            // landmarks are read once per step
-    for (int i = 0; i < kSmStages && i < n_my; ++i) {
+    for (int i = 0; i < kSmStages && i < n_my && !p.dynamic_lm; ++i) {
       const int row0 = bh * p.N + (cx + i * p.ctas_per_row) * kSmTileRows;
       mbarrier_expect_tx(&full_bar[i], kSmTileBytes);
       tma_load_2d_hint(sA + i * kSmTileBytes, &map_lm, 0, row0, &full_bar[i], pol);
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
     // ===== TMA producer =====
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
-      for (int i = kSmStages; i < n_my; ++i) {               // the first kSmStages tiles were issued during set-up
+      for (int i = p.dynamic_lm ? 0 : kSmStages; i < n_my; ++i) {   // static landmarks: the first kSmStages tiles were issued during set-up
         const int stage = i % kSmStages, ph = (i / kSmStages) & 1;
         const int tile = cx + i * p.ctas_per_row;
         mbarrier_wait(&empty_bar[stage], ph ^ 1);
@@ -218,13 +219,14 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
 
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
-                          int64_t buf_rows) {
+                          int64_t buf_rows, bool dynamic_landmarks) {
   CUtensorMap map;
   int rc = make_tensor_map_2d(&map, lm, uint64_t(BH) * N, kHeadDim, kSmTileRows, 64);
   if (rc) return rc;
   ScoreMmaParams p{};
   p.q = q; p.scores = scores; p.part_max = pmax; p.part_sum = psum;
   p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
+  p.dynamic_lm = dynamic_landmarks ? 1 : 0;
   if (append) p.ap = *append;
   // two (or three) CTAs per SM; every CTA of a row strides over that row's tiles
   static const int stages = [] { const char *e = getenv("SKV_SCORE_STAGES"); return (e && e[0] == '2') ? 2 : 3; }();
@@ -237,12 +239,9 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   if (cpr < 1) cpr = 1;
   p.ctas_per_row = cpr;
   const int smem = stages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmMaxStages + 4) * 8 + 8 + 2 * 4 * 32 * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(score_tcgen05_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(score_tcgen05_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = true;
-  }
+  if (int rc2 = ensure_dynamic_smem(stages == 2 ? reinterpret_cast<const void *>(score_tcgen05_kernel<2, 3>)
+                                                : reinterpret_cast<const void *>(score_tcgen05_kernel<3, 2>),
+                                    smem, "score_tcgen05_kernel")) return rc2;
   cudaError_t e = stages == 2
       ? launch_kernel(score_tcgen05_kernel<2, 3>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p)
       : launch_kernel(score_tcgen05_kernel<3, 2>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p);

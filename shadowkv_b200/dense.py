@@ -168,13 +168,13 @@ def linear_qkv_rope(x: torch.Tensor, wqkv: torch.Tensor, q_heads: int, kv_heads:
     q = k = v = None
     if has_q:
         q = torch.empty(B, q_heads, 1, 128, dtype=torch.bfloat16, device=dev) if q_out is None else q_out
-    kv_row = kv_sb = kv_sh = 0
+    kv_row = kv_sb = kv_sh = kv_rows = 0
     if has_kv:
         if kv_cache is not None:
             k, v, kv_row = kv_cache
             if k.dim() != 4 or k.stride(3) != 1 or k.stride(2) != 128 or k.stride() != v.stride():
                 raise ValueError("kv_cache buffers must be [B, H, rows, 128] with contiguous rows")
-            kv_sb, kv_sh = k.stride(0), k.stride(1)
+            kv_sb, kv_sh, kv_rows = k.stride(0), k.stride(1), k.shape[2]
         else:
             k = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if k_out is None else k_out
             v = torch.empty(B, kv_heads, 1, 128, dtype=torch.bfloat16, device=dev) if v_out is None else v_out
@@ -187,7 +187,7 @@ def linear_qkv_rope(x: torch.Tensor, wqkv: torch.Tensor, q_heads: int, kv_heads:
                              out=q.data_ptr() if q is not None else k.data_ptr(),
                              k_out=k.data_ptr() if k is not None else None, v_out=v.data_ptr() if v is not None else None,
                              static_weights=int(static_weights), head0=h0, head_count=cnt, kv_row=int(kv_row),
-                             kv_stride_b=kv_sb, kv_stride_h=kv_sh)
+                             kv_rows=int(kv_rows), kv_stride_b=kv_sb, kv_stride_h=kv_sh)
     _launch(x, wqkv, epi, "dense_linear_qkv_rope", prefetch)
     return q, k, v
 

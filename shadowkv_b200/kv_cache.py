@@ -317,7 +317,8 @@ class ShadowKVCache_CPU:
         # scoring + selection kernels on an empty chunk table (every selected chunk is a miss)
         g = Geom(batch=bsz, kv_heads=H, q_groups=self.num_key_value_groups, head_dim=D, chunk=C_, select=self.select_sets,
                  n_landmarks=n - n_out, rank=self.rank, seq_len=incoming, buf_len=self.buf_len,
-                 sparse_start=self.sparse_start, table_mode=1)
+                 sparse_start=self.sparse_start, table_mode=1,
+                 flags=_lib.GEOM_DYNAMIC_LANDMARKS)      # `lm` is the previous kernel's output: no early landmark loads
         ws = torch.empty(lib.skv_select_workspace_bytes(C.byref(g)), dtype=torch.uint8, device=k.device)
         q = last_query_states.reshape(bsz, H * self.num_key_value_groups, D).contiguous()
         pid = self.position_ids[layer_idx][sl]
@@ -556,6 +557,13 @@ class ShadowKVCache_CPU:
             ap = _lib.Append(k_new=kc.data_ptr(), v_new=vc.data_ptr(), k_buf=self.k_cache_buffer[layer_idx].data_ptr(),
                              v_buf=self.v_cache_buffer[layer_idx].data_ptr(),
                              pos_dev=self.gen_dev.data_ptr() if device_counters else None, pos=pos)
+        cur, side = torch.cuda.current_stream(), self.copy_stream
+        if self.hbm_store_ways and self._side_used and not torch.cuda.is_current_stream_capturing():
+            # driven eagerly, the store fill this layer queued on the side stream for the PREVIOUS token reads
+            # position_ids / offsets / cnts of this layer and writes its store: it must be complete before this token's
+            # selection rewrites those tables and before its fetch reads the store.  (In a captured graph the join at the
+            # end of the token body orders them; with several layers the fork / join of the next layer does.)
+            cur.wait_stream(side)
         pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
         if after_select is not None:
             # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
@@ -564,14 +572,8 @@ class ShadowKVCache_CPU:
         if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += 1
             self.gen_offset += 1
-        cur, side = torch.cuda.current_stream(), self.copy_stream
         hooks = after_select is not None or before_attention is not None
         single = self.fused_fetch_rebuild and self.rebuild_impl == 0 and not hooks
-        if self.hbm_store_ways and not torch.cuda.is_current_stream_capturing() and (self.num_layers == 1 or single):
-            # driven eagerly, the store fill of this layer's previous token (side stream) must be done before this
-            # token's fetch reads the store.  With two streams and more than one layer the fork / join below already
-            # orders them, and so does the graph boundary of a replayed graph.
-            cur.wait_stream(side)
         if single:
             # one launch for both transfers of the missed chunks: select -> fetch+rebuild -> attention is a chain of
             # single predecessors, each launched programmatically (no fork / join, no launch gap before the attention)

@@ -6,7 +6,7 @@ import torch
 
 from oracle import shadowkv_oracle as O
 from shadowkv_b200 import synth
-from tests.tolerances import assert_close_bf16, assert_rope_rows_close
+from tests.tolerances import MAX_SELECTION_DIFF, assert_close_bf16, assert_rope_rows_close
 
 pytestmark = pytest.mark.gpu
 
@@ -64,7 +64,7 @@ def test_decode_steps_match_oracle(cuda, model, B, prompt_len, budget):
                 for h in range(H):
                     a, bb = set(sel[b, h].tolist()), set(info["own_selected"][b, h].tolist())
                     assert len(a) == S
-                    assert len(a ^ bb) <= max(8, S // 16), f"selection differs in {len(a ^ bb)} chunks"
+                    assert len(a ^ bb) // 2 <= MAX_SELECTION_DIFF, f"selection differs in {len(a ^ bb) // 2} chunks"
             np.testing.assert_array_equal(cache.cnts.cpu().numpy(), info["cnts"])
             np.testing.assert_array_equal(cache.offsets.cpu().numpy().reshape(B * H, S), info["offsets"])
             assert torch.equal(cache.position_ids[l].cpu(), ora[l].resident)

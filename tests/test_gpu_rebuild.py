@@ -6,7 +6,7 @@ import torch
 
 from oracle import shadowkv_oracle as O
 from shadowkv_b200 import synth
-from tests.tolerances import assert_close_bf16, assert_rope_rows_close, assert_ulp_bf16
+from tests.tolerances import assert_close_bf16, assert_rope_rows_close, assert_ulp_bf16, cosine
 
 pytestmark = pytest.mark.gpu
 
@@ -50,8 +50,10 @@ def test_rebuild_keys(cuda, impl, glm, R, S):
         b, h = divmod(r, H)
         mask[b, h, ss + int(cnts[r]) * 8:ss + S * 8] = True
     assert torch.equal(got[~mask], kbuf[~mask])
-    assert_close_bf16(got[mask], want[mask], max_abs=6e-2, what="rebuilt K")       # entries up to ~4: 1 ulp = 3e-2
+    # the bound: <= 1 bf16 ulp of the pre-RoPE value, rotated (tests/tolerances.py); no fixed absolute cap, see there.
+    # north_star's cosine bar is kept on top of it
     assert_rope_rows_close(got[mask], want[mask], glm=glm, frac_exact=0.90, what="rebuilt K")
+    assert cosine(got[mask], want[mask]) > 0.9999
 
 
 def test_tcgen05_equals_simt(cuda):

@@ -12,7 +12,7 @@ import torch
 
 from oracle import shadowkv_oracle as O
 from shadowkv_b200 import synth
-from tests.tolerances import assert_ulp_bf16
+from tests.tolerances import MAX_SELECTION_DIFF, assert_ulp_bf16
 
 pytestmark = pytest.mark.gpu
 
@@ -81,6 +81,7 @@ def test_select_chunks(cuda, model, N, S):
     want_sel, want_top, want_score = O.select_chunks(soft, idx, S)
     assert_ulp_bf16(score, want_score, ulps=2, frac_exact=0.90, what="max-over-groups softmax")
     pos_of = [{int(c): i for i, c in enumerate(idx.view(B * H, N)[r].tolist())} for r in range(B * H)]
+    worst = 0
     for r in range(B * H):
         b, h = divmod(r, H)
         got_top = torch.tensor([pos_of[r][int(c)] for c in sel[b, h].tolist()])
@@ -91,15 +92,18 @@ def test_select_chunks(cuda, model, N, S):
         # 2. against the oracle's scores: differences only among near-ties of the S-th value
         a, bset = set(got_top.tolist()), set(want_top[b, h].tolist())
         kth = float(torch.sort(want_score[b, h].float(), descending=True).values[S - 1])
-        assert len(a ^ bset) <= max(8, S // 16), f"row {r}: {len(a ^ bset)} chunks differ"
-        for i in a ^ bset:
-            assert abs(float(want_score[b, h, i]) - kth) <= kth * 2 ** -6
+        worst = max(worst, len(a ^ bset) // 2)
+        assert len(a ^ bset) // 2 <= MAX_SELECTION_DIFF, f"row {r}: {len(a ^ bset) // 2} chunks differ"
+        for i in a ^ bset:          # ... and only where the oracle's score is within 1 bf16 ulp of its S-th value
+            assert abs(float(want_score[b, h, i]) - kth) <= kth * 2 ** -7
         # 3. chunk-table update is bit-exact given the kernel's selection
         nk, no, nc = O.reorder_keys_and_compute_offsets(resident.view(B * H, S)[r:r + 1].numpy(),
                                                         sel.view(B * H, S)[r:r + 1].numpy())
         np.testing.assert_array_equal(new_res.view(B * H, S)[r].numpy(), nk[0])
         np.testing.assert_array_equal(off[r].numpy(), no[0])
         assert int(cnt[r]) == int(nc[0])
+    print(f"\n[{model} N={N} S={S}] chunks selected differently from the oracle (1-ulp score differences at the S-th "
+          f"value): worst row {worst} of {S}")
 
 
 def test_select_massive_ties(cuda):

@@ -190,3 +190,44 @@ def test_cuda_rope_and_scores_and_rebuild_equal_reference(cuda):
     torch.cuda.synchronize()
     assert_ulp_bf16(scratch[:, :, ::4], _bf(g["rebuild_pre_rows"]), ulps=1, frac_exact=0.97, what="pre-RoPE K vs reference")
     assert_rope_rows_close(kc[:, :, ::4], _bf(g["rebuild_rope_rows"]), frac_exact=0.95, what="RoPE'd K vs reference")
+
+
+@needs_golden
+@pytest.mark.gpu
+def test_cuda_product_scoring_and_selection_kernels_equal_reference(cuda):
+    """The PRODUCT kernels (score_tcgen05_kernel: TMA ring + tcgen05; select_kernel), not the SIMT drop-in entry point,
+    against the reference's batch_gemm_softmax outputs: the scaled bf16 dot products D within 1 bf16 ulp, and the
+    max-over-heads bf16 softmax the selection ranks within 2 ulp of the max over the reference's Softmax rows."""
+    import ctypes as C
+    from shadowkv_b200 import _lib
+    g = _g()
+    bc, m, n, A, Bm = _score_inputs()
+    S = 256
+    geom = _lib.Geom(batch=bc, kv_heads=1, q_groups=m, head_dim=128, chunk=8, select=S, n_landmarks=n, rank=160,
+                     seq_len=n * 8, buf_len=S * 8 + 600, sparse_start=448, table_mode=1)
+    ws = torch.zeros(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    d_q, d_lm = A.to(cuda).contiguous(), Bm.to(cuda).contiguous()
+    idx = torch.arange(n, dtype=torch.int64, device=cuda).expand(bc, 1, n).contiguous()
+    res = torch.full((bc, 1, S), -1, dtype=torch.int64, device=cuda)
+    off = torch.zeros(bc * S, dtype=torch.int32, device=cuda)
+    cnt = torch.zeros(bc, dtype=torch.int32, device=cuda)
+    sel = torch.zeros(bc, 1, S, dtype=torch.int64, device=cuda)
+    score = torch.zeros(bc, 1, n, dtype=torch.bfloat16, device=cuda)
+    _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(), idx.data_ptr(), res.data_ptr(),
+                                          off.data_ptr(), cnt.data_ptr(), sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                          None, torch.cuda.current_stream().cuda_stream), "select_chunks")
+    torch.cuda.synchronize()
+    ldn = (n + 7) // 8 * 8
+    D = ws[:bc * m * ldn * 2].view(torch.bfloat16).view(bc, m, ldn)[:, :, :n]      # the workspace starts with the scores
+    assert_ulp_bf16(D, _bf(g["score_D"]), ulps=1, frac_exact=0.97, what="product scoring kernel D vs reference")
+    want_score = _bf(g["score_softmax"]).float().max(dim=1).values.to(torch.bfloat16)
+    assert_ulp_bf16(score.view(bc, n), want_score, ulps=2, frac_exact=0.90, what="selection key vs max_g reference Softmax")
+    # and the selection itself: top-S of the REFERENCE's softmax, modulo chunks within 2 ulp of its S-th value
+    key = want_score.view(torch.int16).int()
+    for b in range(bc):
+        thr = int(key[b].sort(descending=True).values[S - 1])
+        mine = set(sel[b, 0].tolist())
+        theirs = set(torch.sort(want_score[b].float(), descending=True, stable=True).indices[:S].tolist())
+        assert len(mine ^ theirs) // 2 <= 3
+        for c in mine ^ theirs:
+            assert abs(int(key[b, c]) - thr) <= 2
