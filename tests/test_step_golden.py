@@ -25,7 +25,7 @@ from tests.tolerances import assert_close_bf16, assert_rope_rows_close
 
 PATH = os.path.join(os.path.dirname(__file__), "golden", "step_golden.npz")
 needs_golden = pytest.mark.skipif(not os.path.exists(PATH), reason="step_golden.npz not generated yet")
-MAX_TIE_CHUNKS = 3
+MAX_TIE_CHUNKS = 2
 
 
 def _bf(a):
