@@ -41,6 +41,9 @@ typedef uint16_t skv_bf16;  /* raw bfloat16 bits */
 const char *skv_version(void);
 /* Last error message of the calling thread ("" if none). */
 const char *skv_last_error(void);
+/* Implementations active in this process (the product kernels, or a cross-check / A-B variant selected through an
+ * SKV_* environment variable); a string owned by the library. */
+const char *skv_active_config(void);
 
 /* ======================================================================
  * Part 1 -- the reference's 12 extension entry points
@@ -303,6 +306,26 @@ int skv_fetch_and_rebuild(const skv_geom *geom, const skv_bf16 *v_host, int64_t 
                           const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
                           const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
                           const skv_vstore *vstore, skv_stream_t stream);
+
+/* Bytes of device scratch skv_fetch_rebuild_attend needs (softmax partials of the tile and split CTAs + arrival
+ * counters).  Zero-filled ONCE by the caller; the kernel leaves its counters at zero. */
+int64_t skv_attend_workspace_bytes(int batch, int kv_heads, int q_groups);
+
+/* (a6) + (a7) + (a8) in ONE launch: everything of the decode step behind the chunk selection.  The reference joins its
+ * two streams and only then calls flash_attn_with_kvcache (models/base.py:326-341), which re-reads every rebuilt K row
+ * from HBM.  Here the CTA that rebuilds 16 missed chunks' K rows (tcgen05, RoPE in the TMEM epilogue) and fetches their V
+ * chunks also takes their softmax partial on chip, while other CTAs of the same grid attend over what is already
+ * resident (local window, outliers, chunk-cache hits, generated rows) during the PCIe transfer; the last CTA of a
+ * (b, kv head) row merges.  K / V buffers, chunk table: exactly as skv_fetch_and_rebuild leaves them; out [B, H*G, 128]:
+ * softmax(q K^T * scale) V over rows [0, kv_len) (min(kv_len, *kv_len_dev) when kv_len_dev != NULL).
+ * Requires geom->table_mode == 1 (in-place chunk table: hits keep their slots) and q_groups <= 8; `v_store` is the
+ * chunk-major V store wherever it lives (pinned host memory or HBM), store_stride = elements between (b,h) blocks.
+ * Launched programmatically behind the selection kernel (its only predecessor in `stream`). */
+int skv_fetch_rebuild_attend(const skv_geom *geom, const skv_bf16 *v_store, int64_t store_stride, skv_bf16 *v_buf,
+                             const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
+                             const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
+                             const skv_vstore *vstore, const skv_bf16 *q, skv_bf16 *out, int kv_len,
+                             const int32_t *kv_len_dev, float scale, void *workspace, skv_stream_t stream);
 
 /* ======================================================================
  * Part 3 -- prefill-side state build (reference models/kv_cache.py:788-980, ShadowKVCache_CPU.prefill_kv_cache)

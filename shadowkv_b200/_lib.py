@@ -83,6 +83,8 @@ _SIGS = {
     "skv_attention_decode": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _p],
     "skv_attention_decode_ex": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _i, _p],
     "skv_fetch_and_rebuild": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(VStore), _p],
+    "skv_fetch_rebuild_attend": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(VStore), _p, _p, _i, _p,
+                                 _f, _p, _p],
     "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
     "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "skv_argmax": [_p, _p, _i, _i, _p],
@@ -90,8 +92,8 @@ _SIGS = {
     "skv_l2_prefetch": [_p, _l, _p],
 }
 # every symbol include/shadowkv_b200.h declares (tests check the library exports all of them)
-EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_select_workspace_bytes",
-                                "skv_attention_workspace_bytes", "skv_dense_workspace_bytes",
+EXPORTS = sorted(list(_SIGS) + ["skv_version", "skv_last_error", "skv_active_config", "skv_select_workspace_bytes",
+                                "skv_attention_workspace_bytes", "skv_attend_workspace_bytes", "skv_dense_workspace_bytes",
                                 "skv_dense_partial_bytes"])
 
 for _name, _args in _SIGS.items():
@@ -100,10 +102,13 @@ for _name, _args in _SIGS.items():
     _fn.restype = C.c_int
 lib.skv_version.restype = C.c_char_p
 lib.skv_last_error.restype = C.c_char_p
+lib.skv_active_config.restype = C.c_char_p
 lib.skv_select_workspace_bytes.argtypes = [C.POINTER(Geom)]
 lib.skv_select_workspace_bytes.restype = C.c_int64
 lib.skv_attention_workspace_bytes.argtypes = [_i] * 5
 lib.skv_attention_workspace_bytes.restype = C.c_int64
+lib.skv_attend_workspace_bytes.argtypes = [_i] * 3
+lib.skv_attend_workspace_bytes.restype = C.c_int64
 lib.skv_dense_workspace_bytes.argtypes = []
 lib.skv_dense_workspace_bytes.restype = C.c_int64
 lib.skv_dense_partial_bytes.argtypes = [_i, _i, _i]
@@ -122,3 +127,8 @@ def check(rc: int, what: str) -> None:
 
 def version() -> str:
     return lib.skv_version().decode()
+
+
+def active_config() -> str:
+    """Implementations active in this process (product kernels or an SKV_* selected cross-check / A-B variant)."""
+    return lib.skv_active_config().decode()

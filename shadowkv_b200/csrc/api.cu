@@ -42,4 +42,18 @@ bool pdl_enabled() {
 extern "C" {
 const char *skv_version(void) { return "shadowkv_b200 0.2 (sm_100a; tcgen05 scoring / K rebuild / dense stream-K linears, TMA rings)"; }
 const char *skv_last_error(void) { return skv::g_err; }
+// Which implementation every stage of the decode step runs in THIS process.  The cross-check kernels that ship inside
+// the library (SIMT scoring / attention / rebuild) and the A/B knobs are selected by environment variables read here
+// and at the launch sites; a bench or test line that prints this string cannot pick one of them up silently.
+const char *skv_active_config(void) {
+  static thread_local char buf[384];
+  auto on = [](const char *name, char v) { const char *e = getenv(name); return e && e[0] == v; };
+  const char *ctas = getenv("SKV_SCORE_CTAS");
+  snprintf(buf, sizeof(buf),
+           "score=%s select=cluster8-radix rebuild=%s attention=%s attend_fusion=%s pdl=%s score_ring=%s score_ctas=%s",
+           on("SKV_SCORE_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05+TMA", on("SKV_REBUILD_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05",
+           on("SKV_ATTN_IMPL", '1') ? "SIMT(cross-check)" : "mma.sync+TMA", on("SKV_FUSED_ATTEND", '0') ? "off" : "on",
+           skv::pdl_enabled() ? "on" : "off", on("SKV_SCORE_STAGES", '2') ? "2x3" : "3x2", (ctas && *ctas) ? ctas : "default");
+  return buf;
+}
 }

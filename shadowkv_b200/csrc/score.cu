@@ -323,6 +323,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   for (int e = 0; e < 8; ++e) ids0[e] = (tid * 8 + e < count) ? static_cast<int>(lidx[tid * 8 + e]) : 0;   // map.cuh:776
   for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
   pdl_wait();                                   // scores, partials and the chunk table are the predecessors' outputs
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 21);
   int old_id = 0;
   if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
   // the scores of this thread's first 8 landmarks for the first four heads, requested together with the partial
@@ -526,6 +527,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
                                   cnts + bh);
   SKV_STAMP(bh == 0 ? rank : 999, 14);
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 22);
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

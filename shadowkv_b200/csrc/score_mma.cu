@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   const int n_my = (p.T - cx + p.ctas_per_row - 1) / p.ctas_per_row;   // tiles cx, cx + cpr, ... < T
   const int tr = bh == 0 ? cx : 999;
   SKV_STAMP(tr, 0);
+  if (threadIdx.x == 0) SKV_STAMP_NS((bh == 0 && cx == 0) ? 0 : -1, 20);
 
   pdl_launch_dependents();                                   // the selection kernel may be scheduled behind us
   if (threadIdx.x == 0) {
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   tcgen05_fence_before();
   __syncthreads();
   SKV_STAMP(tr, 15);
+  if (threadIdx.x == 0) SKV_STAMP_NS((bh == 0 && cx == 0) ? 0 : -1, 23);
   if (warp == 1) tcgen05_dealloc(tmem_base, 32);
 }
 

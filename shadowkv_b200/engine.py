@@ -57,11 +57,18 @@ class DecodeStepGraph:
         # one launch for both buffers in front of the fused launch, one per buffer otherwise)
         fused = cache.fused_fetch_rebuild and cache.rebuild_impl == 0
         per_layer = (4 if fused else 5) + (0 if cache.table_mode == "inplace" else (1 if fused else 2))
+        if fused and cache.can_fuse_attend():
+            per_layer = 3                      # score (+append), select, fetch + rebuild + attention
         self.launches_per_step = L * (per_layer + (1 if cache.hbm_store_ways else 0))
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0
         self._presets = {}
+
+    @staticmethod
+    def exchange_kind() -> str:
+        """How the kv-head split exchanges a layer's attention output (bench / DESIGN reporting)."""
+        return "NCCL all_gather_into_tensor, one node per layer inside the captured graph"
 
     @property
     def hits_d(self):

@@ -59,12 +59,17 @@ class ShadowKVCache_CPU:
 
     def __init__(self, config, batch_size: int = 1, max_length: int = 32 * 1024, device: str = "cuda:0",
                  dtype=torch.bfloat16, sparse_budget: int = 2048, chunk_size: int = 8, rank: int = 160,
-                 table_mode: str = "inplace", hbm_store_ways: int = 0) -> None:
+                 table_mode: str = "inplace", hbm_store_ways: int = 0, v_residency: str = "host") -> None:
         """table_mode: "inplace" (default; chunk-cache hits keep their slots, no compaction traffic) or
         "reference" (slot order of reference map.cuh:754-796: hits compacted to the front).
         hbm_store_ways: > 0 adds a direct-mapped HBM chunk store of that many 2 KiB ways per (layer, b, h)
         between the sparse slots and the pinned host store (power of two; 0 = the reference's behaviour: every
-        chunk that is not in a sparse slot crosses PCIe).  Results are byte-identical either way."""
+        chunk that is not in a sparse slot crosses PCIe).  Results are byte-identical either way.
+        v_residency: where the full chunk-major V store lives (reference kv_cache.py:554-563 keeps it in pinned host
+        memory, the only choice on an 80 GB part).  "host" = the reference's; "hbm" = in HBM (a 122K-token Llama-3.1-8B
+        sequence is 8.2 GB of V against 180 GB), the miss fetch is then an HBM gather; "auto" = HBM when the whole
+        store fits in `V_HBM_FRACTION` of the free HBM next to the factors and landmarks that follow, else host (and
+        `apply_residency_policy()` then sizes an HBM chunk store from what is left).  Byte-identical results."""
         if dtype != torch.bfloat16:
             raise ValueError("the sm_100a kernels compute in bf16 only")
         if table_mode not in ("inplace", "reference"):
@@ -96,7 +101,10 @@ class ShadowKVCache_CPU:
             raise ValueError("sparse_budget must be 1024, 2048, 4096 or 8192")
 
         L, B, H, D = self.num_layers, batch_size, self.num_key_value_heads, self.head_dim
-        # pinned-host chunk-major V store                      kv_cache.py:554-563
+        if v_residency not in ("host", "hbm", "auto"):
+            raise ValueError("v_residency must be 'host', 'hbm' or 'auto'")
+        self.v_residency = self._decide_v_residency(v_residency)
+        # chunk-major V store (pinned host: kv_cache.py:554-563; the attribute keeps the reference's name in HBM too)
         self.v_cache_cpu = self._alloc_v_store(L, B, H, max_length // chunk_size, D * chunk_size)
         self.buf_len = self._buffer_len()
         self.k_cache_buffer = torch.zeros(L, B, H, self.buf_len, D, dtype=dtype, device=self.device)
@@ -142,6 +150,10 @@ class ShadowKVCache_CPU:
         # streams like the reference's choreography (SKV_FUSED_FETCH=0; kept for A/B measurements)
         self.fused_fetch_rebuild = os.environ.get("SKV_FUSED_FETCH", "1") != "0"
         self.programmatic_attention = os.environ.get("SKV_ATTN_PDL", "1") != "0"     # A/B knob, single-launch path only
+        # decode_layer: V fetch + K rebuild + attention as ONE launch (skv_fetch_rebuild_attend; in-place table, G <= 8).
+        # SKV_FUSED_ATTEND=0 keeps the attention as its own launch behind skv_fetch_and_rebuild (A/B measurements)
+        self.fused_attend = os.environ.get("SKV_FUSED_ATTEND", "1") != "0"
+        self._attend_ws = None
         self._side_used = False
         self.rope_glm = False
         # device-side copies of the generation counters, so a captured CUDA graph of the step can be replayed
@@ -157,8 +169,58 @@ class ShadowKVCache_CPU:
     def _buffer_len(self) -> int:
         return self.sparse_budget + 128 + (self.outlier_chunk + self.local_chunk) * self.chunk_size   # kv_cache.py:574
 
+    V_HBM_FRACTION = 0.6      # "auto": share of the free HBM the V store + factors + landmarks may take
+
+    def state_bytes(self):
+        """(V store bytes, bytes of the factors + landmarks + K/V buffers that live in HBM in every configuration)."""
+        L, B, H, D = self.num_layers, self.batch_size, self.num_key_value_heads, self.head_dim
+        v = L * B * H * (self.max_length // self.chunk_size) * D * self.chunk_size * 2
+        n_lm = self.max_length // self.chunk_size
+        other = L * B * (self.max_length * self.rank * 2 + H * D * self.rank * 2 + H * n_lm * (D * 2 + 8)
+                         + 2 * H * self._buffer_len() * D * 2)
+        return v, other
+
+    def _decide_v_residency(self, want: str) -> str:
+        if want != "auto":
+            return want
+        free, _ = torch.cuda.mem_get_info(self.device)
+        v, other = self.state_bytes()
+        return "hbm" if v + other <= self.V_HBM_FRACTION * free else "host"
+
     def _alloc_v_store(self, *shape):
+        if self.v_residency == "hbm":
+            return torch.zeros(*shape, dtype=self.dtype, device=self.device)
         return torch.zeros(*shape, dtype=self.dtype, device="cpu", pin_memory=True)
+
+    def migrate_v_store(self, residency: str):
+        """Move the V store between pinned host memory and HBM ("host" / "hbm" / "auto"), layer by layer.  Captured CUDA
+        graphs of the step hold the old pointers and must be re-captured.  Returns the residency now in effect."""
+        target = self._decide_v_residency(residency) if residency == "auto" else residency
+        if target not in ("host", "hbm"):
+            raise ValueError("residency must be 'host', 'hbm' or 'auto'")
+        if target == self.v_residency:
+            return target
+        torch.cuda.synchronize(self.device)
+        old = self.v_cache_cpu
+        self.v_residency = target
+        new = self._alloc_v_store(*old.shape)
+        for l in range(old.shape[0]):
+            new[l].copy_(old[l])
+        torch.cuda.synchronize(self.device)
+        self.v_cache_cpu = new
+        return target
+
+    def apply_residency_policy(self, fraction: float = 0.5):
+        """The tiered policy in one call (after H2D / load_state): V store in HBM when it fits ("auto"), otherwise the
+        pinned host store with a direct-mapped HBM chunk store sized from `fraction` of what is free.  Returns a dict
+        describing the tiers chosen."""
+        tier = self.migrate_v_store("auto")
+        ways = 0
+        if tier == "host":
+            self.enable_hbm_store("auto", fraction)
+            ways = self.hbm_store_ways
+        v, other = self.state_bytes()
+        return {"v_residency": tier, "hbm_chunk_store_ways": ways, "v_store_bytes": v, "other_state_bytes": other}
 
     # ------------------------------------------------------------------------------------------
     def print_stats(self):
@@ -215,6 +277,8 @@ class ShadowKVCache_CPU:
             self._attn_ws = torch.zeros(
                 lib.skv_attention_workspace_bytes(g.batch, g.kv_heads, g.q_groups, g.head_dim, 0),
                 dtype=torch.uint8, device=self.device)
+            self._attend_ws = torch.zeros(lib.skv_attend_workspace_bytes(g.batch, g.kv_heads, g.q_groups),
+                                          dtype=torch.uint8, device=self.device)
         if cos_sin_cache is not None:
             width = cos_sin_cache.shape[-1]
             if width not in (self.head_dim, self.head_dim // 2):
@@ -515,6 +579,41 @@ class ShadowKVCache_CPU:
                                         self.cnts.data_ptr(), self.offsets.data_ptr(),
                                         C.byref(vs) if vs is not None else None, st), "fetch_and_rebuild")
 
+    def can_fuse_attend(self) -> bool:
+        """skv_fetch_rebuild_attend handles the in-place chunk table, G <= 8 and the tcgen05 rebuild."""
+        return (self.fused_attend and self.table_mode == "inplace" and self.num_key_value_groups <= 8
+                and self.rebuild_impl == 0)
+
+    def fetch_rebuild_attend(self, layer_idx, cos_sin_cache, query_states, out=None, kv_len=None, device_counters=False,
+                             resident=None):
+        """get_value_cache + get_key_cache + flash_attn_with_kvcache of one layer (base.py:326-341) in ONE launch: the CTAs
+        that rebuild / fetch the missed chunks also take their softmax partial on chip, other CTAs attend over what is
+        already resident while the transfer is in flight.  Returns [B,1,Hq,D].  `resident`: chunk table to use instead of
+        position_ids[layer_idx] (kernel benches with constructed hit rates)."""
+        g = self._geometry(cos_sin_cache)
+        if device_counters:
+            kv_len = self.buf_len                    # sizes the grid; the kernel reads the real length
+        elif kv_len is None:
+            kv_len = self._view_len(layer_idx)
+        q = query_states.contiguous()
+        B, Hq = q.shape[0], q.shape[1]
+        if out is None:
+            out = torch.empty(B, 1, Hq, self.head_dim, dtype=self.dtype, device=self.device)
+        self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
+        kb, vb = self.k_cache_buffer[layer_idx], self.v_cache_buffer[layer_idx]
+        vh = self.v_cache_cpu[layer_idx]
+        vs = self._vstore(layer_idx)
+        res = self.position_ids[layer_idx] if resident is None else resident
+        check(lib.skv_fetch_rebuild_attend(C.byref(g), vh.data_ptr(), vh.stride(1), vb.data_ptr(),
+                                           self.U[layer_idx].data_ptr(), self.SV[layer_idx].data_ptr(),
+                                           cos_sin_cache.data_ptr(), kb.data_ptr(), res.data_ptr(), self.cnts.data_ptr(),
+                                           self.offsets.data_ptr(), C.byref(vs) if vs is not None else None,
+                                           q.data_ptr(), out.data_ptr(), kv_len,
+                                           self.kv_len_dev.data_ptr() if device_counters else 0,
+                                           1.0 / math.sqrt(self.head_dim), self._attend_ws.data_ptr(), _cs()),
+              "fetch_rebuild_attend")
+        return out
+
     def attention(self, layer_idx, query_states, kv_len=None, out=None, device_counters=False, programmatic=False):
         """softmax(q K^T / sqrt(D)) V over rows [0, kv_len) of this layer's buffers (base.py:341).
         programmatic=True: programmatic dependent launch behind the single kernel that precedes it in the stream."""
@@ -574,6 +673,18 @@ class ShadowKVCache_CPU:
             self.gen_offset += 1
         hooks = after_select is not None or before_attention is not None
         single = self.fused_fetch_rebuild and self.rebuild_impl == 0 and not hooks
+        kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
+        if single and self.can_fuse_attend():
+            # everything behind the selection as ONE launch: score -> select -> fetch + rebuild + attention, three kernels
+            # per layer, every link a programmatic dependent launch
+            out = self.fetch_rebuild_attend(layer_idx, cos_sin_cache, query_states, out, kv_len, device_counters)
+            if self.hbm_store_ways:           # the store fill runs on the side stream, behind this layer's launch
+                self._side_used = True
+                self._fetch_done.record(cur)
+                with torch.cuda.stream(side):
+                    side.wait_event(self._fetch_done)
+                    self.fill_value_store(layer_idx)
+            return out
         if single:
             # one launch for both transfers of the missed chunks: select -> fetch+rebuild -> attention is a chain of
             # single predecessors, each launched programmatically (no fork / join, no launch gap before the attention)
@@ -602,7 +713,6 @@ class ShadowKVCache_CPU:
             cur.wait_event(self._k_done)
         if before_attention is not None:
             before_attention()
-        kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
         return self.attention(layer_idx, query_states, kv_len, out, device_counters,
                               programmatic=single and self.programmatic_attention)
 
@@ -623,8 +733,8 @@ class ShadowKVCache(ShadowKVCache_CPU):
     def _buffer_len(self) -> int:
         return self.sparse_budget + 4096                                   # kv_cache.py:233-251
 
-    def _alloc_v_store(self, *shape):
-        return torch.zeros(*shape, dtype=self.dtype, device=self.device)   # GPU-resident full V (kv_cache.py:222-230)
+    def _decide_v_residency(self, want: str) -> str:
+        return "hbm"                                                       # GPU-resident full V (kv_cache.py:222-230)
 
     def print_stats(self):
         print(f"ShadowKV | sparse budget {self.sparse_budget} | chunk size {self.chunk_size} |rank {self.rank} "

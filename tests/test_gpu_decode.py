@@ -121,6 +121,8 @@ def test_single_launch_fetch_and_rebuild_equals_the_two_stream_path(cuda, model,
     _, c2, _, _, _, _ = _build(cuda, model, B, prompt_len, budget, 2, table_mode=table_mode)
     assert lay.select == budget // 8
     c1.fused_fetch_rebuild, c2.fused_fetch_rebuild = True, False
+    c1.fused_attend = c2.fused_attend = False       # this test is about skv_fetch_and_rebuild + the stand-alone attention;
+                                                    # the three-way fusion has its own (tests/test_gpu_fused_attend.py)
     if ways:
         c1.enable_hbm_store(ways)
         c2.enable_hbm_store(ways)
@@ -256,7 +258,9 @@ def test_decode_layer_fused_append_equals_update_kv_cache(cuda):
             assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l])
             assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l])
             assert torch.equal(c1.position_ids[l], c2.position_ids[l])
-            assert torch.equal(o1, o2)
+            # decode_layer attends inside the fused fetch + rebuild launch, the stepwise calls through the stand-alone
+            # kernel: same K / V bytes (asserted above), a different fp32 summation order
+            assert_close_bf16(o1, o2, max_abs=4e-3, what="decode_layer vs stepwise attention")
         assert c1.gen_offset == c2.gen_offset == step + 1
 
 
