@@ -581,18 +581,23 @@ def head_split_block(args, full_shape, L, dev, rank, world, barrier, max_over_ra
     ins = make_inputs(L, B, Hq, H, dev, args.noise, steps + warm, 100000 * (rank + 1), base)
     out = {"what": f"the same batch-{B} sequence(s) with the {full_shape.num_key_value_heads} kv heads split x{world} "
                    f"(strong scaling); one exchange of the layer's attention output per layer", "n_gpus": world}
-    for label, gather in (("no_exchange", False), ("with_exchange", True)):
+    for label, gather, env in (("no_exchange", False, None), ("nccl_all_gather", True, "nccl"), ("with_exchange", True, "p2p")):
+        if env:
+            os.environ["SKV_HEAD_EXCHANGE"] = env
         run = DecodeStepGraph(cache, cs, host_io=False, gather_heads=gather).capture(warmup=1)
         run.rewind(0)
         ms, hr, _ = time_tokens(run, cache, ins, warm, steps, barrier)
         ms = max_over_ranks(ms)
         out[label] = {"value": steps * B / (ms * 1e-3), "us_per_layer_step": ms / steps / L * 1e3, "hit_rate": round(hr, 4)}
+        if gather:
+            out[label]["exchange"] = run.exchange
         run.graph.reset()
+        barrier()
     a, b = out["no_exchange"]["us_per_layer_step"], out["with_exchange"]["us_per_layer_step"]
     out["exchange_us_per_layer"] = b - a
+    out["nccl_exchange_us_per_layer"] = out["nccl_all_gather"]["us_per_layer_step"] - a
     out["value"] = out["with_exchange"]["value"]
     out["speedup_over_one_gpu"] = out["value"] / one_gpu_value if one_gpu_value else None
-    out["exchange"] = DecodeStepGraph.exchange_kind()
     del cache
     torch.cuda.empty_cache()
     return out

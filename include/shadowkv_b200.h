@@ -307,6 +307,22 @@ int skv_fetch_and_rebuild(const skv_geom *geom, const skv_bf16 *v_host, int64_t 
                           const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
                           const skv_vstore *vstore, skv_stream_t stream);
 
+/* kv-head split of a batch-1 long context over the GPUs of one node: every rank attends over its
+ * H/N kv heads; the only exchange is the layer's attention output [B, Hq/N, 128].  Instead of a collective launch per
+ * layer, the CTA that merges a row inside skv_fetch_rebuild_attend stores the row's output straight into EVERY rank's
+ * gathered buffer over NVLink (peer-mapped pointers, e.g. torch symmetric memory), and the rank's last row of the layer
+ * raises the rank's flag on every peer (system-scope release) with the value of *epoch_dev (a device counter the caller
+ * advances once per token and never rewinds).  skv_wait_flags is the consumer side. */
+#define SKV_MAX_PEERS 8
+typedef struct skv_exchange {
+  int32_t world;                      /* number of ranks (0: no exchange)                                              */
+  int32_t rank;                       /* this rank                                                                      */
+  void *peer_out[SKV_MAX_PEERS];      /* rank r's buffer slot for THIS rank's output of the layer: [B, Hq/N, 128] bf16  */
+  int32_t *peer_flags[SKV_MAX_PEERS]; /* rank r's flag word for (layer, this rank)                                      */
+  int32_t *rows_done;                 /* local scratch word of the layer, zero between launches                         */
+  const int32_t *epoch_dev;           /* device counter: value the flags take for the current token                     */
+} skv_exchange;
+
 /* Bytes of device scratch skv_fetch_rebuild_attend needs (softmax partials of the tile and split CTAs + arrival
  * counters).  Zero-filled ONCE by the caller; the kernel leaves its counters at zero. */
 int64_t skv_attend_workspace_bytes(int batch, int kv_heads, int q_groups);
@@ -325,7 +341,12 @@ int skv_fetch_rebuild_attend(const skv_geom *geom, const skv_bf16 *v_store, int6
                              const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
                              const int64_t *resident, const int32_t *cnts, const int32_t *offsets,
                              const skv_vstore *vstore, const skv_bf16 *q, skv_bf16 *out, int kv_len,
-                             const int32_t *kv_len_dev, float scale, void *workspace, skv_stream_t stream);
+                             const int32_t *kv_len_dev, float scale, void *workspace,
+                             const skv_exchange *exchange, skv_stream_t stream);
+
+/* Blocks `stream` (one tiny kernel) until flags[0..n) >= *epoch_dev: the outputs of all n ranks for that layer have
+ * landed in this rank's gathered buffer. */
+int skv_wait_flags(const int32_t *flags, int n, const int32_t *epoch_dev, skv_stream_t stream);
 
 /* ======================================================================
  * Part 3 -- prefill-side state build (reference models/kv_cache.py:788-980, ShadowKVCache_CPU.prefill_kv_cache)

@@ -35,6 +35,15 @@ class VStore(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+MAX_PEERS = 8
+
+
+class Exchange(C.Structure):
+    """struct skv_exchange (include/shadowkv_b200.h)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("peer_out", C.c_void_p * MAX_PEERS),
+                ("peer_flags", C.c_void_p * MAX_PEERS), ("rows_done", C.c_void_p), ("epoch_dev", C.c_void_p)]
+
+
 class DenseEpilogue(C.Structure):
     """struct skv_dense_epilogue (include/shadowkv_b200.h)."""
     _fields_ = [("mode", C.c_int32), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("rope_mode", C.c_int32),
@@ -84,7 +93,8 @@ _SIGS = {
     "skv_attention_decode_ex": [_p] * 4 + [_i] * 5 + [_l] * 3 + [_f, _i, _p, _p, _i, _p],
     "skv_fetch_and_rebuild": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(VStore), _p],
     "skv_fetch_rebuild_attend": [C.POINTER(Geom), _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, C.POINTER(VStore), _p, _p, _i, _p,
-                                 _f, _p, _p],
+                                 _f, _p, C.POINTER(Exchange), _p],
+    "skv_wait_flags": [_p, _i, _p, _p],
     "skv_dense_linear": [_p, _p, _i, _i, _i, C.POINTER(DenseEpilogue), _p, _p],
     "skv_rmsnorm": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "skv_argmax": [_p, _p, _i, _i, _p],

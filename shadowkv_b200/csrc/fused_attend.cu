@@ -64,6 +64,7 @@ struct FaParams {
   int kv_len, G, Gp, keys_per_split, n_splits, n_tiles, BH;
   int tail_off;                // byte offset of the fixed tail region in dynamic shared memory
   float scale_log2;
+  skv_exchange xc;             // kv-head split: peers that receive this rank's attention output (world == 0: none)
 };
 
 __device__ __forceinline__ void fa_tile_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -187,7 +188,41 @@ __device__ __forceinline__ void fa_merge(const FaParams &p, const int bh, const 
     uint2 packed;
     packed.x = pack_bf16x2(acc.x * inv, acc.y * inv);
     packed.y = pack_bf16x2(acc.z * inv, acc.w * inv);
-    *reinterpret_cast<uint2 *>(p.out + (size_t(bh) * p.G + hq) * kHeadDim + c4 * 4) = packed;
+    const size_t at = (size_t(bh) * p.G + hq) * kHeadDim + c4 * 4;
+    *reinterpret_cast<uint2 *>(p.out + at) = packed;
+    // kv-head split: the row's output goes straight into every peer's gathered buffer over NVLink (P2P stores); no
+    // collective launch on the chain
+    for (int r = 0; r < p.xc.world; ++r) *reinterpret_cast<uint2 *>(static_cast<skv_bf16 *>(p.xc.peer_out[r]) + at) = packed;
+  }
+  if (p.xc.world > 0) {
+    // The rank's last row of the layer raises this rank's flag on every peer: every merging CTA fences its remote
+    // stores at system scope and counts itself in; the one that completes the count fences again and releases.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int prev = atomicAdd(p.xc.rows_done, 1);
+      if (prev == p.BH - 1) {
+        *p.xc.rows_done = 0;
+        __threadfence_system();
+        const int epoch = *p.xc.epoch_dev;
+        for (int r = 0; r < p.xc.world; ++r)
+          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.xc.peer_flags[r]), "r"(epoch) : "memory");
+      }
+    }
+  }
+}
+
+// kv-head split: wait until every rank's flag of the layer has reached the current epoch (the gathered attention output
+// of the layer is then complete in THIS rank's buffer).  One warp, lane = peer rank.
+__global__ void __launch_bounds__(32) wait_flags_kernel(const int32_t *flags, int n, const int32_t *epoch_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (int(threadIdx.x) < n) {
+    const int want = *epoch_dev;
+    int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + threadIdx.x) : "memory");
+    } while (seen < want);
   }
 }
 
@@ -838,7 +873,7 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
                              const skv_bf16 *U, const skv_bf16 *SV, const skv_bf16 *cos_sin, skv_bf16 *k_buf,
                              const int64_t *resident, const int32_t *cnts, const int32_t *offsets, const skv_vstore *vstore,
                              const skv_bf16 *q, skv_bf16 *out, int kv_len, const int32_t *kv_len_dev, float scale,
-                             void *workspace, skv_stream_t stream) {
+                             void *workspace, const skv_exchange *exchange, skv_stream_t stream) {
   if (!g || !v_store || !v_buf || !U || !SV || !cos_sin || !k_buf || !resident || !cnts || !offsets || !q || !out || !workspace) {
     set_error("fetch_rebuild_attend: null pointer"); return SKV_ERR_ARGUMENT;
   }
@@ -867,6 +902,14 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
   p.v_src = v_store; p.v_src_stride_bh = store_stride; p.v_buf = v_buf;
   if (vstore) p.vs = *vstore;
   p.q = q; p.out = out; p.kv_len_dev = kv_len_dev; p.kv_len = kv_len;
+  if (exchange && exchange->world > 0) {
+    if (exchange->world > SKV_MAX_PEERS || !exchange->rows_done || !exchange->epoch_dev) {
+      set_error("fetch_rebuild_attend: exchange needs 1..%d peers, rows_done and epoch_dev", SKV_MAX_PEERS); return SKV_ERR_ARGUMENT;
+    }
+    for (int r = 0; r < exchange->world; ++r)
+      if (!exchange->peer_out[r] || !exchange->peer_flags[r]) { set_error("fetch_rebuild_attend: null peer pointer"); return SKV_ERR_ARGUMENT; }
+    p.xc = *exchange;
+  }
   p.G = g->q_groups; p.Gp = (g->q_groups + 3) / 4 * 4;
   p.BH = BH; p.n_tiles = S / kFaTileChunks;
   p.scale_log2 = scale * 1.4426950408889634f;
@@ -915,6 +958,13 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
                                 /*pdl=*/true, map_sv, map_k, map_v, p);
   if (e != cudaSuccess) { set_error("fetch_rebuild_attend_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("fetch_rebuild_attend_kernel");
+}
+
+int skv_wait_flags(const int32_t *flags, int n, const int32_t *epoch_dev, skv_stream_t stream) {
+  if (!flags || !epoch_dev || n < 1 || n > 32) { set_error("wait_flags: bad argument"); return SKV_ERR_ARGUMENT; }
+  cudaError_t e = launch_kernel(wait_flags_kernel, dim3(1), dim3(32), 0, as_stream(stream), /*pdl=*/true, flags, n, epoch_dev);
+  if (e != cudaSuccess) { set_error("wait_flags_kernel: %s", cudaGetErrorString(e)); return int(e); }
+  return launch_status("wait_flags_kernel");
 }
 
 }  // extern "C"

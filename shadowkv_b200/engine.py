@@ -41,9 +41,22 @@ class DecodeStepGraph:
         self.v_d = torch.zeros(L, B, H, 1, D, dtype=dt, device=dev)
         self.out_d = torch.zeros(L, B, 1, Hq, D, dtype=dt, device=dev)
         self.out_all = None
+        self.xchg = None
+        self.exchange = "none"
         if gather_heads:
+            import os
             import torch.distributed as dist
-            self.out_all = torch.zeros(L, dist.get_world_size(), B, 1, Hq, D, dtype=dt, device=dev)
+            hooks_free = cache.fused_fetch_rebuild and cache.can_fuse_attend()
+            if hooks_free and os.environ.get("SKV_HEAD_EXCHANGE", "p2p") != "nccl":
+                # peer stores from inside the fused launch + one flag wait per layer (parallel.HeadExchange)
+                self.xchg = parallel.HeadExchange(L, B, Hq, dev, D)
+                self.out_all = self.xchg.out_all
+                self.exchange = ("P2P stores over NVLink from the merging CTA of skv_fetch_rebuild_attend into every rank's "
+                                 "symmetric-memory buffer + one flag wait per layer (no collective launch)")
+            else:
+                world = dist.get_world_size() if dist.is_initialized() else 1
+                self.out_all = torch.zeros(L, world, B, 1, Hq, D, dtype=dt, device=dev)
+                self.exchange = "NCCL all_gather_into_tensor, one node per layer inside the captured graph"
         if host_io:
             self.q_h = torch.zeros(L, B, Hq, 1, D, dtype=dt).pin_memory()
             self.k_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
@@ -60,15 +73,13 @@ class DecodeStepGraph:
         if fused and cache.can_fuse_attend():
             per_layer = 3                      # score (+append), select, fetch + rebuild + attention
         self.launches_per_step = L * (per_layer + (1 if cache.hbm_store_ways else 0))
+        self._per_layer = per_layer
+        if self.xchg is not None:
+            self.launches_per_step += L        # the per-layer flag wait of the peer-store exchange
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0
         self._presets = {}
-
-    @staticmethod
-    def exchange_kind() -> str:
-        """How the kv-head split exchanges a layer's attention output (bench / DESIGN reporting)."""
-        return "NCCL all_gather_into_tensor, one node per layer inside the captured graph"
 
     @property
     def hits_d(self):
@@ -86,11 +97,15 @@ class DecodeStepGraph:
         c = self.cache
         for l in range(c.num_layers):
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
-                           device_counters=True)
-            if self.gather:
+                           device_counters=True, exchange=self.xchg.struct(l) if self.xchg is not None else None)
+            if self.xchg is not None:
+                self.xchg.wait(l)          # what consumes the layer's gathered output (o_proj) must not start before it
+            elif self.gather:
                 parallel.gather_heads(self.out_d[l], self.out_all[l])
         c.join_side_streams()
         c.advance_device_counters()
+        if self.xchg is not None:
+            self.xchg.advance()
         if self.host_io:
             self.out_h.copy_(self.out_all if self.gather else self.out_d, non_blocking=True)
 

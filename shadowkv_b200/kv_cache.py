@@ -585,11 +585,12 @@ class ShadowKVCache_CPU:
                 and self.rebuild_impl == 0)
 
     def fetch_rebuild_attend(self, layer_idx, cos_sin_cache, query_states, out=None, kv_len=None, device_counters=False,
-                             resident=None):
+                             resident=None, exchange=None):
         """get_value_cache + get_key_cache + flash_attn_with_kvcache of one layer (base.py:326-341) in ONE launch: the CTAs
         that rebuild / fetch the missed chunks also take their softmax partial on chip, other CTAs attend over what is
         already resident while the transfer is in flight.  Returns [B,1,Hq,D].  `resident`: chunk table to use instead of
-        position_ids[layer_idx] (kernel benches with constructed hit rates)."""
+        position_ids[layer_idx] (kernel benches with constructed hit rates).  `exchange`: _lib.Exchange of the kv-head split
+        (the merged rows are also stored into every peer's gathered buffer; parallel.HeadExchange)."""
         g = self._geometry(cos_sin_cache)
         if device_counters:
             kv_len = self.buf_len                    # sizes the grid; the kernel reads the real length
@@ -610,7 +611,8 @@ class ShadowKVCache_CPU:
                                            self.offsets.data_ptr(), C.byref(vs) if vs is not None else None,
                                            q.data_ptr(), out.data_ptr(), kv_len,
                                            self.kv_len_dev.data_ptr() if device_counters else 0,
-                                           1.0 / math.sqrt(self.head_dim), self._attend_ws.data_ptr(), _cs()),
+                                           1.0 / math.sqrt(self.head_dim), self._attend_ws.data_ptr(),
+                                           C.byref(exchange) if exchange is not None else None, _cs()),
               "fetch_rebuild_attend")
         return out
 
@@ -636,7 +638,7 @@ class ShadowKVCache_CPU:
         return out
 
     def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
-                     device_counters=False, after_select=None, before_attention=None):
+                     device_counters=False, after_select=None, before_attention=None, exchange=None):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
         query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
@@ -677,7 +679,8 @@ class ShadowKVCache_CPU:
         if single and self.can_fuse_attend():
             # everything behind the selection as ONE launch: score -> select -> fetch + rebuild + attention, three kernels
             # per layer, every link a programmatic dependent launch
-            out = self.fetch_rebuild_attend(layer_idx, cos_sin_cache, query_states, out, kv_len, device_counters)
+            out = self.fetch_rebuild_attend(layer_idx, cos_sin_cache, query_states, out, kv_len, device_counters,
+                                            exchange=exchange)
             if self.hbm_store_ways:           # the store fill runs on the side stream, behind this layer's launch
                 self._side_used = True
                 self._fetch_done.record(cur)
@@ -685,6 +688,9 @@ class ShadowKVCache_CPU:
                     side.wait_event(self._fetch_done)
                     self.fill_value_store(layer_idx)
             return out
+        if exchange is not None:
+            raise RuntimeError("the peer-store exchange rides on the fused fetch + rebuild + attention launch "
+                               "(in-place chunk table, G <= 8, no hooks)")
         if single:
             # one launch for both transfers of the missed chunks: select -> fetch+rebuild -> attention is a chain of
             # single predecessors, each launched programmatically (no fork / join, no launch gap before the attention)

@@ -91,3 +91,27 @@ def test_rewind_reuses_generation_region(cuda):
     torch.cuda.synchronize()
     assert c.gen_offset == 1
     assert torch.equal(c.k_cache_buffer[0][:, :, c.sparse_end], k2[0][:, :, 0])
+
+
+def test_peer_store_exchange_single_rank(cuda):
+    """The kv-head split's exchange path with one rank (peer = self; no process group): the merging CTAs of the fused
+    launch also store every row into the gathered buffer and the rank's last row raises the layer's flag with the token's
+    epoch; skv_wait_flags is in the captured chain.  Same kernel path the N-GPU runs take over NVLink."""
+    from shadowkv_b200.engine import DecodeStepGraph
+    shape = synth.MODELS["llama-3.1-8b"]
+    B, prompt_len, budget, layers = 2, 8192, 1024, 3
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    c = _cache(cuda, shape, B, prompt_len, budget, layers, cs)
+    run = DecodeStepGraph(c, cs.to(cuda), host_io=False, gather_heads=True).capture(warmup=1)
+    assert run.xchg is not None and run.xchg.world == 1 and "P2P" in run.exchange
+    g = torch.Generator().manual_seed(5)
+    for t in range(4):
+        q = torch.randn(layers, B, 32, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+        k = torch.randn(layers, B, 8, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+        out = run.step_device(q, k, k)
+        run.stream.synchronize()
+        assert torch.equal(run.out_all[:, 0], out), f"gathered buffer differs from the local output at token {t}"
+        # warm-up token used epoch 1; this replay is epoch t + 2, and the device counter already points at the next one
+        assert int(run.xchg.epoch) == t + 3
+        assert bool((run.xchg.flags == t + 2).all()), run.xchg.flags
+        assert int(run.xchg.rows_done.abs().sum()) == 0
