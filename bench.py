@@ -738,6 +738,17 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, hit_rate, step_u
     kernels["select"] = {"us": t_select, "GBps": sel_bytes / t_select * 1e-3, "bound": "latency (1 MB of L2-resident scores + the landmark index)",
                          "frac": sel_bytes / t_select * 1e-3 / peaks["hbm"]}
 
+    def score_select(l):             # the launch the step uses: scoring + selection + chunk-table update in one cluster kernel
+        check(lib.skv_select_chunks(C.byref(g), q[l].data_ptr(), cache.k_landmark[l].data_ptr(),
+                                    cache.k_landmark_idx[l].data_ptr(), cache.position_ids[l].data_ptr(),
+                                    cache.offsets_all[l].data_ptr(), cache.cnts_all[l].data_ptr(), 0, 0,
+                                    cache._sel_ws.data_ptr(), None, cur()), "select_chunks")
+
+    t_ss = timed(score_select, 2 * L)
+    kernels["score_select"] = {"us": t_ss, "GBps": score_bytes / t_ss * 1e-3, "bound": "hbm", "frac": score_bytes / t_ss * 1e-3 / peaks["hbm"],
+                               "note": "stage a3-a5 as launched by the step (two launches; one cluster kernel with SKV_FUSED_SELECT=1); "
+                                       "`score` and `select` above are the two-launch path's kernels timed alone"}
+
     def attn(l):
         cache.attention(l, q[l], kv_len=lay.sparse_end + 1, out=out)
 
@@ -853,7 +864,7 @@ def kernel_table(args, cache, cs, shape, L, B, lay, peaks, dev, hit_rate, step_u
         dom = dict(hbm_roof)
     dom["hbm"] = hbm_roof
     dom["kernels"] = {k: {kk: vv for kk, vv in v.items() if kk in ("us", "GBps", "bound", "frac")}
-                      for k, v in kernels.items() if k in ("score", "select", "attention")}
+                      for k, v in kernels.items() if k in ("score", "select", "score_select", "attention")}
     for label in ("h0", "h60", "h100"):
         if label in kernels:
             dom["kernels"][label] = kernels[label]

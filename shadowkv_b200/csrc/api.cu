@@ -50,8 +50,10 @@ const char *skv_active_config(void) {
   auto on = [](const char *name, char v) { const char *e = getenv(name); return e && e[0] == v; };
   const char *ctas = getenv("SKV_SCORE_CTAS");
   snprintf(buf, sizeof(buf),
-           "score=%s select=cluster8-radix rebuild=%s attention=%s attend_fusion=%s pdl=%s score_ring=%s score_ctas=%s",
-           on("SKV_SCORE_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05+TMA", on("SKV_REBUILD_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05",
+           "score=%s select=%s rebuild=%s attention=%s attend_fusion=%s pdl=%s score_ring=%s score_ctas=%s",
+           on("SKV_SCORE_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05+TMA",
+           (on("SKV_FUSED_SELECT", '1') && !on("SKV_SCORE_IMPL", '1')) ? "fused-with-scoring(experiment)" : "own-launch(cluster8-radix)",
+           on("SKV_REBUILD_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05",
            on("SKV_ATTN_IMPL", '1') ? "SIMT(cross-check)" : "mma.sync+TMA", on("SKV_FUSED_ATTEND", '0') ? "off" : "on",
            skv::pdl_enabled() ? "on" : "off", on("SKV_SCORE_STAGES", '2') ? "2x3" : "3x2", (ctas && *ctas) ? ctas : "default");
   return buf;

@@ -18,6 +18,11 @@ namespace cg = cooperative_groups;
 
 namespace skv {
 
+// score_select.cu: scoring + selection in one cluster launch (experiment, SKV_FUSED_SELECT=1; SKV_ERR_UNSUPPORTED: shape not taken)
+int launch_score_select(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, const int64_t *landmark_idx,
+                        int64_t *resident, int32_t *offsets, int32_t *cnts, int64_t *selected_out, skv_bf16 *score_out,
+                        const skv_append *append, cudaStream_t st);
+
 // score_mma.cu: TMA + tcgen05 scoring (product path)
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
@@ -651,6 +656,25 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
 int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *landmarks, const int64_t *landmark_idx,
                       int64_t *resident, int32_t *offsets, int32_t *cnts, int64_t *selected_out,
                       skv_bf16 *score_out, void *workspace, const skv_append *append, skv_stream_t stream) {
+  if (!g || !q || !landmarks || !landmark_idx || !resident || !offsets || !cnts || !workspace) {
+    set_error("select_chunks: null pointer"); return SKV_ERR_ARGUMENT;
+  }
+  if (int rc = check_select_geom(g, "select_chunks")) return rc;
+  if (append && (!append->k_new || !append->v_new || !append->k_buf || !append->v_buf || append->pos < 0 ||
+                 append->pos >= g->buf_len)) {
+    set_error("select_chunks: bad fused append (pos %d, buffer %d rows)", append->pos, g->buf_len);
+    return SKV_ERR_ARGUMENT;
+  }
+  // experiment (SKV_FUSED_SELECT=1): scoring + selection as ONE cluster launch (score_select.cu).  Measured slower than
+  // the two launches below at every batch (a row's cluster cannot span enough SMs to keep HBM busy),
+  // so it is NOT the product path; shapes it does not take fall through
+  const char *fe = getenv("SKV_FUSED_SELECT"), *se = getenv("SKV_SCORE_IMPL");      // read per call: tests flip it
+  const bool fused = (fe && fe[0] == '1') && !(se && se[0] == '1');
+  if (fused) {
+    const int rc = launch_score_select(g, q, landmarks, landmark_idx, resident, offsets, cnts, selected_out, score_out,
+                                       append, as_stream(stream));
+    if (rc != SKV_ERR_UNSUPPORTED) return rc;
+  }
   if (int rc = skv_score_landmarks(g, q, landmarks, workspace, append, stream)) return rc;
   return skv_select_from_scores(g, landmark_idx, resident, offsets, cnts, selected_out, score_out, workspace, stream);
 }

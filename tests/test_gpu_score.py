@@ -159,3 +159,54 @@ def test_select_underflowed_probabilities_and_ragged_tail(cuda):
     for h in range(H):
         assert torch.equal(sel[0, h].cpu(), want), "underflow ties must resolve to the lowest landmark indices"
         assert torch.equal(res[0, h].cpu(), want)
+
+
+@pytest.mark.parametrize("model,B,N,S", [("llama-3.1-8b", 1, 15560, 256),      # 8 rows: 16-CTA clusters (cfg2)
+                                         ("llama-3.1-8b", 2, 15560, 256),      # 16 rows: 8-CTA clusters
+                                         ("glm-4-9b-1m", 1, 16328, 256),       # 4 rows x G = 8
+                                         ("llama-3-8b-1m", 4, 65480, 256),     # cfg3: 64 KiB of scores per CTA
+                                         ("yi-9b-200k", 3, 25544, 128),
+                                         ("llama-3.1-8b", 1, 1000, 128)])      # fewer tiles than CTAs, ragged N
+def test_fused_score_select_experiment_agrees_with_the_two_launches(cuda, monkeypatch, model, B, N, S):
+    """The one-launch experiment (SKV_FUSED_SELECT=1, score_select.cu; measured slower, not the product path) against the
+    product path skv_score_landmarks + skv_select_from_scores: same bf16 scores; the softmax sums are accumulated in a
+    different order (per CTA, then over the cluster), so a key may differ by 1 bf16 ulp and the selection only at the
+    threshold value."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    shape = synth.MODELS[model]
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(N + S + B)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16).to(cuda)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S]] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448, table_mode=1)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    d_idx = idx.to(cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SKV_FUSED_SELECT", fused)
+        res = resident.to(cuda).clone()
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+        _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.data_ptr(), lm.data_ptr(), d_idx.data_ptr(), res.data_ptr(),
+                                              off.data_ptr(), cnt.data_ptr(), sel.data_ptr(), score.data_ptr(),
+                                              ws.data_ptr(), None, st), "select_chunks")
+        torch.cuda.synchronize()
+        outs.append((res.cpu(), off.cpu(), cnt.cpu(), sel.cpu(), score.cpu()))
+    (r1, o1, c1, s1, k1), (r2, o2, c2, s2, k2) = outs
+    kd = (k1.view(torch.int16).int() - k2.view(torch.int16).int()).abs()
+    assert int(kd.max()) <= 1 and float((kd == 0).float().mean()) >= 0.999, "selection keys differ by more than the summation order explains"
+    for r in range(B * H):
+        a, b = set(s1.view(B * H, S)[r].tolist()), set(s2.view(B * H, S)[r].tolist())
+        assert len(a) == S and len(a ^ b) <= 4, f"row {r}: {len(a ^ b)} chunks selected differently"
+    if torch.equal(s1, s2):
+        assert torch.equal(c1, c2) and torch.equal(r1, r2), "chunk table differs"
+        nm = (S - c1.long()).view(-1, 1)
+        live = torch.arange(S).view(1, -1) < nm                   # offsets[i] is defined for i < number of misses
+        assert torch.equal(o1.view(B * H, S)[live], o2.view(B * H, S)[live])
