@@ -180,6 +180,13 @@ typedef struct skv_geom {
   int32_t table_mode;   /* 0: reference slot order (hits compacted to the front, needs skv_compact_hits);
                          * 1: in-place table (hits keep their slots; offsets[i] = slot of the i-th miss) */
   int32_t flags;        /* SKV_GEOM_* bits                     */
+  int32_t *row_flags;   /* optional [B*H] words (device, zero-initialised, one array per layer): per-row hand-over from
+                         * the selection to skv_fetch_rebuild_attend.  When set, the selection kernel clears its row's
+                         * word after its own dependency wait and before it releases its dependents, and raises it
+                         * (release) once the row's chunk table is written; the CTAs of the fetch launch wait for their
+                         * row's word instead of for the completion of the whole selection grid.  Pass the SAME pointer
+                         * to skv_select_chunks / skv_select_from_scores and to the skv_fetch_rebuild_attend call that
+                         * follows it on the stream; NULL (all other entry points ignore it): plain dependent launches */
 } skv_geom;
 
 /* The scoring launch is a programmatic dependent launch that streams the landmarks into shared memory BEFORE it

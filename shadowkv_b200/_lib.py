@@ -17,7 +17,7 @@ class Geom(C.Structure):
     """struct skv_geom (include/shadowkv_b200.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "batch", "kv_heads", "q_groups", "head_dim", "chunk", "select", "n_landmarks", "rank", "seq_len",
-        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode", "flags")]
+        "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode", "flags")] + [("row_flags", C.c_void_p)]
 
 
 GEOM_DYNAMIC_LANDMARKS = 1   # SKV_GEOM_DYNAMIC_LANDMARKS

@@ -65,7 +65,25 @@ struct FaParams {
   int tail_off;                // byte offset of the fixed tail region in dynamic shared memory
   float scale_log2;
   skv_exchange xc;             // kv-head split: peers that receive this rank's attention output (world == 0: none)
+  const int32_t *row_flags;    // [BH] or null: per-row hand-over from the selection kernel (skv_geom.row_flags)
 };
+
+// Everything behind this point reads what the selection kernel wrote for row bh (chunk table, hit count, miss list) and,
+// through it, its predecessors' outputs (the appended K / V row).  With row flags the CTA waits for ITS row's word, which
+// the selection raises (release) as soon as the row's table is written, instead of for the completion and flush of the
+// whole selection grid (~2 us later); the acquire makes the table -- and, by cumulativity, what the selection kernel's
+// own dependency wait had made visible to it -- visible to this CTA.  The kernel still executes griddepcontrol.wait once,
+// at its very end, so that ITS dependents keep the transitive guarantee of the chain.
+__device__ __forceinline__ void fa_wait_row(const FaParams &p, const int bh) {
+  if (!p.row_flags) { pdl_wait(); return; }
+  if (threadIdx.x == 0) {
+    int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.row_flags + bh) : "memory");
+    } while (seen == 0);
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ void fa_tile_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // TMA bulk copy global (device or pinned host memory) -> shared memory, completion on an mbarrier
@@ -271,15 +289,15 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
   }
   if (warp == 0) tcgen05_alloc(tmem_slot, 128);
   // ---- everything below reads what the selection kernel (and, through it, its predecessors) wrote -------------------
-  pdl_wait();
+  fa_wait_row(p, bh);
   int raw = 0;
-  if (tid < kFaTileChunks) raw = p.miss_slots[size_t(bh) * S + tile * kFaTileChunks + tid];   // read before the hit count
-  const int cnt = p.cnts[bh];                                                                  // is known (in range anyway)
+  if (tid < kFaTileChunks) raw = __ldcg(p.miss_slots + size_t(bh) * S + tile * kFaTileChunks + tid);   // read before the
+  const int cnt = __ldcg(p.cnts + bh);                                                          // hit count is known
   const int n_miss = S - cnt;
   const int n_active = (n_miss + kFaTileChunks - 1) / kFaTileChunks;
   if (tid < kFaTileChunks) {
     const int slot = raw & (S - 1);                             // S is a power of two; a no-op for real entries
-    const int id = static_cast<int>(p.resident[size_t(bh) * S + slot]);
+    const int id = static_cast<int>(__ldcg(p.resident + size_t(bh) * S + slot));
     const bool on = tile * kFaTileChunks + tid < n_miss;
     s_ids[tid] = on ? id : -1;
     s_slots[tid] = on ? slot : 0;
@@ -662,13 +680,13 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
   }
   if (tid < 32) s_mask[tid] = 0u;
   __syncthreads();
-  pdl_wait();
+  fa_wait_row(p, bh);
 
   const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
   const int k_begin = split * p.keys_per_split;
   const int k_end = min(kv_len, k_begin + p.keys_per_split);
   const int n_tiles = k_end > k_begin ? (k_end - k_begin + kFaTileKeys - 1) / kFaTileKeys : 0;
-  const int cnt = p.cnts[bh];
+  const int cnt = __ldcg(p.cnts + bh);
   const int n_miss = S - cnt;
   const int n_active = (n_miss + kFaTileChunks - 1) / kFaTileChunks;
 
@@ -676,6 +694,9 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
   // being overwritten by the tile CTAs right now and belong to THEIR partials)
   int p_stage = 0, p_ph = 0, p_next = 0;
   if (warp == 4 && lane == 0) {
+    // the K / V rows were written through the generic proxy (previous launches, the fused append); with the row
+    // hand-over no kernel boundary lies in between, so order them in front of this thread's async-proxy reads
+    if (p.row_flags) asm volatile("fence.proxy.async;" ::: "memory");
     for (; p_next < n_tiles && p_next < kFaStages; ++p_next) {
       mbarrier_expect_tx(&full_bar[p_stage], kFaRingTile);
       unsigned char *dst = ring + p_stage * kFaRingTile;
@@ -688,7 +709,7 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
     }
   }
   for (int i = tid; i < n_miss; i += kFaThreads) {
-    const int slot = p.miss_slots[size_t(bh) * S + i] & (S - 1);
+    const int slot = __ldcg(p.miss_slots + size_t(bh) * S + i) & (S - 1);
     atomicOr(&s_mask[slot >> 5], 1u << (slot & 31));
   }
   __syncthreads();
@@ -849,6 +870,7 @@ __global__ void __launch_bounds__(kFaThreads, 2)
     const int id = int(blockIdx.x) - n_tile_ctas;
     fa_split_role(&map_k, &map_v, p, id / p.n_splits, id % p.n_splits, smem);
   }
+  if (p.row_flags) pdl_wait();   // see fa_wait_row: by now the selection grid has long completed
 }
 
 int make_tensor_map_2d(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
@@ -902,6 +924,7 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
   p.v_src = v_store; p.v_src_stride_bh = store_stride; p.v_buf = v_buf;
   if (vstore) p.vs = *vstore;
   p.q = q; p.out = out; p.kv_len_dev = kv_len_dev; p.kv_len = kv_len;
+  p.row_flags = g->row_flags;
   if (exchange && exchange->world > 0) {
     if (exchange->world > SKV_MAX_PEERS || !exchange->rows_done || !exchange->epoch_dev) {
       set_error("fetch_rebuild_attend: exchange needs 1..%d peers, rows_done and epoch_dev", SKV_MAX_PEERS); return SKV_ERR_ARGUMENT;

@@ -296,6 +296,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
                   int32_t *__restrict__ offsets, int32_t *__restrict__ cnts,
                   int64_t *__restrict__ selected_out,         // [BH, S] or null
                   skv_bf16 *__restrict__ score_out,           // [BH, N] or null
+                  int32_t *row_flags,                         // [BH] or null: per-row hand-over to the fetch launch
                   int G, int N, int ldn, int T, int per) {
   constexpr int kThreads = S > 256 ? S : 256;
   constexpr int kWarps = kThreads / 32;
@@ -321,13 +322,27 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
 
   // early, independent global loads: the (static) landmark ids of this thread's first 8 landmarks.  Under a
   // programmatic launch this and the histogram clearing overlap the tail of the scoring kernel.
-  pdl_launch_dependents();
+  if (!row_flags) pdl_launch_dependents();
   const int64_t *lidx = landmark_idx + size_t(bh) * N + n_begin;
   int ids0[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) ids0[e] = (tid * 8 + e < count) ? static_cast<int>(lidx[tid * 8 + e]) : 0;   // map.cuh:776
   for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
   pdl_wait();                                   // scores, partials and the chunk table are the predecessors' outputs
+  if (row_flags) {
+    // Row hand-over (skv_geom.row_flags): the dependents of this launch wait for their ROW's word, not for this grid.
+    // The word still carries the previous token's 1; every consumer of that value has finished (this kernel's wait
+    // covers, transitively, the previous launch that read it), and no consumer of the new value exists before the
+    // trigger below: clear it, make the store visible, and only then let the dependent grid be scheduled.
+    if (rank == 0) {
+      if (tid == 0) {
+        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(0) : "memory");
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    pdl_launch_dependents();
+  }
   if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 21);
   int old_id = 0;
   if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
@@ -532,6 +547,13 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
   chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
                                   cnts + bh);
   SKV_STAMP(bh == 0 ? rank : 999, 14);
+  if (row_flags) {                              // the row's chunk table (resident, offsets, cnt) is written: release it
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(1) : "memory");
+    }
+  }
   if (tid == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 22);
 }
 
@@ -635,7 +657,7 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP>), smem, "select_kernel")) return rc; \
     cudaError_t e = launch_kernel(select_kernel<SV, IP>, dim3(kSelCluster, BH), dim3(kThreads), smem, st, true,     \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
-                                  score_out, G, N, w.ldn, w.T, per);                                              \
+                                  score_out, g->row_flags, G, N, w.ldn, w.T, per);                                \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL(SV)                                                                                              \
@@ -669,7 +691,7 @@ int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *land
   // the two launches below at every batch (a row's cluster cannot span enough SMs to keep HBM busy),
   // so it is NOT the product path; shapes it does not take fall through
   const char *fe = getenv("SKV_FUSED_SELECT"), *se = getenv("SKV_SCORE_IMPL");      // read per call: tests flip it
-  const bool fused = (fe && fe[0] == '1') && !(se && se[0] == '1');
+  const bool fused = (fe && fe[0] == '1') && !(se && se[0] == '1') && !g->row_flags;   // the experiment has no row hand-over
   if (fused) {
     const int rc = launch_score_select(g, q, landmarks, landmark_idx, resident, offsets, cnts, selected_out, score_out,
                                        append, as_stream(stream));

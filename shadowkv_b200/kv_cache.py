@@ -143,6 +143,7 @@ class ShadowKVCache_CPU:
         self._fetch_done = torch.cuda.Event()
         self._k_done = torch.cuda.Event()
         self._geom = None
+        self._row_flags = None
         self._sel_ws = None
         self._attn_ws = None
         self.rebuild_impl = 0      # 0: tcgen05 (product); 1: SIMT cross-check (tests only)
@@ -279,6 +280,10 @@ class ShadowKVCache_CPU:
                 dtype=torch.uint8, device=self.device)
             self._attend_ws = torch.zeros(lib.skv_attend_workspace_bytes(g.batch, g.kv_heads, g.q_groups),
                                           dtype=torch.uint8, device=self.device)
+            # per-row hand-over words between the selection and the fused fetch launch (skv_geom.row_flags), one array
+            # per layer; SKV_ROW_FLAGS=0 keeps plain dependent launches (A/B runs)
+            self._row_flags = (torch.zeros(self.num_layers, g.batch * g.kv_heads, dtype=torch.int32, device=self.device)
+                               if os.environ.get("SKV_ROW_FLAGS", "1") != "0" else None)
         if cos_sin_cache is not None:
             width = cos_sin_cache.shape[-1]
             if width not in (self.head_dim, self.head_dim // 2):
@@ -665,7 +670,17 @@ class ShadowKVCache_CPU:
             # selection rewrites those tables and before its fetch reads the store.  (In a captured graph the join at the
             # end of the token body orders them; with several layers the fork / join of the next layer does.)
             cur.wait_stream(side)
-        pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
+        hooks = after_select is not None or before_attention is not None
+        single = self.fused_fetch_rebuild and self.rebuild_impl == 0 and not hooks
+        fused_attend = single and self.can_fuse_attend()
+        if fused_attend and self._row_flags is not None:
+            # selection -> fetch + rebuild + attention hand over per (b, kv head) row instead of per grid
+            g.row_flags = self._row_flags[layer_idx].data_ptr()
+        try:
+            pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
+        except Exception:
+            g.row_flags = None
+            raise
         if after_select is not None:
             # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
             # idle; the runner uses the window to pull the next dense weights into L2 on its own stream
@@ -673,14 +688,15 @@ class ShadowKVCache_CPU:
         if layer_idx == self.num_layers - 1 and not device_counters:
             self.kv_offset += 1
             self.gen_offset += 1
-        hooks = after_select is not None or before_attention is not None
-        single = self.fused_fetch_rebuild and self.rebuild_impl == 0 and not hooks
         kv_len = self.sparse_end + self.gen_offset + (0 if layer_idx == self.num_layers - 1 else 1)
-        if single and self.can_fuse_attend():
+        if fused_attend:
             # everything behind the selection as ONE launch: score -> select -> fetch + rebuild + attention, three kernels
             # per layer, every link a programmatic dependent launch
-            out = self.fetch_rebuild_attend(layer_idx, cos_sin_cache, query_states, out, kv_len, device_counters,
-                                            exchange=exchange)
+            try:
+                out = self.fetch_rebuild_attend(layer_idx, cos_sin_cache, query_states, out, kv_len, device_counters,
+                                                exchange=exchange)
+            finally:
+                g.row_flags = None
             if self.hbm_store_ways:           # the store fill runs on the side stream, behind this layer's launch
                 self._side_used = True
                 self._fetch_done.record(cur)

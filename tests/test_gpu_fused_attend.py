@@ -122,3 +122,35 @@ def test_fused_launch_matches_oracle(cuda, model, B):
                     pos = {int(c): i for i, c in enumerate(res[b, h].tolist())}
                     src = torch.tensor([pos[int(c)] for c in ora[l].resident[b, h].tolist()])
                     ora[l].k_buf[b, h, ss:ss + S * 8] = kb[b, h, ss:ss + S * 8].view(S, 8, -1)[src].reshape(S * 8, -1)
+
+
+@pytest.mark.parametrize("model,B,prompt_len,budget", [("llama-3.1-8b", 1, 32768, 2048),     # one wave (296 CTAs)
+                                                       ("llama-3.1-8b", 12, 8192, 2048),     # 96 rows: several waves
+                                                       ("glm-4-9b-1m", 5, 8192, 1024)])
+def test_row_flag_handover_equals_plain_dependent_launches(cuda, monkeypatch, model, B, prompt_len, budget):
+    """skv_geom.row_flags: the CTAs of the fused fetch launch wait for their ROW's word from the selection kernel instead
+    of for the completion of the selection grid.  Same kernels, same arithmetic: every output is bit-identical to the
+    plain programmatic launches (SKV_ROW_FLAGS=0), over enough steps and rows that late-starting CTAs occur."""
+    monkeypatch.setenv("SKV_ROW_FLAGS", "1")
+    shape, c1, _, cs = _build(cuda, model, B, prompt_len, budget, 2)
+    d_cs = cs.to(cuda)
+    c1._geometry(d_cs)
+    monkeypatch.setenv("SKV_ROW_FLAGS", "0")
+    _, c2, _, _ = _build(cuda, model, B, prompt_len, budget, 2)
+    c2._geometry(d_cs)
+    assert c1._row_flags is not None and c2._row_flags is None
+    base = None
+    for step in range(8):
+        for l in range(2):
+            q, kn, vn = synth.queries(shape, B, seed=31 * step + l, base=base, noise=0.4)
+            base = q if base is None else base
+            dq, dk, dv = q.to(cuda), kn.to(cuda), vn.to(cuda)
+            o1 = c1.decode_layer(l, dq, dk, dv, d_cs)
+            o2 = c2.decode_layer(l, dq, dk, dv, d_cs)
+        torch.cuda.synchronize()
+        assert int(c1._row_flags.min()) == 1, "every row's word is raised once its table is written"
+        for l in range(2):
+            assert torch.equal(c1.position_ids[l], c2.position_ids[l]) and torch.equal(c1.cnts_all[l], c2.cnts_all[l])
+            assert torch.equal(c1.k_cache_buffer[l], c2.k_cache_buffer[l]), f"K bytes differ at step {step} layer {l}"
+            assert torch.equal(c1.v_cache_buffer[l], c2.v_cache_buffer[l]), f"V bytes differ at step {step} layer {l}"
+        assert torch.equal(o1, o2), f"attention output differs at step {step}"
