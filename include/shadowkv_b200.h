@@ -187,6 +187,11 @@ typedef struct skv_geom {
                          * row's word instead of for the completion of the whole selection grid.  Pass the SAME pointer
                          * to skv_select_chunks / skv_select_from_scores and to the skv_fetch_rebuild_attend call that
                          * follows it on the stream; NULL (all other entry points ignore it): plain dependent launches */
+  const int32_t *wait_flags;      /* optional, kv-head split (skv_exchange): the scoring launch (skv_score_landmarks /  */
+  const int32_t *wait_epoch_dev;  /* skv_select_chunks) first waits until wait_flags[0 .. wait_count) >= *wait_epoch_dev */
+  int32_t wait_count;             /* -- the previous layer's gathered attention output is then complete in this rank's  */
+  int32_t reserved;               /* buffer, which is what the layer's query depends on -- instead of a skv_wait_flags  */
+                                  /* launch of its own between the layers.  NULL / 0: no wait                           */
 } skv_geom;
 
 /* The scoring launch is a programmatic dependent launch that streams the landmarks into shared memory BEFORE it

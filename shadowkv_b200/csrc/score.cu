@@ -26,7 +26,8 @@ int launch_score_select(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
 // score_mma.cu: TMA + tcgen05 scoring (product path)
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
-                          int64_t buf_rows, bool dynamic_landmarks);
+                          int64_t buf_rows, bool dynamic_landmarks, const int32_t *wait_flags = nullptr,
+                          const int32_t *wait_epoch_dev = nullptr, int wait_count = 0);
 
 constexpr int kScoreThreads = 256;   // 8 warps
 
@@ -632,11 +633,16 @@ int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
   }
   SelectWorkspace w = carve(g, workspace);
   // scale = 1/sqrt(128), the constant the reference hard-codes (kv_cache.py:1017)
+  if (g->wait_flags && (!g->wait_epoch_dev || g->wait_count < 1 || g->wait_count > 32)) {
+    set_error("score_landmarks: wait_flags needs wait_epoch_dev and 1..32 flags"); return SKV_ERR_ARGUMENT;
+  }
   static const bool simt = [] { const char *e = getenv("SKV_SCORE_IMPL"); return e && e[0] == '1'; }();
   if (!simt)   // product path: TMA ring + tcgen05 (score_mma.cu); SKV_SCORE_IMPL=1 selects the SIMT cross-check
     return launch_scores_tcgen05(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                                  g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append,
-                                 g->buf_len, (g->flags & SKV_GEOM_DYNAMIC_LANDMARKS) != 0);
+                                 g->buf_len, (g->flags & SKV_GEOM_DYNAMIC_LANDMARKS) != 0, g->wait_flags,
+                                 g->wait_epoch_dev, g->wait_count);
+  if (g->wait_flags) { set_error("score_landmarks: the SIMT cross-check kernel has no flag wait"); return SKV_ERR_UNSUPPORTED; }
   return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                            g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append, g->buf_len);
 }
@@ -691,7 +697,7 @@ int skv_select_chunks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *land
   // the two launches below at every batch (a row's cluster cannot span enough SMs to keep HBM busy),
   // so it is NOT the product path; shapes it does not take fall through
   const char *fe = getenv("SKV_FUSED_SELECT"), *se = getenv("SKV_SCORE_IMPL");      // read per call: tests flip it
-  const bool fused = (fe && fe[0] == '1') && !(se && se[0] == '1') && !g->row_flags;   // the experiment has no row hand-over
+  const bool fused = (fe && fe[0] == '1') && !(se && se[0] == '1') && !g->row_flags && !g->wait_flags;   // the experiment has neither hand-over
   if (fused) {
     const int rc = launch_score_select(g, q, landmarks, landmark_idx, resident, offsets, cnts, selected_out, score_out,
                                        append, as_stream(stream));

@@ -36,6 +36,8 @@ struct ScoreMmaParams {
   float alpha;
   skv_append ap;
   int64_t buf_rows;
+  const int32_t *wait_flags, *wait_epoch_dev;   // kv-head split: peers' flags of the previous layer (skv_geom.wait_flags)
+  int wait_count;
 };
 
 template <int kSmStages, int kCtasPerSm>
@@ -79,6 +81,18 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   if (warp == 1) tcgen05_alloc(tmem_slot, 32);
   // everything below touches data of the predecessor (q, the K/V buffers, the score scratch)
   pdl_wait();
+  if (p.wait_flags) {
+    // kv-head split: the query of this layer depends on the previous layer's GATHERED attention output; every peer raises
+    // its flag (release, system scope) behind its last row's stores into this rank's buffer.  Lane = peer rank.
+    if (int(threadIdx.x) < p.wait_count) {
+      const int want = *p.wait_epoch_dev;
+      int seen;
+      do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.wait_flags + threadIdx.x) : "memory");
+      } while (seen < want);
+    }
+    __syncthreads();
+  }
 
   // fused append (a2): the first CTA of every (b,h) writes the new token's K and V rows
   if (p.ap.k_new && cx == 0 && warp == 2) {
@@ -221,7 +235,8 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
 
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
-                          int64_t buf_rows, bool dynamic_landmarks) {
+                          int64_t buf_rows, bool dynamic_landmarks, const int32_t *wait_flags,
+                          const int32_t *wait_epoch_dev, int wait_count) {
   CUtensorMap map;
   int rc = make_tensor_map_2d(&map, lm, uint64_t(BH) * N, kHeadDim, kSmTileRows, 64);
   if (rc) return rc;
@@ -230,6 +245,9 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
   p.dynamic_lm = dynamic_landmarks ? 1 : 0;
   if (append) p.ap = *append;
+  if (wait_flags && wait_epoch_dev && wait_count > 0) {
+    p.wait_flags = wait_flags; p.wait_epoch_dev = wait_epoch_dev; p.wait_count = wait_count < 32 ? wait_count : 32;
+  }
   // two (or three) CTAs per SM; every CTA of a row strides over that row's tiles
   static const int stages = [] { const char *e = getenv("SKV_SCORE_STAGES"); return (e && e[0] == '2') ? 2 : 3; }();
   static const int target = [] {

@@ -18,6 +18,8 @@ device (``ShadowKVCache_CPU.gen_dev`` / ``kv_len_dev``) so the same graph is val
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import parallel
@@ -44,7 +46,6 @@ class DecodeStepGraph:
         self.xchg = None
         self.exchange = "none"
         if gather_heads:
-            import os
             import torch.distributed as dist
             hooks_free = cache.fused_fetch_rebuild and cache.can_fuse_attend()
             if hooks_free and os.environ.get("SKV_HEAD_EXCHANGE", "p2p") != "nccl":
@@ -52,7 +53,7 @@ class DecodeStepGraph:
                 self.xchg = parallel.HeadExchange(L, B, Hq, dev, D)
                 self.out_all = self.xchg.out_all
                 self.exchange = ("P2P stores over NVLink from the merging CTA of skv_fetch_rebuild_attend into every rank's "
-                                 "symmetric-memory buffer + one flag wait per layer (no collective launch)")
+                                 "symmetric-memory buffer; the next layer's scoring launch waits for the peers' flags (no collective launch)")
             else:
                 world = dist.get_world_size() if dist.is_initialized() else 1
                 self.out_all = torch.zeros(L, world, B, 1, Hq, D, dtype=dt, device=dev)
@@ -74,8 +75,9 @@ class DecodeStepGraph:
             per_layer = 3                      # score (+append), select, fetch + rebuild + attention
         self.launches_per_step = L * (per_layer + (1 if cache.hbm_store_ways else 0))
         self._per_layer = per_layer
+        self.inline_wait = os.environ.get("SKV_HEAD_WAIT", "inline") != "launch"
         if self.xchg is not None:
-            self.launches_per_step += L        # the per-layer flag wait of the peer-store exchange
+            self.launches_per_step += 1 if self.inline_wait else L      # flag-wait launches of the peer-store exchange
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
         self.replays = 0
@@ -96,10 +98,16 @@ class DecodeStepGraph:
     def _body(self):
         c = self.cache
         for l in range(c.num_layers):
+            # peer-store exchange: what consumes a layer's gathered output (o_proj; here the next layer's query) must not
+            # start before every peer's rows have arrived.  Between layers the next scoring launch waits for the flags
+            # itself (SKV_HEAD_WAIT=launch keeps a flag-wait launch per layer); the last layer gets the wait launch
+            inline_wait = self.xchg is not None and self.inline_wait
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
-                           device_counters=True, exchange=self.xchg.struct(l) if self.xchg is not None else None)
+                           device_counters=True, exchange=self.xchg.struct(l) if self.xchg is not None else None,
+                           wait_for=self.xchg.wait_spec(l - 1) if inline_wait and l > 0 else None)
             if self.xchg is not None:
-                self.xchg.wait(l)          # what consumes the layer's gathered output (o_proj) must not start before it
+                if not inline_wait or l == c.num_layers - 1:
+                    self.xchg.wait(l)
             elif self.gather:
                 parallel.gather_heads(self.out_d[l], self.out_all[l])
         c.join_side_streams()

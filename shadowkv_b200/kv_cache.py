@@ -643,7 +643,7 @@ class ShadowKVCache_CPU:
         return out
 
     def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
-                     device_counters=False, after_select=None, before_attention=None, exchange=None):
+                     device_counters=False, after_select=None, before_attention=None, exchange=None, wait_for=None):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
         query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
@@ -676,11 +676,17 @@ class ShadowKVCache_CPU:
         if fused_attend and self._row_flags is not None:
             # selection -> fetch + rebuild + attention hand over per (b, kv head) row instead of per grid
             g.row_flags = self._row_flags[layer_idx].data_ptr()
+        if wait_for is not None:
+            # kv-head split: (flags pointer, count, epoch pointer) of the PREVIOUS layer's exchange; the scoring launch
+            # waits for them itself (skv_geom.wait_flags) instead of a flag-wait launch between the layers
+            g.wait_flags, g.wait_count, g.wait_epoch_dev = wait_for
         try:
             pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
         except Exception:
             g.row_flags = None
             raise
+        finally:
+            g.wait_flags, g.wait_count, g.wait_epoch_dev = None, 0, None
         if after_select is not None:
             # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
             # idle; the runner uses the window to pull the next dense weights into L2 on its own stream

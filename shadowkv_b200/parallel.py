@@ -157,6 +157,11 @@ class HeadExchange:
         check(lib.skv_wait_flags(self.flags.data_ptr() + layer * self.world * 4, self.world, self.epoch.data_ptr(),
                                  torch.cuda.current_stream().cuda_stream), "wait_flags")
 
+    def wait_spec(self, layer: int):
+        """(flags pointer, count, epoch pointer) for ``decode_layer(wait_for=...)`` of the layer BEHIND `layer`: its scoring
+        launch then waits for `layer`'s gathered output itself, with no launch of its own in between."""
+        return (self.flags.data_ptr() + layer * self.world * 4, self.world, self.epoch.data_ptr())
+
     def advance(self):
         """Next token: epoch += 1 on the device (part of the captured step; never rewound)."""
         self.epoch.add_(1)
