@@ -322,16 +322,17 @@ int skv_fetch_and_rebuild(const skv_geom *geom, const skv_bf16 *v_host, int64_t 
 /* kv-head split of a batch-1 long context over the GPUs of one node: every rank attends over its
  * H/N kv heads; the only exchange is the layer's attention output [B, Hq/N, 128].  Instead of a collective launch per
  * layer, the CTA that merges a row inside skv_fetch_rebuild_attend stores the row's output straight into EVERY rank's
- * gathered buffer over NVLink (peer-mapped pointers, e.g. torch symmetric memory), and the rank's last row of the layer
- * raises the rank's flag on every peer (system-scope release) with the value of *epoch_dev (a device counter the caller
- * advances once per token and never rewinds).  skv_wait_flags is the consumer side. */
+ * gathered buffer over NVLink (peer-mapped pointers, e.g. torch symmetric memory) and then raises THAT ROW's flag word
+ * on every peer (one system-scope fence, then the stores) with the value of *epoch_dev (a device counter the caller
+ * advances once per token and never rewinds): no counting of rows, no second fence on the chain.  The consumer waits for
+ * all N * B * H/N row words of the layer: skv_geom.wait_flags (inside the next scoring launch) or skv_wait_flags. */
 #define SKV_MAX_PEERS 8
 typedef struct skv_exchange {
   int32_t world;                      /* number of ranks (0: no exchange)                                              */
   int32_t rank;                       /* this rank                                                                      */
   void *peer_out[SKV_MAX_PEERS];      /* rank r's buffer slot for THIS rank's output of the layer: [B, Hq/N, 128] bf16  */
-  int32_t *peer_flags[SKV_MAX_PEERS]; /* rank r's flag word for (layer, this rank)                                      */
-  int32_t *rows_done;                 /* local scratch word of the layer, zero between launches                         */
+  int32_t *peer_flags[SKV_MAX_PEERS]; /* rank r's flag words for (layer, this rank): [B * H/N], one per local row       */
+  int32_t *rows_done;                 /* unused (kept for layout compatibility); may be NULL                            */
   const int32_t *epoch_dev;           /* device counter: value the flags take for the current token                     */
 } skv_exchange;
 
@@ -356,8 +357,8 @@ int skv_fetch_rebuild_attend(const skv_geom *geom, const skv_bf16 *v_store, int6
                              const int32_t *kv_len_dev, float scale, void *workspace,
                              const skv_exchange *exchange, skv_stream_t stream);
 
-/* Blocks `stream` (one tiny kernel) until flags[0..n) >= *epoch_dev: the outputs of all n ranks for that layer have
- * landed in this rank's gathered buffer. */
+/* Blocks `stream` (one tiny kernel) until flags[0..n) >= *epoch_dev (n <= 4096 row words: the outputs of all ranks for
+ * that layer have landed in this rank's gathered buffer). */
 int skv_wait_flags(const int32_t *flags, int n, const int32_t *epoch_dev, skv_stream_t stream);
 
 /* ======================================================================

@@ -213,33 +213,28 @@ __device__ __forceinline__ void fa_merge(const FaParams &p, const int bh, const 
     for (int r = 0; r < p.xc.world; ++r) *reinterpret_cast<uint2 *>(static_cast<skv_bf16 *>(p.xc.peer_out[r]) + at) = packed;
   }
   if (p.xc.world > 0) {
-    // The rank's last row of the layer raises this rank's flag on every peer: every merging CTA fences its remote
-    // stores at system scope and counts itself in; the one that completes the count fences again and releases.
-    __threadfence_system();
+    // The row's flag word on every peer: the barrier makes the CTA's remote stores precede thread 0's fence (fences are
+    // cumulative), one system-scope fence orders them in front of the flag stores.
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int prev = atomicAdd(p.xc.rows_done, 1);
-      if (prev == p.BH - 1) {
-        *p.xc.rows_done = 0;
-        __threadfence_system();
-        const int epoch = *p.xc.epoch_dev;
-        for (int r = 0; r < p.xc.world; ++r)
-          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.xc.peer_flags[r]), "r"(epoch) : "memory");
-      }
+      const int epoch = *p.xc.epoch_dev;
+      __threadfence_system();
+      for (int r = 0; r < p.xc.world; ++r)
+        asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p.xc.peer_flags[r] + bh), "r"(epoch) : "memory");
     }
   }
 }
 
-// kv-head split: wait until every rank's flag of the layer has reached the current epoch (the gathered attention output
-// of the layer is then complete in THIS rank's buffer).  One warp, lane = peer rank.
-__global__ void __launch_bounds__(32) wait_flags_kernel(const int32_t *flags, int n, const int32_t *epoch_dev) {
+// kv-head split: wait until every row word of the layer has reached the current epoch (the gathered attention output of
+// the layer is then complete in THIS rank's buffer).
+__global__ void __launch_bounds__(128) wait_flags_kernel(const int32_t *flags, int n, const int32_t *epoch_dev) {
   pdl_launch_dependents();
   pdl_wait();
-  if (int(threadIdx.x) < n) {
-    const int want = *epoch_dev;
+  const int want = *epoch_dev;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     int seen;
     do {
-      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + threadIdx.x) : "memory");
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + i) : "memory");
     } while (seen < want);
   }
 }
@@ -926,8 +921,8 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
   p.q = q; p.out = out; p.kv_len_dev = kv_len_dev; p.kv_len = kv_len;
   p.row_flags = g->row_flags;
   if (exchange && exchange->world > 0) {
-    if (exchange->world > SKV_MAX_PEERS || !exchange->rows_done || !exchange->epoch_dev) {
-      set_error("fetch_rebuild_attend: exchange needs 1..%d peers, rows_done and epoch_dev", SKV_MAX_PEERS); return SKV_ERR_ARGUMENT;
+    if (exchange->world > SKV_MAX_PEERS || !exchange->epoch_dev) {
+      set_error("fetch_rebuild_attend: exchange needs 1..%d peers and epoch_dev", SKV_MAX_PEERS); return SKV_ERR_ARGUMENT;
     }
     for (int r = 0; r < exchange->world; ++r)
       if (!exchange->peer_out[r] || !exchange->peer_flags[r]) { set_error("fetch_rebuild_attend: null peer pointer"); return SKV_ERR_ARGUMENT; }
@@ -984,8 +979,8 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
 }
 
 int skv_wait_flags(const int32_t *flags, int n, const int32_t *epoch_dev, skv_stream_t stream) {
-  if (!flags || !epoch_dev || n < 1 || n > 32) { set_error("wait_flags: bad argument"); return SKV_ERR_ARGUMENT; }
-  cudaError_t e = launch_kernel(wait_flags_kernel, dim3(1), dim3(32), 0, as_stream(stream), /*pdl=*/true, flags, n, epoch_dev);
+  if (!flags || !epoch_dev || n < 1 || n > 4096) { set_error("wait_flags: bad argument"); return SKV_ERR_ARGUMENT; }
+  cudaError_t e = launch_kernel(wait_flags_kernel, dim3(1), dim3(128), 0, as_stream(stream), /*pdl=*/true, flags, n, epoch_dev);
   if (e != cudaSuccess) { set_error("wait_flags_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("wait_flags_kernel");
 }

@@ -633,8 +633,8 @@ int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
   }
   SelectWorkspace w = carve(g, workspace);
   // scale = 1/sqrt(128), the constant the reference hard-codes (kv_cache.py:1017)
-  if (g->wait_flags && (!g->wait_epoch_dev || g->wait_count < 1 || g->wait_count > 32)) {
-    set_error("score_landmarks: wait_flags needs wait_epoch_dev and 1..32 flags"); return SKV_ERR_ARGUMENT;
+  if (g->wait_flags && (!g->wait_epoch_dev || g->wait_count < 1 || g->wait_count > 4096)) {
+    set_error("score_landmarks: wait_flags needs wait_epoch_dev and 1..4096 flags"); return SKV_ERR_ARGUMENT;
   }
   static const bool simt = [] { const char *e = getenv("SKV_SCORE_IMPL"); return e && e[0] == '1'; }();
   if (!simt)   // product path: TMA ring + tcgen05 (score_mma.cu); SKV_SCORE_IMPL=1 selects the SIMT cross-check

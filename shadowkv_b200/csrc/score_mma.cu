@@ -83,12 +83,12 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   pdl_wait();
   if (p.wait_flags) {
     // kv-head split: the query of this layer depends on the previous layer's GATHERED attention output; every peer raises
-    // its flag (release, system scope) behind its last row's stores into this rank's buffer.  Lane = peer rank.
-    if (int(threadIdx.x) < p.wait_count) {
-      const int want = *p.wait_epoch_dev;
+    // a flag word per row (system scope) behind the row's stores into this rank's buffer.
+    const int want = *p.wait_epoch_dev;
+    for (int i = threadIdx.x; i < p.wait_count; i += kSmThreads) {
       int seen;
       do {
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.wait_flags + threadIdx.x) : "memory");
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.wait_flags + i) : "memory");
       } while (seen < want);
     }
     __syncthreads();
@@ -246,7 +246,7 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   p.dynamic_lm = dynamic_landmarks ? 1 : 0;
   if (append) p.ap = *append;
   if (wait_flags && wait_epoch_dev && wait_count > 0) {
-    p.wait_flags = wait_flags; p.wait_epoch_dev = wait_epoch_dev; p.wait_count = wait_count < 32 ? wait_count : 32;
+    p.wait_flags = wait_flags; p.wait_epoch_dev = wait_epoch_dev; p.wait_count = wait_count;
   }
   // two (or three) CTAs per SM; every CTA of a row strides over that row's tiles
   static const int stages = [] { const char *e = getenv("SKV_SCORE_STAGES"); return (e && e[0] == '2') ? 2 : 3; }();

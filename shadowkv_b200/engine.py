@@ -50,7 +50,7 @@ class DecodeStepGraph:
             hooks_free = cache.fused_fetch_rebuild and cache.can_fuse_attend()
             if hooks_free and os.environ.get("SKV_HEAD_EXCHANGE", "p2p") != "nccl":
                 # peer stores from inside the fused launch + one flag wait per layer (parallel.HeadExchange)
-                self.xchg = parallel.HeadExchange(L, B, Hq, dev, D)
+                self.xchg = parallel.HeadExchange(L, B, Hq, dev, D, rows=B * H)
                 self.out_all = self.xchg.out_all
                 self.exchange = ("P2P stores over NVLink from the merging CTA of skv_fetch_rebuild_attend into every rank's "
                                  "symmetric-memory buffer; the next layer's scoring launch waits for the peers' flags (no collective launch)")

@@ -100,24 +100,26 @@ def heads_to_model_order(gathered: torch.Tensor) -> torch.Tensor:
 
 class HeadExchange:
     """Peer-store exchange of the kv-head split: every rank's gathered buffer
-    ``out_all [layers, world, B, 1, Hq/world, D]`` and flag words ``flags [layers, world]`` live in symmetric memory
+    ``out_all [layers, world, B, 1, Hq/world, D]`` and flag words ``flags [layers, world, rows]`` live in symmetric memory
     (``torch.distributed._symmetric_memory``: the same allocation mapped into every rank of the node); the CTA that
     merges a row inside ``skv_fetch_rebuild_attend`` stores the row's attention output into EVERY rank's buffer over
-    NVLink and the rank's last row of a layer raises the rank's flag everywhere; ``wait(layer)`` blocks the stream until all
-    ranks' flags of the layer carry the current epoch.  No collective launch on the per-layer chain.
+    NVLink and then raises that row's flag word everywhere; ``wait(layer)`` / ``wait_spec(layer)`` wait until all
+    row words of the layer carry the current epoch.  No collective launch on the per-layer chain.
     world == 1 (or no process group): plain device tensors and self pointers -- the same kernel path, used by the tests."""
 
-    def __init__(self, layers: int, batch: int, hq_local: int, device, head_dim: int = 128, group=None):
+    def __init__(self, layers: int, batch: int, hq_local: int, device, head_dim: int = 128, group=None, rows: int = 1):
+        """rows: local (b, kv head) rows of a layer = flag words per (layer, rank): B * H/world."""
         import torch.distributed as dist
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         if self.world > 8:
             raise ValueError("the peer-store exchange handles up to 8 ranks of one node")
         self.layers, self.row_elems = layers, batch * hq_local * head_dim
+        self.rows = int(rows)
         shape = (layers, self.world, batch, 1, hq_local, head_dim)
         if self.world == 1:
             self.out_all = torch.zeros(shape, dtype=torch.bfloat16, device=device)
-            self.flags = torch.zeros(layers, 1, dtype=torch.int32, device=device)
+            self.flags = torch.zeros(layers, 1, self.rows, dtype=torch.int32, device=device)
             self._out_ptrs, self._flag_ptrs = [self.out_all.data_ptr()], [self.flags.data_ptr()]
         else:
             import torch.distributed._symmetric_memory as symm
@@ -127,7 +129,7 @@ class HeadExchange:
             except Exception:  # noqa: BLE001  -- newer builds enable it implicitly
                 pass
             self.out_all = symm.empty(shape, dtype=torch.bfloat16, device=device)
-            self.flags = symm.empty((layers, self.world), dtype=torch.int32, device=device)
+            self.flags = symm.empty((layers, self.world, self.rows), dtype=torch.int32, device=device)
             self.out_all.zero_()
             self.flags.zero_()
             torch.cuda.synchronize(device)
@@ -136,7 +138,6 @@ class HeadExchange:
             self._handles = (h_out, h_flag)
             dist.barrier(grp)
             torch.cuda.synchronize(device)
-        self.rows_done = torch.zeros(layers, dtype=torch.int32, device=device)
         self.epoch = torch.ones(1, dtype=torch.int32, device=device)       # flags start at 0 < epoch 1
 
     def struct(self, layer: int):
@@ -146,21 +147,21 @@ class HeadExchange:
         slot = (layer * self.world + self.rank)
         for r in range(self.world):
             ex.peer_out[r] = self._out_ptrs[r] + slot * self.row_elems * 2
-            ex.peer_flags[r] = self._flag_ptrs[r] + slot * 4
-        ex.rows_done = self.rows_done.data_ptr() + layer * 4
+            ex.peer_flags[r] = self._flag_ptrs[r] + slot * self.rows * 4
         ex.epoch_dev = self.epoch.data_ptr()
         return ex
 
     def wait(self, layer: int):
         """Block the current stream until every rank's output of `layer` (current epoch) is in this rank's buffer."""
         from ._lib import check, lib
-        check(lib.skv_wait_flags(self.flags.data_ptr() + layer * self.world * 4, self.world, self.epoch.data_ptr(),
+        check(lib.skv_wait_flags(self.flags.data_ptr() + layer * self.world * self.rows * 4, self.world * self.rows,
+                                 self.epoch.data_ptr(),
                                  torch.cuda.current_stream().cuda_stream), "wait_flags")
 
     def wait_spec(self, layer: int):
         """(flags pointer, count, epoch pointer) for ``decode_layer(wait_for=...)`` of the layer BEHIND `layer`: its scoring
         launch then waits for `layer`'s gathered output itself, with no launch of its own in between."""
-        return (self.flags.data_ptr() + layer * self.world * 4, self.world, self.epoch.data_ptr())
+        return (self.flags.data_ptr() + layer * self.world * self.rows * 4, self.world * self.rows, self.epoch.data_ptr())
 
     def advance(self):
         """Next token: epoch += 1 on the device (part of the captured step; never rewound)."""

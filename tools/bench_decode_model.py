@@ -262,13 +262,29 @@ def main():
     ap.add_argument("--model", default="llama-3.1-8b")
     ap.add_argument("--no-split-qkv", action="store_true")
     ap.add_argument("--store-ways", type=int, default=0, help="also time the native loop with an HBM chunk store")
+    ap.add_argument("--v-residency", default="host", choices=["host", "hbm", "auto"],
+                    help="where the chunk-major V store lives (ShadowKVCache_CPU(v_residency=)); 'host' = the reference's")
+    ap.add_argument("--modes", default="hot,native,library")
     args = ap.parse_args()
-    m = Llama(args.model, batch_size=args.batch, max_length=args.ctx, device="cuda:0", num_layers=args.layers or None,
-              hbm_store_ways=args.hbm_store_ways, l2_prefetch_mb=args.l2_prefetch_mb,
-              next_prefetch_mb=args.next_prefetch_mb, split_qkv=not args.no_split_qkv)
+    import time
+    from shadowkv_b200.kv_cache import ShadowKVCache_CPU
+    t0 = time.time()
+    shape = synth.MODELS[args.model]
+    L = args.layers or shape.num_hidden_layers
+    cache = ShadowKVCache_CPU(shape.config(L), batch_size=args.batch, max_length=args.ctx, device="cuda:0",
+                              hbm_store_ways=args.hbm_store_ways, v_residency=args.v_residency)
+    m = Llama(args.model, batch_size=args.batch, max_length=args.ctx, device="cuda:0", num_layers=L, kv_cache=cache,
+              l2_prefetch_mb=args.l2_prefetch_mb, next_prefetch_mb=args.next_prefetch_mb, split_qkv=not args.no_split_qkv)
     install_synthetic_state(m, args.ctx)
-    print(json.dumps(whole_model(m, steps=args.steps, warmup=args.warmup, noise=args.noise, coupled=args.coupled,
-                                 ops=not args.skip_ops, store_ways=args.store_ways)))
+    out = whole_model(m, steps=args.steps, warmup=args.warmup, noise=args.noise, coupled=args.coupled,
+                      modes=tuple(args.modes.split(",")), ops=not args.skip_ops, store_ways=args.store_ways)
+    v, other = cache.state_bytes()
+    out["v_residency"] = cache.v_residency
+    out["v_store_GB"], out["other_decode_state_GB"] = v / 1e9, other / 1e9
+    out["setup_s"] = round(time.time() - t0, 1)
+    out["published_reference"] = ("reference test/e2e.py:161-166 / index.html:212: Llama-3.1-8B, 122K, ShadowKV, batch 24, gen_len 100 on "
+                                  "one A100-80GB: 245.9 tokens/s (other hardware; context only)")
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
