@@ -288,8 +288,10 @@ __device__ __forceinline__ void block_excl_scan2(int a, int b, int *wa, int *wb,
   tot_b = wb[kWarps];
 }
 
-template <int S, bool kInPlace>
-__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? S : 256)
+// kT threads per CTA: max(S, 256) normally; 512 when a CTA's slice is long (contexts of 256K tokens and more), where the
+// key pass (G exponentials per landmark) is what the kernel spends its time on.
+template <int S, bool kInPlace, int kT>
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT)
     select_kernel(const skv_bf16 *__restrict__ scores,        // [BH, G, ldn] bf16 scaled dot products
                   const float *__restrict__ part_max, const float *__restrict__ part_sum,   // [BH, G, T]
                   const int64_t *__restrict__ landmark_idx,   // [BH, N]
@@ -299,7 +301,8 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(S > 256 ? 
                   skv_bf16 *__restrict__ score_out,           // [BH, N] or null
                   int32_t *row_flags,                         // [BH] or null: per-row hand-over to the fetch launch
                   int G, int N, int ldn, int T, int per) {
-  constexpr int kThreads = S > 256 ? S : 256;
+  constexpr int kThreads = kT;
+  static_assert(kT >= S && kT >= 256 && kT % 32 == 0, "one thread per table entry and per histogram bin");
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char sel_smem[];
   int *whist1 = reinterpret_cast<int *>(sel_smem);                                 // [kWarps][256] level 1
@@ -658,20 +661,30 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const int BH = g->batch * g->kv_heads, G = g->q_groups, N = g->n_landmarks;
   SelectWorkspace w = carve(g, workspace);
   const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
-#define SKV_SEL_LAUNCH(SV, IP)                                                                                    \
+#define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
   {                                                                                                              \
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP>), smem, "select_kernel")) return rc; \
-    cudaError_t e = launch_kernel(select_kernel<SV, IP>, dim3(kSelCluster, BH), dim3(kThreads), smem, st, true,     \
+    const int smem = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                                   \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT>), smem, "select_kernel")) return rc; \
+    cudaError_t e = launch_kernel(select_kernel<SV, IP, KT>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,       \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
                                   score_out, g->row_flags, G, N, w.ldn, w.T, per);                                \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL(SV)                                                                                              \
   case SV: {                                                                                                     \
-    constexpr int kThreads = SV > 256 ? SV : 256;                                                                \
-    const int smem = 2 * (kThreads / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                           \
-    if (g->table_mode) SKV_SEL_LAUNCH(SV, true) else SKV_SEL_LAUNCH(SV, false)                                   \
+    constexpr int kBase = SV > 256 ? SV : 256, kWide = SV > 512 ? SV : 512;                                      \
+    if (wide2 && kBase != 1024) {                                                                                \
+      if (g->table_mode) SKV_SEL_LAUNCH(SV, true, 1024) else SKV_SEL_LAUNCH(SV, false, 1024)                     \
+    } else if (wide && kWide != kBase) {                                                                         \
+      if (g->table_mode) SKV_SEL_LAUNCH(SV, true, kWide) else SKV_SEL_LAUNCH(SV, false, kWide)                   \
+    } else {                                                                                                     \
+      if (g->table_mode) SKV_SEL_LAUNCH(SV, true, kBase) else SKV_SEL_LAUNCH(SV, false, kBase)                   \
+    }                                                                                                            \
   } break;
+  const char *wf = getenv("SKV_SELECT_WIDE_FROM");          // read per call: tests and A/B runs flip it
+  const bool wide = per >= ((wf && *wf) ? atoi(wf) : 3072);  // landmarks per CTA from which 512 threads pay
+  const char *wf2 = getenv("SKV_SELECT_WIDE2_FROM");
+  const bool wide2 = per >= ((wf2 && *wf2) ? atoi(wf2) : 6144);  // ... and 1024 threads
   switch (g->select) {
     SKV_SEL(128) SKV_SEL(256) SKV_SEL(512) SKV_SEL(1024)
     default: return SKV_ERR_UNSUPPORTED;

@@ -210,3 +210,43 @@ def test_fused_score_select_experiment_agrees_with_the_two_launches(cuda, monkey
         nm = (S - c1.long()).view(-1, 1)
         live = torch.arange(S).view(1, -1) < nm                   # offsets[i] is defined for i < number of misses
         assert torch.equal(o1.view(B * H, S)[live], o2.view(B * H, S)[live])
+
+
+@pytest.mark.parametrize("model,B,N,S", [("llama-3-8b-1m", 2, 65480, 256), ("yi-9b-200k", 2, 25544, 128),
+                                         ("llama-3.1-8b", 1, 15560, 256)])
+def test_select_wide_cta_equals_base(cuda, monkeypatch, model, B, N, S):
+    """select_kernel with 512 threads per CTA (long slices: contexts of 256K tokens and more) against the 256-thread
+    instantiation on the same scores: same keys, same selection, same chunk table, bit for bit."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    shape = synth.MODELS[model]
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(N + S + B + 1)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16).to(cuda)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S]] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448, table_mode=1)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    d_idx = idx.to(cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib.skv_score_landmarks(C.byref(geom), q.data_ptr(), lm.data_ptr(), ws.data_ptr(), None, st), "score")
+    outs = []
+    for wide_from in ("1", "1000000"):
+        monkeypatch.setenv("SKV_SELECT_WIDE_FROM", wide_from)
+        res = resident.to(cuda).clone()
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+        _lib.check(_lib.lib.skv_select_from_scores(C.byref(geom), d_idx.data_ptr(), res.data_ptr(), off.data_ptr(),
+                                                   cnt.data_ptr(), sel.data_ptr(), score.data_ptr(), ws.data_ptr(), st),
+                   "select_from_scores")
+        torch.cuda.synchronize()
+        outs.append((res.cpu(), off.cpu(), cnt.cpu(), sel.cpu(), score.cpu()))
+    (r1, o1, c1, s1, k1), (r2, o2, c2, s2, k2) = outs
+    assert torch.equal(k1.view(torch.int16), k2.view(torch.int16)), "selection keys differ"
+    assert torch.equal(s1, s2) and torch.equal(c1, c2) and torch.equal(r1, r2), "selection / chunk table differs"
+    live = torch.arange(S).view(1, -1) < (S - c1.long()).view(-1, 1)
+    assert torch.equal(o1.view(B * H, S)[live], o2.view(B * H, S)[live])
