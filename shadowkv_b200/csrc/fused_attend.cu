@@ -242,13 +242,14 @@ __global__ void __launch_bounds__(128) wait_flags_kernel(const int32_t *flags, i
 // ------------------------------------------------------------------------------------------------
 // Tile CTA: 16 entries of the miss list of row bh.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, const FaParams &p, const int bh, const int tile,
-                                             unsigned char *smem) {
+__device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, const CUtensorMap *map_u_ptr, const FaParams &p,
+                                             const int bh, const int tile, unsigned char *smem) {
   unsigned char *sA = smem;                                    // n_slabs x 16 KiB (U rows)
   unsigned char *sB = smem + p.n_slabs * kFaSlabBytes;         // n_slabs x 16 KiB (SV panel)
   // the operand area [0, tail_off) (tail_off >= 96 KiB) is reused once the MMA has retired: scratch at 0, V staging behind it
   unsigned char *tail = smem + p.tail_off;
-  float *s_q = reinterpret_cast<float *>(tail);                // [8][128], pre-scaled by scale * log2(e)
+  unsigned char *sQ = tail;                                    // q as the B operand of the q.K MMA: 2 slabs x [16 head
+                                                               // rows (zero padded) x 64 dims] bf16, 128-byte swizzled
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail + 4096);
   uint64_t *mma_bar = full_bar + kFaMaxSlabs;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 1);
@@ -257,6 +258,7 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
   float *s_red = reinterpret_cast<float *>(s_slots + kFaTileChunks);   // [4 warps][8 heads][2]
   int *s_flag = reinterpret_cast<int *>(s_red + 4 * kFaMaxG * 2);      // the CTA's ticket
   uint64_t *full_v = reinterpret_cast<uint64_t *>(s_flag + 2);         // [2]
+  uint64_t *full_a = full_v + 2;                                       // [kFaMaxSlabs] U rows of the tile, per slab
   // scratch (valid after mma_bar): probabilities, P.V staging, merge weights -- 28.1 KiB at offset 0
   float *s_p = reinterpret_cast<float *>(smem);                // [128 rows][8 heads]           4 KiB
   float *s_o = s_p + kFaTileRows * kFaMaxG;                    // [4 row groups][8 heads][128] 16 KiB
@@ -275,12 +277,20 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
   if (tid == 0) SKV_STAMP_NS(tr, 0);
 
   if (tid == 0) {
-    for (int s = 0; s < p.n_slabs; ++s) mbarrier_init(&full_bar[s], 1);
+    for (int s = 0; s < p.n_slabs; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&full_a[s], kFaThreads / 32); }
     mbarrier_init(mma_bar, 1);
     mbarrier_init(&full_v[0], 1);
     mbarrier_init(&full_v[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_sv_ptr) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map_u_ptr) : "memory");
+    // The SV panel of the row is static state (written at prefill): it is requested ahead of the wait for the selection,
+    // so the MMA finds it in shared memory.  A tile that turns out to be beyond the miss list waits for it before it
+    // leaves (shared memory with a bulk copy in flight must not be handed to the next CTA).
+    for (int s = 0; s < p.n_slabs; ++s) {
+      mbarrier_expect_tx(&full_bar[s], kFaSlabBytes);
+      tma_load_2d(sB + s * kFaSlabBytes, map_sv_ptr, s * 64, bh * kHeadDim, &full_bar[s]);
+    }
   }
   if (warp == 0) tcgen05_alloc(tmem_slot, 128);
   // ---- everything below reads what the selection kernel (and, through it, its predecessors) wrote -------------------
@@ -297,10 +307,11 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
     s_ids[tid] = on ? id : -1;
     s_slots[tid] = on ? slot : 0;
   }
-  if (tid >= 128) {
-    const int d = tid - 128;
-    for (int g = 0; g < G; ++g)
-      s_q[g * kHeadDim + d] = bf16_bits_to_f32(p.q[(size_t(bh) * G + g) * kHeadDim + d]) * p.scale_log2;
+  {                                                             // one 16-byte piece of the q operand per thread
+    const int slab = tid >> 7, hr = (tid >> 3) & 15, c = tid & 7;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (hr < G) v = *reinterpret_cast<const int4 *>(p.q + (size_t(bh) * G + hr) * kHeadDim + slab * 64 + c * 8);
+    *reinterpret_cast<int4 *>(sQ + slab * 2048 + (hr >> 3) * 1024 + (hr & 7) * 128 + ((c ^ (hr & 7)) << 4)) = v;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -308,46 +319,41 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
   const uint32_t tmem_base = *tmem_slot;
   if (tile >= n_active) {                                       // nothing of the miss list left for this tile
     if (warp == 0) tcgen05_dealloc(tmem_base, 128);
+    if (tid == 0)
+      for (int s = 0; s < p.n_slabs; ++s) mbarrier_wait(&full_bar[s], 0);      // the SV panel's copies have landed
     return;
   }
   if (tid == 0) SKV_STAMP_NS(tr, 1);
   const int n_parts = n_active + p.n_splits;
 
+  // ================= operands of the tile's 128 x 128 x R product ======================================================
+  // U rows of a chunk are 8 consecutive rows of the [B*L, R] matrix = exactly one 8-row x 64-column box per slab in the
+  // 128-byte-swizzled K-major layout (1 KiB).  A TMA issue is a per-warp (uniform datapath) instruction, so boxes issued
+  // by several lanes of ONE warp go out one after the other (~30 ns each: 48 boxes from one warp were 1.6 us of the
+  // chain; 16-byte cp.async from all threads, the round-1 form, kept the LSU busy for ~2 us): every warp of the CTA
+  // issues the boxes of two chunks and arrives on the slab barriers with its own byte count.  Columns beyond R are zero
+  // filled by the TMA.
+  {
+    const int j = warp * 2 + (lane & 1);                        // lanes 0 / 1: the warp's two chunks
+    const int id = lane < 2 ? s_ids[j] : -1;
+    const unsigned live = __ballot_sync(0xffffffffu, id >= 0);
+    if (lane < p.n_slabs) mbarrier_expect_tx(&full_a[lane], __popc(live) * 1024);
+    __syncwarp();
+    if (id >= 0) {
+      const int row0 = b * p.L + id * kChunkTokens;
+      for (int s = 0; s < p.n_slabs; ++s)
+        tma_load_2d(sA + s * kFaSlabBytes + j * 1024, map_u_ptr, s * 64, row0, &full_a[s]);
+    }
+  }
   if (tid < 128) {
-    // ================= warps 0-3: operands of the tile's 128 x 128 x R product (rebuild_tile of rebuild.cu) ===========
-    {
-      const int ppr = p.R >> 3;                                 // 16-byte pieces per U row
-      const __nv_bfloat16 *ub = p.U + size_t(b) * p.L * p.R;
-      for (int qi = tid; qi < kFaTileRows * ppr; qi += 128) {
-        const int r = qi / ppr, c = qi - r * ppr;
-        const int id = s_ids[r >> 3];
-        if (id >= 0) {
-          const __nv_bfloat16 *src = ub + (size_t(id) * kChunkTokens + (r & 7)) * p.R + c * 8;
-          const uint32_t dst = smem_addr(sA + (c >> 3) * kFaSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        }
-      }
-      if (p.R & 8) {                                            // last 16-column MMA step is half valid: zero the rest
-        const int r = tid, c = ppr;
-        *reinterpret_cast<int4 *>(sA + (c >> 3) * kFaSlabBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) =
-            make_int4(0, 0, 0, 0);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    if (tid == 0) SKV_STAMP_NS(tr, 6);
     if (tid == 0) {
-      for (int s = 0; s < p.n_slabs; ++s) {
-        mbarrier_expect_tx(&full_bar[s], kFaSlabBytes);
-        tma_load_2d(sB + s * kFaSlabBytes, map_sv_ptr, s * 64, bh * kHeadDim, &full_bar[s]);
-      }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    fence_proxy_async_smem();                                   // cp.async wrote through the generic proxy
-    fa_tile_sync();
-    if (tid == 0) {
+      SKV_STAMP_NS(tr, 7);
       int step = 0;
       constexpr uint32_t idesc = umma_idesc_bf16_m128(128);
       for (int s = 0; s < p.n_slabs; ++s) {
         mbarrier_wait(&full_bar[s], 0);
+        mbarrier_wait(&full_a[s], 0);
         tcgen05_fence_after();
         const uint64_t da = umma_desc_k_sw128(smem_addr(sA + s * kFaSlabBytes));
         const uint64_t db = umma_desc_k_sw128(smem_addr(sB + s * kFaSlabBytes));
@@ -427,9 +433,12 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
     __syncwarp();
     if (v_on && lane >= kFaVRingChunks) bulk_load(sV2 + (lane - kFaVRingChunks) * kChunkBytes, v_src_ptr, kChunkBytes, &full_v[1]);
   }
-  float dot[kFaMaxG];
-#pragma unroll
-  for (int g = 0; g < kFaMaxG; ++g) dot[g] = 0.f;
+  // The post-RoPE rows go to their slots in the K buffer AND, as bf16 in the swizzled K-major layout, into the operand
+  // area (free since the rebuild MMA retired) as the A operand of a second tcgen05.mma: S[key][head] = K_tile . q^T
+  // (M = 128 keys, N = 16 head columns, K = 128 dims) into columns 0..15 of the SAME accumulator, which every warp has
+  // read by then.  Thread = key row reads its G dot products back with one tcgen05.ld: no SIMT dot products (they were
+  // 1 100 instructions per thread, ~2 us of the chain).
+  unsigned char *sK = smem + 65536;                             // 2 slabs x 16 KiB; [64 KiB, 96 KiB) of the operand area
   {
     const uint32_t taddr = tmem_base + (uint32_t((warp & 3) * 32) << 16);
     __nv_bfloat16 *orow = p.k_buf + size_t(bh) * p.buf_stride_bh + (size_t(p.sparse_start) + size_t(slot) * kChunkTokens + r) * kHeadDim;
@@ -438,39 +447,39 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
     tcgen05_ld32(taddr + 64 + half * 32, hi);         // columns [64+32*half, ...)
     tcgen05_wait_ld();
     tcgen05_fence_before();
-    if (write) {
-      uint32_t olo[16], ohi[16];
-      if (p.rope == 1) {
+    uint32_t olo[16], ohi[16];
+    if (p.rope == 1) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const __nv_bfloat162 x1 = __floats2bfloat162_rn(__uint_as_float(lo[2 * e]), __uint_as_float(lo[2 * e + 1]));
-          const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
-          const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
-          const __nv_bfloat162 sn = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
-          const __nv_bfloat162 o1 = __hfma2(x1, c, __hmul2(__hneg2(x2), sn));
-          const __nv_bfloat162 o2 = __hfma2(x2, c, __hmul2(x1, sn));
-          olo[e] = *reinterpret_cast<const uint32_t *>(&o1);
-          ohi[e] = *reinterpret_cast<const uint32_t *>(&o2);
-        }
-      } else {
-        // GLM: interleaved pairs over dims [0,64) with [cos32|sin32]; dims [64,128) copied.
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {         // two pairs per iteration: elements 4e..4e+3
-          const __nv_bfloat162 xe = __floats2bfloat162_rn(__uint_as_float(lo[4 * e]), __uint_as_float(lo[4 * e + 2]));
-          const __nv_bfloat162 xo = __floats2bfloat162_rn(__uint_as_float(lo[4 * e + 1]), __uint_as_float(lo[4 * e + 3]));
-          const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
-          const __nv_bfloat162 sn = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
-          const __nv_bfloat162 oe = __hfma2(xe, c, __hmul2(__hneg2(xo), sn));
-          const __nv_bfloat162 oo = __hfma2(xo, c, __hmul2(xe, sn));
-          olo[2 * e] = pack_bf16(__low2bfloat16(oe), __low2bfloat16(oo));
-          olo[2 * e + 1] = pack_bf16(__high2bfloat16(oe), __high2bfloat16(oo));
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
-          ohi[e] = *reinterpret_cast<const uint32_t *>(&x2);
-        }
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat162 x1 = __floats2bfloat162_rn(__uint_as_float(lo[2 * e]), __uint_as_float(lo[2 * e + 1]));
+        const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
+        const __nv_bfloat162 sn = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
+        const __nv_bfloat162 o1 = __hfma2(x1, c, __hmul2(__hneg2(x2), sn));
+        const __nv_bfloat162 o2 = __hfma2(x2, c, __hmul2(x1, sn));
+        olo[e] = *reinterpret_cast<const uint32_t *>(&o1);
+        ohi[e] = *reinterpret_cast<const uint32_t *>(&o2);
       }
+    } else {
+      // GLM: interleaved pairs over dims [0,64) with [cos32|sin32]; dims [64,128) copied.
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {         // two pairs per iteration: elements 4e..4e+3
+        const __nv_bfloat162 xe = __floats2bfloat162_rn(__uint_as_float(lo[4 * e]), __uint_as_float(lo[4 * e + 2]));
+        const __nv_bfloat162 xo = __floats2bfloat162_rn(__uint_as_float(lo[4 * e + 1]), __uint_as_float(lo[4 * e + 3]));
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162 *>(&cw[e]);
+        const __nv_bfloat162 sn = *reinterpret_cast<const __nv_bfloat162 *>(&sw[e]);
+        const __nv_bfloat162 oe = __hfma2(xe, c, __hmul2(__hneg2(xo), sn));
+        const __nv_bfloat162 oo = __hfma2(xo, c, __hmul2(xe, sn));
+        olo[2 * e] = pack_bf16(__low2bfloat16(oe), __low2bfloat16(oo));
+        olo[2 * e + 1] = pack_bf16(__high2bfloat16(oe), __high2bfloat16(oo));
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const __nv_bfloat162 x2 = __floats2bfloat162_rn(__uint_as_float(hi[2 * e]), __uint_as_float(hi[2 * e + 1]));
+        ohi[e] = *reinterpret_cast<const uint32_t *>(&x2);
+      }
+    }
+    if (write) {
       uint4 *d1 = reinterpret_cast<uint4 *>(orow + half * 32);
       uint4 *d2 = reinterpret_cast<uint4 *>(orow + 64 + half * 32);
 #pragma unroll
@@ -478,36 +487,44 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
         d1[qd] = make_uint4(olo[4 * qd], olo[4 * qd + 1], olo[4 * qd + 2], olo[4 * qd + 3]);
         d2[qd] = make_uint4(ohi[4 * qd], ohi[4 * qd + 1], ohi[4 * qd + 2], ohi[4 * qd + 3]);
       }
-      // q . k over the 64 dims of this half, for every query head of the group (q pre-scaled, broadcast reads)
+    }
+    // A operand: dims [32 half, +32) are pieces 4 half .. 4 half + 3 of slab 0, dims [64 + 32 half, +32) the same pieces
+    // of slab 1.  Rows beyond the miss list hold whatever the accumulator held (never NaN-propagating across rows: an
+    // MMA row only feeds its own output row, which is masked below).
+    unsigned char *krow = sK + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-      for (int g = 0; g < kFaMaxG; ++g) {
-        if (g < G) {                                            // block uniform
-          const float4 *ql = reinterpret_cast<const float4 *>(s_q + g * kHeadDim + half * 32);
-          const float4 *qh = reinterpret_cast<const float4 *>(s_q + g * kHeadDim + 64 + half * 32);
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 x = ql[e4], y = qh[e4];
-            a0 = fmaf(bf16_lo(olo[2 * e4]), x.x, a0); a0 = fmaf(bf16_hi(olo[2 * e4]), x.y, a0);
-            a0 = fmaf(bf16_lo(olo[2 * e4 + 1]), x.z, a0); a0 = fmaf(bf16_hi(olo[2 * e4 + 1]), x.w, a0);
-            a1 = fmaf(bf16_lo(ohi[2 * e4]), y.x, a1); a1 = fmaf(bf16_hi(ohi[2 * e4]), y.y, a1);
-            a1 = fmaf(bf16_lo(ohi[2 * e4 + 1]), y.z, a1); a1 = fmaf(bf16_hi(ohi[2 * e4 + 1]), y.w, a1);
-          }
-          dot[g] = a0 + a1;
-        }
-      }
+    for (int qd = 0; qd < 4; ++qd) {
+      const int piece = ((half * 4 + qd) ^ (row & 7)) << 4;
+      *reinterpret_cast<uint4 *>(krow + piece) = make_uint4(olo[4 * qd], olo[4 * qd + 1], olo[4 * qd + 2], olo[4 * qd + 3]);
+      *reinterpret_cast<uint4 *>(krow + kFaSlabBytes + piece) = make_uint4(ohi[4 * qd], ohi[4 * qd + 1], ohi[4 * qd + 2], ohi[4 * qd + 3]);
     }
   }
-  // the upper column half hands its partial dot products to the lower one through shared memory
-  if (half == 1) {
-    *reinterpret_cast<float4 *>(s_p + row * kFaMaxG) = make_float4(dot[0], dot[1], dot[2], dot[3]);
-    *reinterpret_cast<float4 *>(s_p + row * kFaMaxG + 4) = make_float4(dot[4], dot[5], dot[6], dot[7]);
+  fence_proxy_async_smem();                                     // generic-proxy writes (K rows, q) -> the MMA's async proxy
+  fa_cta_sync2();                                               // every warp has read the accumulator and staged its rows
+  if (tid == 0) {
+    SKV_STAMP_NS(tr, 12);
+    tcgen05_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16_m128(16);
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+      const uint64_t da = umma_desc_k_sw128(smem_addr(sK + sl * kFaSlabBytes));
+      const uint64_t db = umma_desc_k_sw128(smem_addr(sQ + sl * 2048));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        tcgen05_mma_bf16(tmem_base, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc_s, (sl | kk) > 0);
+    }
+    tcgen05_commit(mma_bar);                                    // second phase of the same barrier
   }
-  fa_cta_sync2();
-  if (warp == 0) tcgen05_dealloc(tmem_base, 128);
   if (half == 0) {
-    const float4 x = *reinterpret_cast<const float4 *>(s_p + row * kFaMaxG), y = *reinterpret_cast<const float4 *>(s_p + row * kFaMaxG + 4);
-    dot[0] += x.x; dot[1] += x.y; dot[2] += x.z; dot[3] += x.w; dot[4] += y.x; dot[5] += y.y; dot[6] += y.z; dot[7] += y.w;
+    mbarrier_wait(mma_bar, 1);
+    tcgen05_fence_after();
+    uint32_t sd[16];
+    tcgen05_ld16(tmem_base + (uint32_t((warp & 3) * 32) << 16), sd);
+    tcgen05_wait_ld();
+    tcgen05_fence_before();
+    float dot[kFaMaxG];
+#pragma unroll
+    for (int g = 0; g < kFaMaxG; ++g) dot[g] = __uint_as_float(sd[g]) * p.scale_log2;
     float t_dot[kFaMaxG];                                       // scaled q.k of this thread's row (log2 domain)
 #pragma unroll
     for (int g = 0; g < kFaMaxG; ++g) t_dot[g] = (write && g < G) ? dot[g] : -INFINITY;
@@ -519,7 +536,8 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
         if (lane == 0) s_red[(warp * kFaMaxG + g) * 2] = m;
       }
     }
-    fa_tile_sync();
+    fa_tile_sync();                                             // also: all four warps are past their TMEM loads
+    if (warp == 0) tcgen05_dealloc(tmem_base, 128);
     float l_part[kFaMaxG];
 #pragma unroll
     for (int g = 0; g < kFaMaxG; ++g) {
@@ -853,14 +871,15 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
 }
 
 __global__ void __launch_bounds__(kFaThreads, 2)
-    fetch_rebuild_attend_kernel(const __grid_constant__ CUtensorMap map_sv, const __grid_constant__ CUtensorMap map_k,
-                                const __grid_constant__ CUtensorMap map_v, FaParams p) {
+    fetch_rebuild_attend_kernel(const __grid_constant__ CUtensorMap map_sv, const __grid_constant__ CUtensorMap map_u,
+                                const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                                FaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   pdl_launch_dependents();
   const int n_tile_ctas = p.BH * p.n_tiles;
   if (int(blockIdx.x) < n_tile_ctas) {
     // tile CTAs come first in the grid: their PCIe reads are the long pole and should be in flight as early as possible
-    fa_tile_role(&map_sv, p, int(blockIdx.x) / p.n_tiles, int(blockIdx.x) % p.n_tiles, smem);
+    fa_tile_role(&map_sv, &map_u, p, int(blockIdx.x) / p.n_tiles, int(blockIdx.x) % p.n_tiles, smem);
   } else {
     const int id = int(blockIdx.x) - n_tile_ctas;
     fa_split_role(&map_k, &map_v, p, id / p.n_splits, id % p.n_splits, smem);
@@ -961,8 +980,10 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
   p.tail_off = tile_bytes > ring_bytes ? tile_bytes : ring_bytes;
   const int smem = p.tail_off + kFaTailBytes;
 
-  CUtensorMap map_sv, map_k, map_v;
+  CUtensorMap map_sv, map_u, map_k, map_v;
   int rc = make_tensor_map_2d(&map_sv, SV, uint64_t(BH) * kHeadDim, g->rank, kHeadDim, 64);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&map_u, U, uint64_t(B) * g->seq_len, g->rank, kChunkTokens, 64);
   if (rc) return rc;
   const int64_t stride_row = kHeadDim, stride_h = int64_t(g->buf_len) * kHeadDim, stride_b = stride_h * H;
   rc = make_tensor_map_kv(&map_k, k_buf, g->buf_len, H, B, stride_row, stride_h, stride_b);
@@ -973,7 +994,7 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
     return rc2;
   const int grid = BH * (p.n_tiles + p.n_splits);
   cudaError_t e = launch_kernel(fetch_rebuild_attend_kernel, dim3(grid), dim3(kFaThreads), smem, as_stream(stream),
-                                /*pdl=*/true, map_sv, map_k, map_v, p);
+                                /*pdl=*/true, map_sv, map_u, map_k, map_v, p);
   if (e != cudaSuccess) { set_error("fetch_rebuild_attend_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("fetch_rebuild_attend_kernel");
 }

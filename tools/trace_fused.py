@@ -47,7 +47,7 @@ def main():
     print(f"last layer of the last token; times in us since the scoring kernel's CTA (0,0) started; hits row 0: {int(cache.cnts_all[L - 1][0])}")
     print(f"score  cta(0,0): start {us(sc[0][20])} end {us(sc[0][23])}")
     print(f"select row 0   : past its wait {us(se[0][21])} table written {us(se[0][22])}")
-    names = ["start", "idx", "ldV", "mma", "stats", "V1st", "-", "-", "Vall", "sync", "part", "waited", "-", "end", "MERGED"]
+    names = ["start", "idx", "ldV", "mma", "stats", "V1st", "issued", "landed", "Vall", "sync", "part", "waited", "dots", "end", "MERGED"]
     print("tile CTAs of row 0:  " + " ".join(f"{n:>7}" for n in names))
     for t in range(64):
         if fa[t][0] and fa[t][1]:
