@@ -565,7 +565,8 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
   if (tid == 128) SKV_STAMP_NS(tr, 5);
   mbarrier_wait(&full_v[1], 0);
   if (tid == 128) SKV_STAMP_NS(tr, 8);
-  if (tid == 0) *s_flag = fa_take_ticket(p, bh);
+  int ticket = 0;                                               // thread 0: drawn now, needed only behind the P.V below,
+  if (tid == 0) ticket = fa_take_ticket(p, bh);                 // so the atomic's round trip is off the chain
   // the fetched chunks go to their sparse slots (fire and forget; they stay resident for the next tokens)
   {
     int4 *dbase = reinterpret_cast<int4 *>(p.v_buf + size_t(bh) * p.buf_stride_bh + size_t(p.sparse_start) * kHeadDim);
@@ -616,6 +617,7 @@ __device__ __forceinline__ void fa_tile_role(const CUtensorMap *map_sv_ptr, cons
     for (int g = 0; g < kFaMaxG; ++g)
       if (g < G) *reinterpret_cast<float2 *>(s_o + (rg * kFaMaxG + g) * kHeadDim + 2 * c) = make_float2(acc[g][0], acc[g][1]);
   }
+  if (tid == 0) *s_flag = ticket;
   __syncthreads();
   {
     const int hq = tid >> 5, c4 = tid & 31;
