@@ -291,7 +291,7 @@ __device__ __forceinline__ void block_excl_scan2(int a, int b, int *wa, int *wb,
 // kT threads per CTA: max(S, 256) normally; 512 when a CTA's slice is long (contexts of 256K tokens and more), where the
 // key pass (G exponentials per landmark) is what the kernel spends its time on.
 template <int S, bool kInPlace, int kT>
-__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT)
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 / kT)
     select_kernel(const skv_bf16 *__restrict__ scores,        // [BH, G, ldn] bf16 scaled dot products
                   const float *__restrict__ part_max, const float *__restrict__ part_sum,   // [BH, G, T]
                   const int64_t *__restrict__ landmark_idx,   // [BH, N]
