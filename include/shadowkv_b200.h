@@ -450,7 +450,7 @@ typedef struct skv_dense_epilogue {
  * zero-fills it ONCE; the kernel leaves the counters at zero.  One workspace serves every launch of a stream. */
 int64_t skv_dense_workspace_bytes(void);
 
-/* y = x W^T for a skinny x [batch <= 32, in_features] bf16 and a row-major W [out_features, in_features] bf16
+/* y = x W^T for a skinny x [batch <= 64, in_features] bf16 and a row-major W [out_features, in_features] bf16
  * (torch Linear layout), fp32 accumulation, epilogue per `epi`.  in_features % 64 == 0. */
 int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_features, int out_features,
                      const skv_dense_epilogue *epi, void *workspace, skv_stream_t stream);

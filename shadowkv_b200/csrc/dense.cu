@@ -3,7 +3,7 @@
 //   o_proj + residual -> rmsnorm -> gate/up -> SiLU*mul -> down + residual      llama.py:387-427, glm.py:359-403
 //   final rmsnorm -> lm_head -> argmax                                        base.py:150-159, tensor_op.py:291-293
 // The reference runs these through library kernels (flashinfer rmsnorm, cuBLAS F.linear, vllm rotary_embedding /
-// silu_and_mul, torch adds): ~11 launches per layer.  With batch <= 32 every linear is a weight stream
+// silu_and_mul, torch adds): ~11 launches per layer.  With batch <= 64 every linear is a weight stream
 // (0.436 GB per Llama-8B layer against 8 KB of activations per sequence), i.e. HBM bound, so the design is one
 // weight-streaming kernel with all element-wise work in its epilogue:
 //
@@ -13,7 +13,7 @@
 //  * warp 0 = TMA producer: W slab (two 64-row boxes, 128-byte swizzle, L2 evict-first) + the matching 64 columns
 //    of x (rows beyond the batch are zero filled by TMA) into a shared-memory ring.  The weights are static, so under
 //    a programmatic dependent launch the ring is filled BEFORE griddepcontrol.wait, while the previous kernel drains.
-//  * warp 1 = MMA issuer: tcgen05.mma M=128 (W rows) x N=16/32 (batch, padded) x K=16, fp32 accumulators in TMEM,
+//  * warp 1 = MMA issuer: tcgen05.mma M=128 (W rows) x N=16/32/64 (batch, padded) x K=16, fp32 accumulators in TMEM,
 //    double buffered so the stream continues while a finished tile is in its epilogue.
 //  * warps 2..5 = epilogue, thread = W row.  A tile whose slabs were split between CTAs is finished by the
 //    last-arriving CTA, which sums the partials in CTA order (deterministic), then: bias, bf16 round, residual add /
@@ -27,7 +27,7 @@ namespace skv {
 constexpr int kDnWBytes = 128 * 128;          // W part of a stage: 128 rows x 64 bf16
 constexpr int kDnMaxStages = 12;
 constexpr int kDnThreads = 64 + 128;
-constexpr int kDnMaxBatch = 32;
+constexpr int kDnMaxBatch = 64;
 constexpr int kDnMaxCtas = 2 * kNumSMs;
 constexpr int kDnMaxTiles = 4096;             // arrival counters in the workspace
 constexpr int64_t kDnCounterBytes = kDnMaxTiles * 4;
@@ -342,8 +342,19 @@ __global__ void __launch_bounds__(kDnThreads, 1)
       float v[NPAD];
       {
         uint32_t r[NPAD];
-        if constexpr (NPAD == 16) tcgen05_ld16(tmem_base + (uint32_t(lg * 32) << 16) + acc * kAccCols, r);
-        else tcgen05_ld32(tmem_base + (uint32_t(lg * 32) << 16) + acc * kAccCols, r);
+        const uint32_t taddr = tmem_base + (uint32_t(lg * 32) << 16) + acc * kAccCols;
+        if constexpr (NPAD == 16) {
+          tcgen05_ld16(taddr, r);
+        } else if constexpr (NPAD == 32) {
+          tcgen05_ld32(taddr, r);
+        } else {                                       // 64 batch columns: two 32-column loads
+          uint32_t lo[32], hi[32];
+          tcgen05_ld32(taddr, lo);
+          tcgen05_ld32(taddr + 32, hi);
+          tcgen05_wait_ld();
+#pragma unroll
+          for (int b = 0; b < 32; ++b) { r[b] = lo[b]; r[32 + b] = hi[b]; }
+        }
         tcgen05_wait_ld();
 #pragma unroll
         for (int b = 0; b < NPAD; ++b) v[b] = __uint_as_float(r[b]);
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(kDnThreads, 1)
 #pragma unroll
         for (int b = 0; b < NPAD; ++b) v[b] = 0.f;
         // sum in CTA order (deterministic); the loads of kGroup contributors are in flight together
-        constexpr int kGroup = NPAD == 16 ? 8 : 4;
+        constexpr int kGroup = NPAD == 16 ? 8 : (NPAD == 32 ? 4 : 1);
         for (int c0 = cf; c0 <= cl; c0 += kGroup) {
           float tmp[kGroup][NPAD];
 #pragma unroll
@@ -653,8 +664,8 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
                      const skv_dense_epilogue *epi, void *workspace, skv_stream_t stream) {
   if (!x || !W || !epi || !workspace || !epi->out) { set_error("dense_linear: null pointer"); return SKV_ERR_ARGUMENT; }
   if (batch < 1 || batch > kDnMaxBatch || in_features < 64 || in_features % 64 || out_features < 1) {
-    set_error("dense_linear: batch %d (1..32), in_features %d (multiple of 64), out_features %d", batch, in_features,
-              out_features);
+    set_error("dense_linear: batch %d (1..%d), in_features %d (multiple of 64), out_features %d", batch, kDnMaxBatch,
+              in_features, out_features);
     return SKV_ERR_UNSUPPORTED;
   }
   DenseParams p{};
@@ -717,13 +728,15 @@ int skv_dense_linear(const skv_bf16 *x, const skv_bf16 *W, int batch, int in_fea
   const DenseSched sched = dense_sched(in_features, out_features, p.T);
   p.total = sched.total;
   const int ctas = sched.ctas;
-  const int npad = batch <= 16 ? 16 : 32;
+  const int npad = batch <= 16 ? 16 : (batch <= 32 ? 32 : 64);
   CUtensorMap mw, mx;
   int rc = make_tensor_map_2d(&mw, W, uint64_t(out_features), uint64_t(in_features), 64, 64);
   if (rc) return rc;
   rc = make_tensor_map_2d(&mx, x, uint64_t(batch), uint64_t(in_features), uint32_t(npad), 64);
   if (rc) return rc;
-  return npad == 16 ? launch_dense<16>(mw, mx, p, ctas, as_stream(stream)) : launch_dense<32>(mw, mx, p, ctas, as_stream(stream));
+  if (npad == 16) return launch_dense<16>(mw, mx, p, ctas, as_stream(stream));
+  if (npad == 32) return launch_dense<32>(mw, mx, p, ctas, as_stream(stream));
+  return launch_dense<64>(mw, mx, p, ctas, as_stream(stream));
 }
 
 int64_t skv_dense_partial_bytes(int batch, int in_features, int out_features) {

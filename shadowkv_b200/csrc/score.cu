@@ -242,6 +242,33 @@ __device__ __forceinline__ void find_threshold_bin(const int *hist, int want, in
   }
 }
 
+// The same search over the SUM of the cluster's partial histograms, by all threads of the CTA (kT >= 256): warp w < 8 owns
+// the 32 bins 255 - 32 w - lane (descending, bank-conflict free), adds the partials, scans; after one barrier the warp
+// whose segment holds the threshold writes res[0] = bin, res[1] = count strictly above it.  Ends with a barrier.
+__device__ __forceinline__ int hist_count(const uint32_t *row, int bin) { return int((row[bin >> 1] >> ((bin & 1) * 16)) & 0xFFFFu); }
+__device__ __forceinline__ void find_threshold_parts(const uint32_t (*parts)[128], int want, int *res, int *s_seg) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v = 0, incl = 0;
+  if (warp < 8) {
+    const int bin = 255 - (warp * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) v += hist_count(parts[r], bin);
+    incl = warp_incl_scan(v);
+    if (lane == 31) s_seg[warp] = incl;
+  }
+  __syncthreads();
+  if (warp < 8) {
+    int carry = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) carry += (w < warp) ? s_seg[w] : 0;
+    if (carry < want && want <= carry + s_seg[warp]) {       // warp uniform: the threshold lies in this warp's segment
+      const unsigned hit = __ballot_sync(0xffffffffu, carry + incl >= want);
+      if (lane == __ffs(hit) - 1) { res[0] = 255 - (warp * 32 + lane); res[1] = carry + incl - v; }
+    }
+  }
+  __syncthreads();
+}
+
 // Final (max, 1/sum) with both partial arrays fetched in one round trip (<= 8 x 32 tiles per lane in
 // registers; longer rows fall back to reduce_partials).
 __device__ __forceinline__ void reduce_partials_fast(const float *pm, const float *ps, int T, int lane, float &m_out,
@@ -290,8 +317,11 @@ __device__ __forceinline__ void block_excl_scan2(int a, int b, int *wa, int *wb,
 
 // kT threads per CTA: max(S, 256) normally; 512 when a CTA's slice is long (contexts of 256K tokens and more), where the
 // key pass (G exponentials per landmark) is what the kernel spends its time on.
-template <int S, bool kInPlace, int kT>
-__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 / kT)
+// kCap: 64-register cap, so that 1024 threads of this kernel fit an SM (4 CTAs of 256).  It pays when the grid has more
+// CTAs than the GPU has SMs (batch 8: 20.4 -> 15.4 us); with fewer (batch 1: 64 CTAs) the uncapped build is the faster
+// one (the score + select pair 18.4 against 20.5 us), so the launcher picks per grid size.
+template <int S, bool kInPlace, int kT, bool kCap>
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ? 1024 / kT : 1)
     select_kernel(const skv_bf16 *__restrict__ scores,        // [BH, G, ldn] bf16 scaled dot products
                   const float *__restrict__ part_max, const float *__restrict__ part_sum,   // [BH, G, T]
                   const int64_t *__restrict__ landmark_idx,   // [BH, N]
@@ -309,9 +339,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 /
   int *whist2 = whist1 + kWarps * 256;                                             // [kWarps][256] level 2
   uint16_t *keys = reinterpret_cast<uint16_t *>(sel_smem + 2 * kWarps * 256 * 4);  // [per rounded to 8]
   __shared__ float s_m[16], s_inv[16];
-  __shared__ int s_parts1[kSelCluster][256];    // level-1 histograms of all 8 CTAs (each CTA stores into every CTA)
-  __shared__ int s_parts2[kSelCluster][256];
-  __shared__ int s_tot[256];
+  // level-1 / level-2 histograms of all 8 CTAs (each CTA stores its own into every CTA), two 16-bit counts per word:
+  // a CTA's slice has fewer than 65536 landmarks (check_select_geom), and the exchange is 4 KiB per CTA instead of 8
+  __shared__ uint32_t s_parts1[kSelCluster][128];
+  __shared__ uint32_t s_parts2[kSelCluster][128];
   __shared__ int s_res[4];
   __shared__ int s_wa[kWarps + 1], s_wb[kWarps + 1];
   __shared__ int s_new[S];                      // CTA 0: selected chunk ids in ascending landmark order
@@ -417,24 +448,20 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 /
   }
   SKV_STAMP(bh == 0 ? rank : 999, 2);
   __syncthreads();
-  if (tid < 256) {
-    int t = 0;
+  if (tid < 128) {
+    int2 t = make_int2(0, 0);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += whist1[w * 256 + tid];
+    for (int w = 0; w < kWarps; ++w) {
+      const int2 x = *reinterpret_cast<const int2 *>(whist1 + w * 256 + 2 * tid);
+      t.x += x.x; t.y += x.y;
+    }
+    const uint32_t pk = uint32_t(t.x) | (uint32_t(t.y) << 16);
 #pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts1[rank][tid], r)[0] = t;   // push to every CTA
+    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts1[rank][tid], r)[0] = pk;   // push to every CTA
   }
   cluster.sync();
   SKV_STAMP(bh == 0 ? rank : 999, 3);
-  if (tid < 256) {
-    int t = 0;
-#pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) t += s_parts1[r][tid];
-    s_tot[tid] = t;
-  }
-  __syncthreads();
-  if (warp == 0) find_threshold_bin(s_tot, S, s_res);
-  __syncthreads();
+  find_threshold_parts(s_parts1, S, s_res, s_wa);
   const int b1 = s_res[0], above1 = s_res[1];
   SKV_STAMP(bh == 0 ? rank : 999, 4);
 
@@ -455,24 +482,20 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 /
   }
   SKV_STAMP(bh == 0 ? rank : 999, 5);
   __syncthreads();
-  if (tid < 256) {
-    int t = 0;
+  if (tid < 128) {
+    int2 t = make_int2(0, 0);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += whist2[w * 256 + tid];
+    for (int w = 0; w < kWarps; ++w) {
+      const int2 x = *reinterpret_cast<const int2 *>(whist2 + w * 256 + 2 * tid);
+      t.x += x.x; t.y += x.y;
+    }
+    const uint32_t pk = uint32_t(t.x) | (uint32_t(t.y) << 16);
 #pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts2[rank][tid], r)[0] = t;
+    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts2[rank][tid], r)[0] = pk;
   }
   cluster.sync();
   SKV_STAMP(bh == 0 ? rank : 999, 6);
-  if (tid < 256) {
-    int t = 0;
-#pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) t += s_parts2[r][tid];
-    s_tot[tid] = t;
-  }
-  __syncthreads();
-  if (warp == 0) find_threshold_bin(s_tot, S - above1, s_res + 2);
-  __syncthreads();
+  find_threshold_parts(s_parts2, S - above1, s_res + 2, s_wa);
   const unsigned thr = (unsigned(b1) << 8) | unsigned(s_res[2]);
   const int need_eq = S - (above1 + s_res[3]);      // how many keys equal to thr are taken (>= 1)
   SKV_STAMP(bh == 0 ? rank : 999, 7);
@@ -487,9 +510,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, 1024 /
 #pragma unroll
       for (int r = 0; r < kSelCluster; ++r) {
         if (r < rank) {
-          if (tid > b1) a += s_parts1[r][tid];
-          if (tid > b2) a += s_parts2[r][tid];
-          if (tid == b2) e += s_parts2[r][tid];
+          const int c1 = hist_count(s_parts1[r], tid), c2 = hist_count(s_parts2[r], tid);
+          if (tid > b1) a += c1;
+          if (tid > b2) a += c2;
+          if (tid == b2) e += c2;
         }
       }
     }
@@ -617,7 +641,7 @@ int64_t skv_select_workspace_bytes(const skv_geom *g) {
 
 static int check_select_geom(const skv_geom *g, const char *who) {
   if (g->head_dim != kHeadDim || g->q_groups < 1 || g->q_groups > 16 || !valid_map_size(g->select) ||
-      g->n_landmarks < g->select || g->n_landmarks > 720000) {
+      g->n_landmarks < g->select || g->n_landmarks > 524280) {   // a select CTA's slice (N / 8) fits 16-bit counts
     set_error("%s: unsupported geometry (D=%d G=%d S=%d N=%d)", who, g->head_dim, g->q_groups, g->select,
               g->n_landmarks);
     return SKV_ERR_UNSUPPORTED;
@@ -661,15 +685,17 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const int BH = g->batch * g->kv_heads, G = g->q_groups, N = g->n_landmarks;
   SelectWorkspace w = carve(g, workspace);
   const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
-#define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
+#define SKV_SEL_LAUNCH2(SV, IP, KT, CAP)                                                                          \
   {                                                                                                              \
-    const int smem = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                                   \
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT>), smem, "select_kernel")) return rc; \
-    cudaError_t e = launch_kernel(select_kernel<SV, IP, KT>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,       \
+    const int smem = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16)) + pad;                             \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT, CAP>), smem, "select_kernel")) return rc; \
+    cudaError_t e = launch_kernel(select_kernel<SV, IP, KT, CAP>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,  \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
                                   score_out, g->row_flags, G, N, w.ldn, w.T, per);                                \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
+#define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
+  { if (cap) SKV_SEL_LAUNCH2(SV, IP, KT, true) else SKV_SEL_LAUNCH2(SV, IP, KT, false) }
 #define SKV_SEL(SV)                                                                                              \
   case SV: {                                                                                                     \
     constexpr int kBase = SV > 256 ? SV : 256, kWide = SV > 512 ? SV : 512;                                      \
@@ -681,6 +707,11 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
       if (g->table_mode) SKV_SEL_LAUNCH(SV, true, kBase) else SKV_SEL_LAUNCH(SV, false, kBase)                   \
     }                                                                                                            \
   } break;
+  // register cap (4 x 256 threads per SM) only when the grid has more CTAs than the GPU has SMs; SKV_SELECT_CAP=0/1 and
+  // SKV_SELECT_PAD_KB (extra dynamic shared memory = fewer CTAs of this kernel per SM) are A/B switches
+  const char *ce = getenv("SKV_SELECT_CAP"), *pe = getenv("SKV_SELECT_PAD_KB");
+  const bool cap = (ce && *ce) ? ce[0] == '1' : BH * kSelCluster > kNumSMs;
+  const int pad = (pe && *pe) ? atoi(pe) * 1024 : 0;
   const char *wf = getenv("SKV_SELECT_WIDE_FROM");          // read per call: tests and A/B runs flip it
   const bool wide = per >= ((wf && *wf) ? atoi(wf) : 3072);  // landmarks per CTA from which 512 threads pay
   const char *wf2 = getenv("SKV_SELECT_WIDE2_FROM");
@@ -690,6 +721,7 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
     default: return SKV_ERR_UNSUPPORTED;
   }
 #undef SKV_SEL_LAUNCH
+#undef SKV_SEL_LAUNCH2
 #undef SKV_SEL
   return launch_status("select_kernel");
 }

@@ -1,6 +1,6 @@
 """Dense remainder of the decode layer: torch-tensor wrappers over Part 4 of the C ABI
 (include/shadowkv_b200.h).  Each function replaces the library call named in its docstring for the decode case
-(one token per sequence, batch <= 32); every output can be preallocated (``out=``) so a whole token can be captured
+(one token per sequence, batch <= 64); every output can be preallocated (``out=``) so a whole token can be captured
 in a CUDA graph.  No fallback: the kernels are the only implementation.
 
 ``static_weights=True`` (model weights: written long before the call) lets the kernel stream W into shared memory
@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import lib, check
 
 F32, RESID, SILU_MUL, QKV_ROPE, PARTIAL = 0, 1, 2, 3, 4
-MAX_BATCH = 32
+MAX_BATCH = 64
 
 _workspaces: dict = {}
 

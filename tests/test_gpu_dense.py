@@ -59,6 +59,8 @@ def test_embed_rmsnorm(cuda):
     (16, 4096, 4096, True, False),       # plain F.linear with bias
     (17, 1024, 200, True, True),         # N=32 accumulator, ragged last tile
     (32, 4096, 4096, False, True),
+    (48, 4096, 4096, True, True),        # N=64 accumulator (the reference's batch 48 / 50 rows, test/e2e.py:56-60)
+    (64, 14336, 4096, False, True),
     (2, 64, 128, False, False),          # one slab, one tile, one CTA
     (3, 128, 40000, False, False),       # many tiles per CTA, none split
 ])
@@ -81,7 +83,8 @@ def test_linear_residual(cuda, B, K, N, bias, resid):
 
 
 @pytest.mark.parametrize("B,K,N,bias", [(1, 4096, 4096, False), (5, 14336, 4096, False), (17, 1024, 200, True),
-                                        (32, 4096, 4096, True), (2, 64, 128, False), (3, 4096, 8192, False)])
+                                        (32, 4096, 4096, True), (2, 64, 128, False), (3, 4096, 8192, False),
+                                        (50, 4096, 4096, False)])
 def test_partial_planes_plus_finish_equal_the_unfused_path_bit_for_bit(cuda, B, K, N, bias):
     """linear_partial + finish_rmsnorm (no cross-CTA fix-up inside the linear; the norm kernel adds the planes) against
     linear(residual=) + rmsnorm: same summation order, so the same bits -- and both against the oracle."""
@@ -122,7 +125,7 @@ def test_linear_is_deterministic_and_leaves_the_counters_at_zero(cuda):
         assert torch.equal(dense.linear(x, W), a)
 
 
-@pytest.mark.parametrize("B,vocab", [(1, 128256), (4, 64000)])
+@pytest.mark.parametrize("B,vocab", [(1, 128256), (4, 64000), (40, 32000)])
 def test_lm_head_f32_and_argmax(cuda, B, vocab):
     from shadowkv_b200 import dense
     g = torch.Generator().manual_seed(vocab)
@@ -142,7 +145,8 @@ def test_lm_head_f32_and_argmax(cuda, B, vocab):
     assert dense.argmax(t).tolist() == [123, 0]
 
 
-@pytest.mark.parametrize("B,K,F", [(1, 4096, 14336), (7, 4096, 11008), (32, 1024, 1024), (16, 4096, 13696)])
+@pytest.mark.parametrize("B,K,F", [(1, 4096, 14336), (7, 4096, 11008), (32, 1024, 1024), (16, 4096, 13696),
+                                   (48, 4096, 14336)])
 def test_linear_silu_mul(cuda, B, K, F):
     from shadowkv_b200 import dense
     g = torch.Generator().manual_seed(B + F)
@@ -160,7 +164,7 @@ def test_linear_silu_mul(cuda, B, K, F):
 
 @pytest.mark.parametrize("model,B,use_dev_pos", [("llama-3.1-8b", 1, False), ("llama-3.1-8b", 4, True),
                                                  ("yi-9b-200k", 2, False), ("glm-4-9b-1m", 3, True),
-                                                 ("glm-4-9b-1m", 20, False)])
+                                                 ("glm-4-9b-1m", 20, False), ("llama-3.1-8b", 48, True)])
 def test_qkv_rope(cuda, model, B, use_dev_pos):
     from shadowkv_b200 import dense
     sh = synth.MODELS[model]
@@ -225,10 +229,10 @@ def test_qkv_head_ranges_and_in_place_append(cuda, model, B):
 
 def test_argument_errors(cuda):
     from shadowkv_b200 import dense
-    x = torch.zeros(33, 4096, dtype=BF16, device=cuda)
+    x = torch.zeros(65, 4096, dtype=BF16, device=cuda)
     W = torch.zeros(256, 4096, dtype=BF16, device=cuda)
     with pytest.raises(ValueError):
-        dense.linear(x, W)                                   # batch > 32
+        dense.linear(x, W)                                   # batch > 64
     with pytest.raises(ValueError):
         dense.linear(x[:2, :100].contiguous(), W[:, :100].contiguous())      # in_features % 64
     with pytest.raises(TypeError):
