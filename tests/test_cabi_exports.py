@@ -92,7 +92,7 @@ def test_dense_entry_points_reject_bad_arguments_without_a_gpu():
     epi = _lib.DenseEpilogue(mode=1, out=8)
     one = 16                                               # any non-null "pointer": nothing is dereferenced
     assert lib.skv_dense_linear(0, one, 1, 4096, 4096, C.byref(epi), one, 0) == -2          # null x
-    assert lib.skv_dense_linear(one, one, 33, 4096, 4096, C.byref(epi), one, 0) == -1       # batch > 32
+    assert lib.skv_dense_linear(one, one, 65, 4096, 4096, C.byref(epi), one, 0) == -1       # batch > 64
     assert lib.skv_dense_linear(one, one, 1, 100, 4096, C.byref(epi), one, 0) == -1         # in_features % 64
     assert b"in_features" in lib.skv_last_error()
     bad = _lib.DenseEpilogue(mode=9, out=8)
