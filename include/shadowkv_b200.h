@@ -192,6 +192,11 @@ typedef struct skv_geom {
   int32_t wait_count;             /* -- the previous layer's gathered attention output is then complete in this rank's  */
   int32_t reserved;               /* buffer, which is what the layer's query depends on -- instead of a skv_wait_flags  */
                                   /* launch of its own between the layers.  NULL / 0: no wait                           */
+  int32_t *select_hint; /* optional [B*H] words (device, zero-initialised, one array per layer), in/out of the selection:
+                         * the bf16 key the row's top-S threshold ended on.  The next selection of the same row starts its
+                         * radix search in a window of single-key bins around it and, when the new threshold lies inside
+                         * (a factor of two either way), needs one histogram exchange instead of two.  Purely a speed
+                         * hint: the selection is identical with any content, 0 or NULL = no hint */
 } skv_geom;
 
 /* The scoring launch is a programmatic dependent launch that streams the landmarks into shared memory BEFORE it

@@ -19,7 +19,7 @@ class Geom(C.Structure):
         "batch", "kv_heads", "q_groups", "head_dim", "chunk", "select", "n_landmarks", "rank", "seq_len",
         "buf_len", "sparse_start", "rope_glm", "cos_sin_rows", "table_mode", "flags")] + [("row_flags", C.c_void_p), ("wait_flags", C.c_void_p),
                                                                            ("wait_epoch_dev", C.c_void_p), ("wait_count", C.c_int32),
-                                                                           ("reserved", C.c_int32)]
+                                                                           ("reserved", C.c_int32), ("select_hint", C.c_void_p)]
 
 
 GEOM_DYNAMIC_LANDMARKS = 1   # SKV_GEOM_DYNAMIC_LANDMARKS

@@ -66,6 +66,7 @@ struct FaParams {
   float scale_log2;
   skv_exchange xc;             // kv-head split: peers that receive this rank's attention output (world == 0: none)
   const int32_t *row_flags;    // [BH] or null: per-row hand-over from the selection kernel (skv_geom.row_flags)
+  int early_splits;            // split CTAs request their first tiles ahead of the row hand-over (SKV_FA_EARLY, default 1)
   int order;                   // CTA order of the grid (SKV_FA_ORDER): 0 = a row's tiles together, 1 = tile index slowest,
                                // 2 = like 1 with the split CTAs in front of the second half of the tile indices
 };
@@ -665,6 +666,16 @@ __device__ __forceinline__ void mma_bf16_16816_lo(float &d0, float &d1, float &z
                : "r"(a0), "r"(zero), "r"(a2), "r"(zero), "r"(b0), "r"(b1));
 }
 
+// one 64-key tile of K and V (two 64-dim slabs each) into a ring stage; rows past the tensor's extent are zero filled
+__device__ __forceinline__ void fa_request_tile(unsigned char *dst, uint64_t *bar, const CUtensorMap *map_k,
+                                                const CUtensorMap *map_v, int row0, int h, int b) {
+  mbarrier_expect_tx(bar, kFaRingTile);
+  tma_load_4d(dst, map_k, 0, row0, h, b, bar);
+  tma_load_4d(dst + kFaKvSlab, map_k, 64, row0, h, b, bar);
+  tma_load_4d(dst + 2 * kFaKvSlab, map_v, 0, row0, h, b, bar);
+  tma_load_4d(dst + 3 * kFaKvSlab, map_v, 64, row0, h, b, bar);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Split CTA: keys [split * keys_per_split, ...) of row bh that are resident when the selection finishes.
 // ------------------------------------------------------------------------------------------------
@@ -697,33 +708,39 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
   }
   if (tid < 32) s_mask[tid] = 0u;
   __syncthreads();
-  fa_wait_row(p, bh);
 
-  const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;
+  const int kv_len = p.kv_len_dev ? min(p.kv_len, *p.kv_len_dev) : p.kv_len;   // generation counter: constant during a token
   const int k_begin = split * p.keys_per_split;
   const int k_end = min(kv_len, k_begin + p.keys_per_split);
   const int n_tiles = k_end > k_begin ? (k_end - k_begin + kFaTileKeys - 1) / kFaTileKeys : 0;
+  const int ss = p.sparse_start, se = p.sparse_start + S * kChunkTokens;
+  int p_stage = 0, p_ph = 0, p_next = 0;
+#define FA_REQUEST(t)                                           /* producer thread: tile t of the split into the ring */ \
+  {                                                                                                                      \
+    fa_request_tile(ring + p_stage * kFaRingTile, &full_bar[p_stage], map_k, map_v, k_begin + (t) * kFaTileKeys, h, b);   \
+    if (++p_stage == kFaStages) { p_stage = 0; p_ph ^= 1; }                                                              \
+  }
+  // Row hand-over: the first tiles are requested AHEAD of the wait for the selection, while it is still running and HBM
+  // is idle -- as long as they lie below the generated rows.  Local window, outliers and sparse slots were written by
+  // launches of earlier tokens; the only rows of them that change during this launch are the slots of the miss list
+  // (rewritten by the tile CTAs), and those are masked below whatever was read (old or new rows: finite either way).
+  // The generated region holds the row the scoring launch of THIS step appended: tiles reaching it wait for the word.
+  if (p.row_flags && p.early_splits && warp == 4 && lane == 0) {
+    for (; p_next < n_tiles && p_next < kFaStages && k_begin + (p_next + 1) * kFaTileKeys <= se; ++p_next) FA_REQUEST(p_next)
+  }
+  fa_wait_row(p, bh);
+
   const int cnt = __ldcg(p.cnts + bh);
   const int n_miss = S - cnt;
   const int n_active = (n_miss + kFaTileChunks - 1) / kFaTileChunks;
 
-  // the producer gets the first tiles moving, then everybody marks the slots of the miss list (their K / V rows are
-  // being overwritten by the tile CTAs right now and belong to THEIR partials)
-  int p_stage = 0, p_ph = 0, p_next = 0;
+  // the producer gets the (other) first tiles moving, then everybody marks the slots of the miss list (their K / V rows
+  // are being overwritten by the tile CTAs right now and belong to THEIR partials)
   if (warp == 4 && lane == 0) {
     // the K / V rows were written through the generic proxy (previous launches, the fused append); with the row
     // hand-over no kernel boundary lies in between, so order them in front of this thread's async-proxy reads
     if (p.row_flags) asm volatile("fence.proxy.async;" ::: "memory");
-    for (; p_next < n_tiles && p_next < kFaStages; ++p_next) {
-      mbarrier_expect_tx(&full_bar[p_stage], kFaRingTile);
-      unsigned char *dst = ring + p_stage * kFaRingTile;
-      const int row0 = k_begin + p_next * kFaTileKeys;          // rows past the tensor's extent are zero filled
-      tma_load_4d(dst, map_k, 0, row0, h, b, &full_bar[p_stage]);
-      tma_load_4d(dst + kFaKvSlab, map_k, 64, row0, h, b, &full_bar[p_stage]);
-      tma_load_4d(dst + 2 * kFaKvSlab, map_v, 0, row0, h, b, &full_bar[p_stage]);
-      tma_load_4d(dst + 3 * kFaKvSlab, map_v, 64, row0, h, b, &full_bar[p_stage]);
-      if (++p_stage == kFaStages) { p_stage = 0; p_ph ^= 1; }
-    }
+    for (; p_next < n_tiles && p_next < kFaStages; ++p_next) FA_REQUEST(p_next)
   }
   for (int i = tid; i < n_miss; i += kFaThreads) {
     const int slot = __ldcg(p.miss_slots + size_t(bh) * S + i) & (S - 1);
@@ -732,7 +749,6 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
   __syncthreads();
 
   if (tid == 0) SKV_STAMP_NS(tr, 1);
-  const int ss = p.sparse_start, se = p.sparse_start + S * kChunkTokens;
   auto live = [&](int key) -> bool {                            // key < k_end and not a slot of the miss list
     if (key >= k_end) return false;
     if (key < ss || key >= se) return true;
@@ -745,14 +761,7 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
     if (lane == 0) {
       for (int t = p_next; t < n_tiles; ++t) {
         mbarrier_wait(&empty_bar[p_stage], p_ph ^ 1);
-        mbarrier_expect_tx(&full_bar[p_stage], kFaRingTile);
-        unsigned char *dst = ring + p_stage * kFaRingTile;
-        const int row0 = k_begin + t * kFaTileKeys;
-        tma_load_4d(dst, map_k, 0, row0, h, b, &full_bar[p_stage]);
-        tma_load_4d(dst + kFaKvSlab, map_k, 64, row0, h, b, &full_bar[p_stage]);
-        tma_load_4d(dst + 2 * kFaKvSlab, map_v, 0, row0, h, b, &full_bar[p_stage]);
-        tma_load_4d(dst + 3 * kFaKvSlab, map_v, 64, row0, h, b, &full_bar[p_stage]);
-        if (++p_stage == kFaStages) { p_stage = 0; p_ph ^= 1; }
+        FA_REQUEST(t)
       }
     }
   } else if (warp < 4) {
@@ -874,6 +883,8 @@ __device__ __forceinline__ void fa_split_role(const CUtensorMap *map_k, const CU
   if (tid == 0) { SKV_STAMP_NS(tr, 5); SKV_STAMP_NS(tr, 14); }
 }
 
+#undef FA_REQUEST
+
 __global__ void __launch_bounds__(kFaThreads, 2)
     fetch_rebuild_attend_kernel(const __grid_constant__ CUtensorMap map_sv, const __grid_constant__ CUtensorMap map_u,
                                 const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -949,6 +960,7 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
   if (vstore) p.vs = *vstore;
   p.q = q; p.out = out; p.kv_len_dev = kv_len_dev; p.kv_len = kv_len;
   p.row_flags = g->row_flags;
+  { const char *ee = getenv("SKV_FA_EARLY"); p.early_splits = (ee && *ee) ? atoi(ee) : 1; }   // A/B switch, read per call
   p.order = -1;
   { const char *oe = getenv("SKV_FA_ORDER"); if (oe && *oe) p.order = atoi(oe); }   // A/B switch, read per call
   if (exchange && exchange->world > 0) {

@@ -9,6 +9,7 @@
 //                       (map.cuh:754-796) -- replaces 3 CUTLASS launches + torch.max + torch.topk + gather +
 //                       reorder of the reference with two launches.
 //  softmax_apply_kernel: only for the drop-in batch_gemm_softmax entry point (materialises Softmax).
+#include <algorithm>
 #include <cooperative_groups.h>
 
 #include "chunk_table.cuh"
@@ -214,6 +215,9 @@ __global__ void __launch_bounds__(256)
 // into CTA 0's shared memory, and CTA 0 runs the chunk-table update.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSelCluster = 8;
+constexpr int kSelSpreadBytes = 100 * 1024;   // dynamic shared memory of a "spread" launch: + 15.3 KiB static + 1 KiB reserved
+                                              // = 116.3 KiB per CTA: more than half of an SM's 228 KiB, and a CTA of the
+                                              // fused fetch launch (109 KiB + 1 at rank 160) still fits next to it
 
 // warp-private histogram: after __match_any_sync the leaders of distinct bins touch distinct words
 __device__ __forceinline__ void hist_add_private(int *hist, unsigned bin) {
@@ -330,6 +334,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
                   int64_t *__restrict__ selected_out,         // [BH, S] or null
                   skv_bf16 *__restrict__ score_out,           // [BH, N] or null
                   int32_t *row_flags,                         // [BH] or null: per-row hand-over to the fetch launch
+                  int32_t *hint,                              // [BH] or null: the row's previous threshold key (in/out)
                   int G, int N, int ldn, int T, int per) {
   constexpr int kThreads = kT;
   static_assert(kT >= S && kT >= 256 && kT % 32 == 0, "one thread per table entry and per histogram bin");
@@ -343,6 +348,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   // a CTA's slice has fewer than 65536 landmarks (check_select_geom), and the exchange is 4 KiB per CTA instead of 8
   __shared__ uint32_t s_parts1[kSelCluster][128];
   __shared__ uint32_t s_parts2[kSelCluster][128];
+  __shared__ uint32_t s_parts0[kSelCluster][128];   // the window histogram (threshold hint), same layout
   __shared__ int s_res[4];
   __shared__ int s_wa[kWarps + 1], s_wb[kWarps + 1];
   __shared__ int s_new[S];                      // CTA 0: selected chunk ids in ascending landmark order
@@ -384,6 +390,13 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   // the scores of this thread's first 8 landmarks for the first four heads, requested together with the partial
   // statistics below: one L2 round trip instead of two in front of the first histogram pass
   const skv_bf16 *sc = scores + size_t(bh) * G * ldn;
+  // Threshold hint: the key this row's selection ended on for the previous token.  The first histogram then has ONE KEY
+  // VALUE per bin in a window around it (bins 1..254 = keys win0 .. win0 + 253, bin 0 = everything below, bin 255 =
+  // everything above), so when the new threshold lies inside the window -- consecutive tokens move it by a few bf16
+  // steps, the window spans a factor of two either way -- ONE histogram exchange settles it exactly; otherwise the
+  // two-level search below runs as if there had been no hint.  The result never depends on the hint.
+  const int hint_key = hint ? __ldcg(hint + bh) : 0;
+  const int win0 = hint_key > 0 ? max(1, hint_key - 126) : 0;          // 0: no window
   int4 w0[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
   if (tid * 8 < count) {
 #pragma unroll
@@ -444,22 +457,84 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
       }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) hist_add_private(my_h1, (on && off + e < count) ? unsigned(best[e] >> 8) : 0xFFFFu);
+    for (int e = 0; e < 8; ++e) {
+      const int k = best[e];
+      const unsigned bin = win0 ? (k < win0 ? 0u : unsigned(min(255, k - win0 + 1))) : unsigned(k >> 8);
+      hist_add_private(my_h1, (on && off + e < count) ? bin : 0xFFFFu);
+    }
   }
   SKV_STAMP(bh == 0 ? rank : 999, 2);
-  __syncthreads();
-  if (tid < 128) {
-    int2 t = make_int2(0, 0);
+  // sum of the warp-private histograms `wh`, two 16-bit counts per word, into row `rank` of `parts` of every CTA
+  auto push_hist = [&](const int *wh, uint32_t (*parts)[128]) {
+    __syncthreads();
+    if (tid < 128) {
+      int2 t = make_int2(0, 0);
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const int2 x = *reinterpret_cast<const int2 *>(whist1 + w * 256 + 2 * tid);
-      t.x += x.x; t.y += x.y;
+      for (int w = 0; w < kWarps; ++w) {
+        const int2 x = *reinterpret_cast<const int2 *>(wh + w * 256 + 2 * tid);
+        t.x += x.x; t.y += x.y;
+      }
+      const uint32_t pk = uint32_t(t.x) | (uint32_t(t.y) << 16);
+#pragma unroll
+      for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&parts[rank][tid], r)[0] = pk;
     }
-    const uint32_t pk = uint32_t(t.x) | (uint32_t(t.y) << 16);
+    cluster.sync();
+  };
+  unsigned thr = 0;
+  int need_eq = 0, gt_before = 0, eq_before = 0;
+  // (greater, equal) counts of the lower-ranked CTAs from the exchanged partial histograms: bins above `ba` of `pa` and
+  // (two-level search) above `bb` of `pb` hold greater keys, bin `bb` of `pb` the keys equal to the threshold
+  auto counts_before = [&](const uint32_t (*pa)[128], int ba, const uint32_t (*pb)[128], int bb) {
+    int a = 0, e = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts1[rank][tid], r)[0] = pk;   // push to every CTA
+      for (int r = 0; r < kSelCluster; ++r) {
+        if (r < rank) {
+          if (pa != nullptr && tid > ba) a += hist_count(pa[r], tid);
+          const int c2 = hist_count(pb[r], tid);
+          if (tid > bb) a += c2;
+          if (tid == bb) e += c2;
+        }
+      }
+    }
+    a = warp_sum_int(a); e = warp_sum_int(e);
+    if (lane == 0) { s_wa[warp] = a; s_wb[warp] = e; }
+    __syncthreads();
+    for (int w = 0; w < (kWarps < 8 ? kWarps : 8); ++w) { gt_before += s_wa[w]; eq_before += s_wb[w]; }
+  };
+  bool settled = false;
+  if (win0) {                                   // cluster uniform (the hint word is the same for all eight CTAs)
+    push_hist(whist1, s_parts0);
+    SKV_STAMP(bh == 0 ? rank : 999, 3);
+    find_threshold_parts(s_parts0, S, s_res, s_wa);
+    const int b0 = s_res[0], above0 = s_res[1];
+    if (b0 >= 1 && b0 <= 254) {                 // the threshold is a key of the window: done after ONE exchange
+      thr = unsigned(win0 + b0 - 1);
+      need_eq = S - above0;
+      counts_before(nullptr, 0, s_parts0, b0);
+      settled = true;
+    } else {                                    // outside: the level-1 histogram of the two-level search, from the keys
+      __syncthreads();
+      for (int i = tid; i < kWarps * 256; i += kThreads) whist1[i] = 0;
+      __syncthreads();
+      for (int base = 0; base < count; base += kThreads * 8) {
+        const int off = base + tid * 8;
+        const bool on = off < count;
+        uint32_t kw[4] = {0, 0, 0, 0};
+        if (on) {
+          const int4 w = *reinterpret_cast<const int4 *>(keys + off);
+          kw[0] = w.x; kw[1] = w.y; kw[2] = w.z; kw[3] = w.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned k = (kw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+          hist_add_private(my_h1, (on && off + e < count) ? (k >> 8) : 0xFFFFu);
+        }
+      }
+    }
   }
-  cluster.sync();
+  if (!settled) {
+  push_hist(whist1, s_parts1);
   SKV_STAMP(bh == 0 ? rank : 999, 3);
   find_threshold_parts(s_parts1, S, s_res, s_wa);
   const int b1 = s_res[0], above1 = s_res[1];
@@ -481,46 +556,16 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
     }
   }
   SKV_STAMP(bh == 0 ? rank : 999, 5);
-  __syncthreads();
-  if (tid < 128) {
-    int2 t = make_int2(0, 0);
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const int2 x = *reinterpret_cast<const int2 *>(whist2 + w * 256 + 2 * tid);
-      t.x += x.x; t.y += x.y;
-    }
-    const uint32_t pk = uint32_t(t.x) | (uint32_t(t.y) << 16);
-#pragma unroll
-    for (int r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(&s_parts2[rank][tid], r)[0] = pk;
-  }
-  cluster.sync();
+  push_hist(whist2, s_parts2);
   SKV_STAMP(bh == 0 ? rank : 999, 6);
   find_threshold_parts(s_parts2, S - above1, s_res + 2, s_wa);
-  const unsigned thr = (unsigned(b1) << 8) | unsigned(s_res[2]);
-  const int need_eq = S - (above1 + s_res[3]);      // how many keys equal to thr are taken (>= 1)
+  thr = (unsigned(b1) << 8) | unsigned(s_res[2]);
+  need_eq = S - (above1 + s_res[3]);                // how many keys equal to thr are taken (>= 1)
   SKV_STAMP(bh == 0 ? rank : 999, 7);
 
   // 3. (greater, equal) counts of the lower-ranked CTAs: every CTA already holds all eight partial
   //    histograms, so no further exchange is needed
-  int gt_before = 0, eq_before = 0;
-  {
-    const int b2 = s_res[2];
-    int a = 0, e = 0;
-    if (tid < 256) {
-#pragma unroll
-      for (int r = 0; r < kSelCluster; ++r) {
-        if (r < rank) {
-          const int c1 = hist_count(s_parts1[r], tid), c2 = hist_count(s_parts2[r], tid);
-          if (tid > b1) a += c1;
-          if (tid > b2) a += c2;
-          if (tid == b2) e += c2;
-        }
-      }
-    }
-    a = warp_sum_int(a); e = warp_sum_int(e);
-    if (lane == 0) { s_wa[warp] = a; s_wb[warp] = e; }
-    __syncthreads();
-    for (int w = 0; w < (kWarps < 8 ? kWarps : 8); ++w) { gt_before += s_wa[w]; eq_before += s_wb[w]; }
+  counts_before(s_parts1, b1, s_parts2, s_res[2]);
   }
   SKV_STAMP(bh == 0 ? rank : 999, 10);
 
@@ -575,6 +620,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
                                   cnts + bh);
   SKV_STAMP(bh == 0 ? rank : 999, 14);
+  if (hint && tid == 0) hint[bh] = int(thr);      // read by this row's selection of the next token, behind its wait
   if (row_flags) {                              // the row's chunk table (resident, offsets, cnt) is written: release it
     __syncthreads();
     if (tid == 0) {
@@ -687,11 +733,12 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
 #define SKV_SEL_LAUNCH2(SV, IP, KT, CAP)                                                                          \
   {                                                                                                              \
-    const int smem = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16)) + pad;                             \
+    const int smem0 = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                                  \
+    const int smem = smem0 + (pad >= 0 ? pad : (spread ? std::max(0, (kSelSpreadBytes - smem0) / 1024 * 1024) : 0)); \
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT, CAP>), smem, "select_kernel")) return rc; \
     cudaError_t e = launch_kernel(select_kernel<SV, IP, KT, CAP>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,  \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
-                                  score_out, g->row_flags, G, N, w.ldn, w.T, per);                                \
+                                  score_out, g->row_flags, sel_hint, G, N, w.ldn, w.T, per);                      \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
@@ -709,9 +756,17 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   } break;
   // register cap (4 x 256 threads per SM) only when the grid has more CTAs than the GPU has SMs; SKV_SELECT_CAP=0/1 and
   // SKV_SELECT_PAD_KB (extra dynamic shared memory = fewer CTAs of this kernel per SM) are A/B switches
+  const char *he = getenv("SKV_SELECT_HINT");               // A/B switch: 0 ignores skv_geom.select_hint
+  int32_t *sel_hint = (he && he[0] == '0') ? nullptr : g->select_hint;
   const char *ce = getenv("SKV_SELECT_CAP"), *pe = getenv("SKV_SELECT_PAD_KB");
   const bool cap = (ce && *ce) ? ce[0] == '1' : BH * kSelCluster > kNumSMs;
-  const int pad = (pe && *pe) ? atoi(pe) * 1024 : 0;
+  // One CTA of this kernel per SM while the grid covers at most half of the SMs (batch 1): the dynamic shared memory is
+  // padded so that two of its CTAs do not fit an SM, but one CTA of the fused fetch launch (109 KiB) still fits next to
+  // it and can set itself up ahead of its row's hand-over.  Measured at batch 1 (122K): score + select 16.8 -> 14.2 us,
+  // step 62.5 -> 61.9 us (V on the host) and 32.4 -> 31.9 us (V in HBM); a larger pad that keeps the fused launch's CTAs
+  // out (100 KiB) costs the HBM configuration 1.2 us, and at batch 2 (128 CTAs) the padding is a loss (9.2 -> 14.5 us).
+  const bool spread = BH * kSelCluster <= kNumSMs / 2;
+  const int pad = (pe && *pe) ? atoi(pe) * 1024 : -1;
   const char *wf = getenv("SKV_SELECT_WIDE_FROM");          // read per call: tests and A/B runs flip it
   const bool wide = per >= ((wf && *wf) ? atoi(wf) : 3072);  // landmarks per CTA from which 512 threads pay
   const char *wf2 = getenv("SKV_SELECT_WIDE2_FROM");

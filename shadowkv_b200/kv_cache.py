@@ -144,6 +144,7 @@ class ShadowKVCache_CPU:
         self._k_done = torch.cuda.Event()
         self._geom = None
         self._row_flags = None
+        self._sel_hint = None
         self._sel_ws = None
         self._attn_ws = None
         self.rebuild_impl = 0      # 0: tcgen05 (product); 1: SIMT cross-check (tests only)
@@ -284,6 +285,9 @@ class ShadowKVCache_CPU:
             # per layer; SKV_ROW_FLAGS=0 keeps plain dependent launches (A/B runs)
             self._row_flags = (torch.zeros(self.num_layers, g.batch * g.kv_heads, dtype=torch.int32, device=self.device)
                                if os.environ.get("SKV_ROW_FLAGS", "1") != "0" else None)
+            # threshold hints of the selection (skv_geom.select_hint): per (layer, b, kv head) the bf16 key the previous
+            # token's top-S threshold ended on; a speed hint only (the selection is the same with any content)
+            self._sel_hint = torch.zeros(self.num_layers, g.batch * g.kv_heads, dtype=torch.int32, device=self.device)
         if cos_sin_cache is not None:
             width = cos_sin_cache.shape[-1]
             if width not in (self.head_dim, self.head_dim // 2):
@@ -475,6 +479,7 @@ class ShadowKVCache_CPU:
         g = self._geometry()
         q = query_states.contiguous()
         self.offsets, self.cnts = self.offsets_all[layer_idx], self.cnts_all[layer_idx]
+        g.select_hint = self._sel_hint[layer_idx].data_ptr()
         check(lib.skv_select_chunks(C.byref(g), q.data_ptr(), self.k_landmark[layer_idx].data_ptr(),
                                     self.k_landmark_idx[layer_idx].data_ptr(), self.position_ids[layer_idx].data_ptr(),
                                     self.offsets.data_ptr(), self.cnts.data_ptr(),

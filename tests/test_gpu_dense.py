@@ -135,7 +135,9 @@ def test_lm_head_f32_and_argmax(cuda, B, vocab):
     assert got.dtype == torch.float32
     assert torch.equal(got.to(BF16).float(), got), "logits must be bf16-representable (F.linear(...).float())"
     assert_ulp_bf16(got.to(BF16), want, ulps=1, frac_exact=0.97, what="lm_head")
-    assert_close_bf16(got, want, what="logits")
+    # every logit is within 1 bf16 ulp (checked above); the absolute bar is therefore one ulp of the largest logit where
+    # that exceeds the 2e-2 of north_star (|logit| >= 4 -> ulp 2^-5)
+    assert_close_bf16(got, want, max_abs=max(2e-2, 2.0 ** -7 * float(want.float().abs().max())), what="logits")
     tok = dense.argmax(got)
     assert torch.equal(tok.cpu(), DO.greedy(got.cpu()))
     # ties resolve to the lowest index
@@ -183,11 +185,18 @@ def test_qkv_rope(cuda, model, B, use_dev_pos):
     assert q.shape == (B, Hq, 1, 128) and k.shape == (B, H, 1, 128) and v.shape == (B, H, 1, 128)
     assert_rope_rows_close(q.view(B, Hq, 128), wq, glm=sh.glm_rope, ulps_in=2, frac_exact=0.90, what="q")
     assert_rope_rows_close(k.view(B, H, 128), wk, glm=sh.glm_rope, ulps_in=2, frac_exact=0.90, what="k")
-    assert_ulp_bf16(v.view(B, H, 128), wv, ulps=2, frac_exact=0.95, what="v")
+    # v is a plain linear of the normed input.  Stage-wise (the oracle's linear on the KERNEL's own h): 1 ulp.  End to end
+    # the ~1 % of h elements where the kernel's rmsnorm is 1 ulp off the oracle's reach v as a sum of ~40 terms of
+    # ulp(h) * |W| ~ 8e-3 * 0.03, i.e. ~1.5e-3 absolutely, which only shows on the few outputs that cancel to nearly zero
+    # (2-6 of 49 152 at batch 48): 2 ulps with a 5e-3 floor there.
+    v_rows = slice((Hq + H) * 128, (Hq + 2 * H) * 128)
+    wv_stage = DO.linear(h.cpu(), Wqkv[v_rows], bias[v_rows] if bias is not None else None)
+    assert_ulp_bf16(v.view(B, H * 128), wv_stage, ulps=1, frac_exact=0.97, what="v (stage)")
+    assert_ulp_bf16(v.view(B, H, 128), wv, ulps=2, frac_exact=0.95, abs_floor=5e-3, what="v")
     # without a table: the plain split of pre_attention_compute (llama.py:380)
     q0, k0, v0 = dense.linear_qkv_rope(h, Wqkv.to(cuda), Hq, H, None, 0, bias=bias.to(cuda) if bias is not None else None)
     n0 = DO.pre_attention(x, w, 1e-5, Wqkv, bias, Hq, H, None, 0, 0)
-    assert_ulp_bf16(q0.view(B, Hq, 128), n0[0], ulps=2, frac_exact=0.95, what="q (no rope)")
+    assert_ulp_bf16(q0.view(B, Hq, 128), n0[0], ulps=2, frac_exact=0.95, abs_floor=5e-3, what="q (no rope)")   # as for v
     assert torch.equal(v0, v)
 
 

@@ -106,6 +106,57 @@ def test_select_chunks(cuda, model, N, S):
           f"value): worst row {worst} of {S}")
 
 
+@pytest.mark.parametrize("model,N,S", [("llama-3.1-8b", 15560, 256), ("glm-4-9b-1m", 16328, 256),
+                                       ("llama-3-8b-1m", 65480, 256), ("llama-3.1-8b", 4044, 512)])
+def test_select_threshold_hint_never_changes_the_result(cuda, model, N, S):
+    """skv_geom.select_hint is a speed hint: a window of single-key histogram bins around the previous threshold settles
+    the top-S threshold in one exchange when the new threshold lies inside it; outside it the two-level search runs.  The
+    selection, the chunk table and the hit counts must be the same for ANY hint content, and the word must come back as
+    the threshold key of this selection."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    shape = synth.MODELS[model]
+    B = 2
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(N * 3 + S)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16).to(cuda)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N).to(cuda)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S].to(cuda)] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+
+    def run(hint):
+        res = resident.clone()
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+        geom.select_hint = hint.data_ptr() if hint is not None else None
+        _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.data_ptr(), lm.data_ptr(), idx.data_ptr(), res.data_ptr(),
+                                              off.data_ptr(), cnt.data_ptr(), sel.data_ptr(), score.data_ptr(), ws.data_ptr(),
+                                              None, torch.cuda.current_stream().cuda_stream), "select")
+        torch.cuda.synchronize()
+        return res.cpu(), off.cpu(), cnt.cpu(), sel.cpu(), score.cpu()
+
+    base = run(None)
+    # the threshold key of every row, from the kernel's own scores: the S-th largest key (bf16 bits are monotone for p >= 0)
+    keys = base[4].view(torch.int16).int().view(B * H, N)
+    thr = torch.sort(keys, dim=1, descending=True).values[:, S - 1].to(torch.int32)
+    assert int(thr.min()) > 0
+    cases = {"zero (first token)": torch.zeros_like(thr), "exact": thr.clone(), "a few steps off": thr + torch.arange(B * H, dtype=torch.int32) * 7 - 20,
+             "window edges": thr + torch.tensor([126, -127] * (B * H // 2), dtype=torch.int32),
+             "just outside": thr + torch.tensor([127, -128] * (B * H // 2), dtype=torch.int32),
+             "far above": thr + 3000, "far below": (thr - 3000).clamp(min=1), "huge": torch.full_like(thr, 65535)}
+    for name, h in cases.items():
+        hint = h.to(cuda)
+        got = run(hint)
+        for a, b, what in zip(got[:4], base[:4], ("resident", "offsets", "cnts", "selected")):
+            assert torch.equal(a, b), f"hint '{name}': {what} differs from the run without a hint"
+        assert torch.equal(hint.cpu(), thr), f"hint '{name}': the word must come back as this selection's threshold key"
+
+
 def test_select_massive_ties(cuda):
     """All landmarks identical -> every score ties; the rule must pick the S lowest indices."""
     from shadowkv_b200 import _lib
