@@ -7,10 +7,10 @@
 // CUTLASS 2.x Sm80 mma.sync, tile 32x256x32) on this path; same rounding points: fp32 accumulate, * alpha,
 // round to bf16, max / sum-of-exp over the ROUNDED values (epilogue_visitor_with_softmax).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 and 6..9 = two
-// epilogue warpgroups that take alternate tiles (warp w reads TMEM lanes 32*(w%4)..+31 = landmark rows of the
-// tile; the per-tile epilogue is a latency chain of shuffles, so two tiles are kept in flight).  Two CTAs fit per
-// SM (3 x 32 KiB ring each).
+// Warp roles (64 + kEpi x 128 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, then kEpi (4, or 2)
+// epilogue warpgroups, each with its own TMEM accumulator, taking tiles g, g + kEpi, ... (warp w reads TMEM lanes
+// 32*(w%4)..+31 = landmark rows of the tile; the per-tile epilogue is a latency chain of shuffles, so several tiles
+// are kept in flight).  Two CTAs fit per SM (3 x 32 KiB ring each).
 #include "sm100_ptx.cuh"
 
 #include <cstdlib>
@@ -23,12 +23,15 @@ constexpr int kSmMaxStages = 3;                  // ring depth is a template par
 constexpr int kSmSlabBytes = kSmTileRows * 128;  // one 64-column (128 B) swizzle slab of a tile
 constexpr int kSmTileBytes = 2 * kSmSlabBytes;   // 32 KiB
 constexpr int kSmQSlabBytes = 16 * 128;          // B operand: 16 rows (heads, zero padded) x 64 columns
-constexpr int kSmEpiGroups = 2;                 // two epilogue warpgroups take alternate tiles
-constexpr int kSmThreads = 64 + kSmEpiGroups * 128;
+constexpr int kSmMaxEpi = 4;                     // epilogue warpgroups (template parameter kEpi: 2 or 4), each with its own
+                                                 // accumulator buffer; group g takes tiles g, g + kEpi, ...
 constexpr int kSmAccCols = 16;                   // fp32 accumulator columns per tile (UMMA N)
 
 struct ScoreMmaParams {
   const skv_bf16 *q;        // [BH, G, 128]
+  const skv_bf16 *lm;       // [BH, N, 128] (the tensor map's base): L2 prefetch of the tiles beyond the ring
+  long long lm_rows;        // BH * N
+  int l2_prefetch;          // SKV_SCORE_L2PF (default 1)
   skv_bf16 *scores;         // [BH, G, ldn]
   float *part_max, *part_sum;   // [BH, G, T]
   int G, N, ldn, T, ctas_per_row;
@@ -40,30 +43,33 @@ struct ScoreMmaParams {
   int wait_count;
 };
 
-template <int kSmStages, int kCtasPerSm>
-__global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
+template <int kSmStages, int kCtasPerSm, int kEpi>
+__global__ void __launch_bounds__(64 + kEpi * 128, kCtasPerSm)
     score_tcgen05_kernel(const __grid_constant__ CUtensorMap map_lm, ScoreMmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sA = smem;                                          // kSmStages x 32 KiB
   unsigned char *sQ = smem + kSmStages * kSmTileBytes;               // 2 slabs x 2 KiB
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sQ + 2 * kSmQSlabBytes);
   uint64_t *empty_bar = full_bar + kSmStages;
-  uint64_t *acc_full = empty_bar + kSmStages;                        // [2]
-  uint64_t *acc_empty = acc_full + 2;                                // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-  float *s_red = reinterpret_cast<float *>(tmem_slot + 2);           // [2 acc][4 warps][16 heads][2]
+  uint64_t *acc_full = empty_bar + kSmStages;                        // [kEpi]
+  uint64_t *acc_empty = acc_full + kSmMaxEpi;                        // [kEpi]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + kSmMaxEpi);
+  float *s_red = reinterpret_cast<float *>(tmem_slot + 2);           // [kEpi acc][4 warps][16 heads][2]
+  constexpr int kSmThreads = 64 + kEpi * 128;
 
   const int bh = blockIdx.y, cx = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (p.T - cx + p.ctas_per_row - 1) / p.ctas_per_row;   // tiles cx, cx + cpr, ... < T
   const int tr = bh == 0 ? cx : 999;
   SKV_STAMP(tr, 0);
-  if (threadIdx.x == 0) SKV_STAMP_NS((bh == 0 && cx == 0) ? 0 : -1, 20);
+  // wall-clock rows of the trace build: row 0 = CTA (0,0), row 1 = the last CTA of the grid
+  const int trn = (bh == 0 && cx == 0) ? 0 : ((bh == int(gridDim.y) - 1 && cx == int(gridDim.x) - 1) ? 1 : -1);
+  if (threadIdx.x == 0) SKV_STAMP_NS(trn, 20);
 
   pdl_launch_dependents();                                   // the selection kernel may be scheduled behind us
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSmStages; ++s) { mbarrier_init(&full_bar[s], 1); mbarrier_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
+    for (int a = 0; a < kEpi; ++a) { mbarrier_init(&acc_full[a], 1); mbarrier_init(&acc_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the ring is empty: fill it right away.  The landmarks are static, so under a programmatic launch this
     // runs while the previous kernel of the stream (the previous layer's attention) is still finishing.
@@ -75,12 +81,23 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
       tma_load_2d_hint(sA + i * kSmTileBytes + kSmSlabBytes, &map_lm, 64, row0, &full_bar[i], pol);
       if (i < 4) SKV_STAMP_ANY(tr, 2 + i);
     }
+    // a CTA with one or two tiles more than the ring holds (batch 1: 4 tiles, 3 stages) pulls them into L2 now, so the
+    // load issued behind the dependency wait is an L2 hit instead of an HBM round trip on the chain
+    if (p.l2_prefetch && !p.dynamic_lm && n_my > kSmStages && n_my <= kSmStages + 2) {
+      for (int i = kSmStages; i < n_my; ++i) {
+        const long long row0 = (long long)bh * p.N + (long long)(cx + i * p.ctas_per_row) * kSmTileRows;
+        const long long rows = min((long long)kSmTileRows, p.lm_rows - row0);
+        if (rows > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.lm + row0 * kHeadDim), "r"(int(rows) * kHeadDim * 2) : "memory");
+      }
+    }
   }
   // TMEM does not depend on the predecessor either (attention and selection hold none; a rebuild CTA that is still
   // resident keeps 128 of the 512 columns)
-  if (warp == 1) tcgen05_alloc(tmem_slot, 32);
+  if (warp == 1) tcgen05_alloc(tmem_slot, kEpi * kSmAccCols);
   // everything below touches data of the predecessor (q, the K/V buffers, the score scratch)
   pdl_wait();
+  if (threadIdx.x == 0) SKV_STAMP_NS(trn, 21);
   if (p.wait_flags) {
     // kv-head split: the query of this layer depends on the previous layer's GATHERED attention output; every peer raises
     // a flag word per row (system scope) behind the row's stores into this rank's buffer.
@@ -119,6 +136,7 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   SKV_STAMP(tr, 1);
+  if (threadIdx.x == 0) SKV_STAMP_NS(trn, 22);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -142,10 +160,11 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
       const uint64_t db0 = umma_desc_k_sw128(smem_addr(sQ)), db1 = umma_desc_k_sw128(smem_addr(sQ + kSmQSlabBytes));
       for (int i = 0; i < n_my; ++i) {
         const int stage = i % kSmStages, ph = (i / kSmStages) & 1;
-        const int acc = i & 1, aph = (i >> 1) & 1;
+        const int acc = i % kEpi, aph = (i / kEpi) & 1;
         mbarrier_wait(&acc_empty[acc], aph ^ 1);
         mbarrier_wait(&full_bar[stage], ph);
         if (i < 4) SKV_STAMP_ANY(tr, 6 + i);
+        if (i < 4) SKV_STAMP_NS(trn, 24 + i);          // tile i of this CTA is in shared memory (wall clock)
         tcgen05_fence_after();
         const uint64_t da0 = umma_desc_k_sw128(smem_addr(sA + stage * kSmTileBytes));
         const uint64_t da1 = umma_desc_k_sw128(smem_addr(sA + stage * kSmTileBytes + kSmSlabBytes));
@@ -163,8 +182,8 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
     const int lg = warp & 3;                                 // TMEM lane group this warp may read
     const int grp = (warp - 2) >> 2;                         // epilogue warpgroup 0 / 1 <-> accumulator buffer
     const int ew = (warp - 2) & 3;                           // 0..3 inside the group
-    for (int i = grp; i < n_my; i += kSmEpiGroups) {
-      const int acc = i & 1, aph = (i >> 1) & 1;
+    for (int i = grp; i < n_my; i += kEpi) {
+      const int acc = grp, aph = (i / kEpi) & 1;
       const int tile = cx + i * p.ctas_per_row;
       mbarrier_wait(&acc_full[acc], aph);
       if (i < 4 && (threadIdx.x == 64 || threadIdx.x == 192)) SKV_STAMP_ANY(tr, 10 + i);
@@ -229,8 +248,8 @@ __global__ void __launch_bounds__(kSmThreads, kCtasPerSm)
   tcgen05_fence_before();
   __syncthreads();
   SKV_STAMP(tr, 15);
-  if (threadIdx.x == 0) SKV_STAMP_NS((bh == 0 && cx == 0) ? 0 : -1, 23);
-  if (warp == 1) tcgen05_dealloc(tmem_base, 32);
+  if (threadIdx.x == 0) SKV_STAMP_NS(trn, 23);
+  if (warp == 1) tcgen05_dealloc(tmem_base, kEpi * kSmAccCols);
 }
 
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
@@ -242,6 +261,8 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   if (rc) return rc;
   ScoreMmaParams p{};
   p.q = q; p.scores = scores; p.part_max = pmax; p.part_sum = psum;
+  p.lm = lm; p.lm_rows = (long long)BH * N;
+  { const char *le = getenv("SKV_SCORE_L2PF"); p.l2_prefetch = (le && le[0] == '0') ? 0 : 1; }
   p.G = G; p.N = N; p.ldn = ldn; p.T = T; p.alpha = alpha; p.buf_rows = buf_rows;
   p.dynamic_lm = dynamic_landmarks ? 1 : 0;
   if (append) p.ap = *append;
@@ -258,13 +279,20 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   if (cpr > T) cpr = T;
   if (cpr < 1) cpr = 1;
   p.ctas_per_row = cpr;
-  const int smem = stages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmMaxStages + 4) * 8 + 8 + 2 * 4 * 32 * 4 + 64;
-  if (int rc2 = ensure_dynamic_smem(stages == 2 ? reinterpret_cast<const void *>(score_tcgen05_kernel<2, 3>)
-                                                : reinterpret_cast<const void *>(score_tcgen05_kernel<3, 2>),
-                                    smem, "score_tcgen05_kernel")) return rc2;
+  // epilogue warpgroups: four (576 threads, 48 registers), each with its own accumulator buffer.  Measured against two
+  // (SKV_SCORE_EPI=2): neutral at batch 1, where the 8 dependent MMAs of a tile (~0.5 us) and the tile that is loaded
+  // behind the dependency wait pace the CTA, not the epilogues; 47.5 -> 46.5 us per launch at batch 8 (122K)
+  const char *ee = getenv("SKV_SCORE_EPI");
+  const int epi = (ee && *ee && atoi(ee) == 2) ? 2 : 4;
+  const int smem = stages * kSmTileBytes + 2 * kSmQSlabBytes + (2 * kSmMaxStages + 2 * kSmMaxEpi) * 8 + 8 + kSmMaxEpi * 4 * 32 * 4 + 64;
+  const void *fn = stages == 2 ? reinterpret_cast<const void *>(score_tcgen05_kernel<2, 3, 2>)
+                 : epi == 4    ? reinterpret_cast<const void *>(score_tcgen05_kernel<3, 2, 4>)
+                               : reinterpret_cast<const void *>(score_tcgen05_kernel<3, 2, 2>);
+  if (int rc2 = ensure_dynamic_smem(fn, smem, "score_tcgen05_kernel")) return rc2;
   cudaError_t e = stages == 2
-      ? launch_kernel(score_tcgen05_kernel<2, 3>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p)
-      : launch_kernel(score_tcgen05_kernel<3, 2>, dim3(cpr, BH), dim3(kSmThreads), smem, st, /*pdl=*/true, map, p);
+      ? launch_kernel(score_tcgen05_kernel<2, 3, 2>, dim3(cpr, BH), dim3(64 + 2 * 128), smem, st, /*pdl=*/true, map, p)
+      : epi == 4 ? launch_kernel(score_tcgen05_kernel<3, 2, 4>, dim3(cpr, BH), dim3(64 + 4 * 128), smem, st, /*pdl=*/true, map, p)
+                 : launch_kernel(score_tcgen05_kernel<3, 2, 2>, dim3(cpr, BH), dim3(64 + 2 * 128), smem, st, /*pdl=*/true, map, p);
   if (e != cudaSuccess) { set_error("score_tcgen05_kernel: %s", cudaGetErrorString(e)); return int(e); }
   return launch_status("score_tcgen05_kernel");
 }

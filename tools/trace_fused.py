@@ -45,7 +45,11 @@ def main():
     t0 = sc[0][20]
     us = lambda t: "-" if t == 0 else f"{(t - t0) / 1e3:7.2f}"   # noqa: E731
     print(f"last layer of the last token; times in us since the scoring kernel's CTA (0,0) started; hits row 0: {int(cache.cnts_all[L - 1][0])}")
-    print(f"score  cta(0,0): start {us(sc[0][20])} end {us(sc[0][23])}")
+    for r, name in ((0, "cta(0,0)"), (1, "last cta")):
+        print(f"score  {name}: start {us(sc[r][20])} past its wait {us(sc[r][21])} q staged {us(sc[r][22])} tiles in smem "
+              f"{us(sc[r][24])} {us(sc[r][25])} {us(sc[r][26])} {us(sc[r][27])} end {us(sc[r][23])}")
+    merged = [fa[t][14] for t in range(256) if fa[t][14] > t0]
+    print(f"fused launch: row 0 merged {us(max(merged)) if merged else '-'} (a step takes one period; the previous layer's merge = this minus the period)")
     print(f"select row 0   : past its wait {us(se[0][21])} table written {us(se[0][22])}")
     names = ["start", "idx", "ldV", "mma", "stats", "V1st", "issued", "landed", "Vall", "sync", "part", "waited", "dots", "end", "MERGED"]
     print("tile CTAs of row 0:  " + " ".join(f"{n:>7}" for n in names))
