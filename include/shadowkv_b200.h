@@ -206,6 +206,17 @@ typedef struct skv_geom {
  * sets this flag; the kernel then loads nothing ahead of griddepcontrol.wait. */
 #define SKV_GEOM_DYNAMIC_LANDMARKS 1
 
+/* Output hand-over into the scoring launch (round 2).  With wait_flags set, the flag words normally come ON TOP of the
+ * launch's wait for its stream predecessor.  When the predecessor is the skv_fetch_rebuild_attend launch whose merging
+ * CTAs raise exactly those words (skv_exchange), the words already say everything the scoring launch consumes from it:
+ * all rows of the previous layer's attention output are written.  With this bit the launch therefore waits for the
+ * words only, does its work, and executes its wait for the predecessor's completion (and flush) at its very END, so the
+ * ~2 us between "last row merged" and "grid complete, memory flushed, dependents released" leave the per-layer chain
+ * while every kernel behind the scoring launch keeps the transitive guarantee that the predecessor has completed.
+ * Only valid when every output of the predecessor that this launch (q, the appended rows' buffers, the score scratch)
+ * touches is covered by the words; ignored without wait_flags. */
+#define SKV_GEOM_WAIT_FLAGS_ONLY 2
+
 /* Optional fused append (a2) for the scoring launch: the new token's K and V rows [B,H,D] are written at
  * buffer row pos (+ *pos_dev when pos_dev != NULL) of every (b,h) by the first CTA of each row, which saves
  * the separate skv_append_kv launch on the critical path. */
@@ -330,7 +341,10 @@ int skv_fetch_and_rebuild(const skv_geom *geom, const skv_bf16 *v_host, int64_t 
  * gathered buffer over NVLink (peer-mapped pointers, e.g. torch symmetric memory) and then raises THAT ROW's flag word
  * on every peer (one system-scope fence, then the stores) with the value of *epoch_dev (a device counter the caller
  * advances once per token and never rewinds): no counting of rows, no second fence on the chain.  The consumer waits for
- * all N * B * H/N row words of the layer: skv_geom.wait_flags (inside the next scoring launch) or skv_wait_flags. */
+ * all N * B * H/N row words of the layer: skv_geom.wait_flags (inside the next scoring launch) or skv_wait_flags.
+ * world == 1 with peer_out[0] == NULL is the ONE-GPU form of the same hand-over: no copy of the row, only the row's flag
+ * word (device-scope fence); with SKV_GEOM_WAIT_FLAGS_ONLY the next layer's scoring launch starts on the rows' words
+ * instead of on the completion of this grid. */
 #define SKV_MAX_PEERS 8
 typedef struct skv_exchange {
   int32_t world;                      /* number of ranks (0: no exchange)                                              */

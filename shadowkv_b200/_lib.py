@@ -23,6 +23,7 @@ class Geom(C.Structure):
 
 
 GEOM_DYNAMIC_LANDMARKS = 1   # SKV_GEOM_DYNAMIC_LANDMARKS
+GEOM_WAIT_FLAGS_ONLY = 2     # SKV_GEOM_WAIT_FLAGS_ONLY
 
 
 class Append(C.Structure):

@@ -213,9 +213,19 @@ __device__ __forceinline__ void fa_merge(const FaParams &p, const int bh, const 
     *reinterpret_cast<uint2 *>(p.out + at) = packed;
     // kv-head split: the row's output goes straight into every peer's gathered buffer over NVLink (P2P stores); no
     // collective launch on the chain
-    for (int r = 0; r < p.xc.world; ++r) *reinterpret_cast<uint2 *>(static_cast<skv_bf16 *>(p.xc.peer_out[r]) + at) = packed;
+    for (int r = 0; r < p.xc.world; ++r)
+      if (p.xc.peer_out[r]) *reinterpret_cast<uint2 *>(static_cast<skv_bf16 *>(p.xc.peer_out[r]) + at) = packed;
   }
-  if (p.xc.world > 0) {
+  if (p.xc.world == 1 && !p.xc.peer_out[0]) {
+    // One-GPU form (SKV_GEOM_WAIT_FLAGS_ONLY in the next scoring launch): the row's output is in `out`; raise the row's
+    // word behind it.  Device scope is enough, the consumer runs on this GPU.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int epoch = *p.xc.epoch_dev;
+      __threadfence();
+      asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.xc.peer_flags[0] + bh), "r"(epoch) : "memory");
+    }
+  } else if (p.xc.world > 0) {
     // The row's flag word on every peer: the barrier makes the CTA's remote stores precede thread 0's fence (fences are
     // cumulative), one system-scope fence orders them in front of the flag stores.
     __syncthreads();
@@ -967,8 +977,9 @@ int skv_fetch_rebuild_attend(const skv_geom *g, const skv_bf16 *v_store, int64_t
     if (exchange->world > SKV_MAX_PEERS || !exchange->epoch_dev) {
       set_error("fetch_rebuild_attend: exchange needs 1..%d peers and epoch_dev", SKV_MAX_PEERS); return SKV_ERR_ARGUMENT;
     }
+    const bool local = exchange->world == 1 && !exchange->peer_out[0];   // one-GPU hand-over: the row's flag word only
     for (int r = 0; r < exchange->world; ++r)
-      if (!exchange->peer_out[r] || !exchange->peer_flags[r]) { set_error("fetch_rebuild_attend: null peer pointer"); return SKV_ERR_ARGUMENT; }
+      if ((!exchange->peer_out[r] && !local) || !exchange->peer_flags[r]) { set_error("fetch_rebuild_attend: null peer pointer"); return SKV_ERR_ARGUMENT; }
     p.xc = *exchange;
   }
   p.G = g->q_groups; p.Gp = (g->q_groups + 3) / 4 * 4;

@@ -28,7 +28,7 @@ int launch_score_select(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
                           int64_t buf_rows, bool dynamic_landmarks, const int32_t *wait_flags = nullptr,
-                          const int32_t *wait_epoch_dev = nullptr, int wait_count = 0);
+                          const int32_t *wait_epoch_dev = nullptr, int wait_count = 0, bool wait_only = false);
 
 constexpr int kScoreThreads = 256;   // 8 warps
 
@@ -714,7 +714,8 @@ int skv_score_landmarks(const skv_geom *g, const skv_bf16 *q, const skv_bf16 *la
     return launch_scores_tcgen05(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                                  g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append,
                                  g->buf_len, (g->flags & SKV_GEOM_DYNAMIC_LANDMARKS) != 0, g->wait_flags,
-                                 g->wait_epoch_dev, g->wait_count);
+                                 g->wait_epoch_dev, g->wait_count,
+                                 (g->flags & SKV_GEOM_WAIT_FLAGS_ONLY) != 0 && !(g->flags & SKV_GEOM_DYNAMIC_LANDMARKS));
   if (g->wait_flags) { set_error("score_landmarks: the SIMT cross-check kernel has no flag wait"); return SKV_ERR_UNSUPPORTED; }
   return launch_scores<16>(q, landmarks, w.scores, w.pmax, w.psum, g->batch * g->kv_heads, g->q_groups,
                            g->n_landmarks, w.ldn, w.T, 0.08838834764831845f, as_stream(stream), append, g->buf_len);

@@ -41,6 +41,7 @@ struct ScoreMmaParams {
   int64_t buf_rows;
   const int32_t *wait_flags, *wait_epoch_dev;   // kv-head split: peers' flags of the previous layer (skv_geom.wait_flags)
   int wait_count;
+  int wait_only;                                // SKV_GEOM_WAIT_FLAGS_ONLY: the flag words cover the predecessor's outputs
 };
 
 template <int kSmStages, int kCtasPerSm, int kEpi>
@@ -95,8 +96,12 @@ __global__ void __launch_bounds__(64 + kEpi * 128, kCtasPerSm)
   // TMEM does not depend on the predecessor either (attention and selection hold none; a rebuild CTA that is still
   // resident keeps 128 of the 512 columns)
   if (warp == 1) tcgen05_alloc(tmem_slot, kEpi * kSmAccCols);
-  // everything below touches data of the predecessor (q, the K/V buffers, the score scratch)
-  pdl_wait();
+  // everything below touches data of the predecessor (q, the K/V buffers, the score scratch).  With
+  // SKV_GEOM_WAIT_FLAGS_ONLY the predecessor's merging CTAs raise one word per row behind the row's output, which is all
+  // this launch consumes from it: the wait for the predecessor's COMPLETION moves to the end of the kernel (dependents
+  // keep the transitive guarantee), and its completion + flush latency leaves the chain.
+  const bool flags_only = p.wait_flags != nullptr && p.wait_only != 0;
+  if (!flags_only) pdl_wait();
   if (threadIdx.x == 0) SKV_STAMP_NS(trn, 21);
   if (p.wait_flags) {
     // kv-head split: the query of this layer depends on the previous layer's GATHERED attention output; every peer raises
@@ -250,12 +255,13 @@ __global__ void __launch_bounds__(64 + kEpi * 128, kCtasPerSm)
   SKV_STAMP(tr, 15);
   if (threadIdx.x == 0) SKV_STAMP_NS(trn, 23);
   if (warp == 1) tcgen05_dealloc(tmem_base, kEpi * kSmAccCols);
+  if (flags_only) pdl_wait();                   // see above: completion of the predecessor, for the kernels behind this one
 }
 
 int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *scores, float *pmax, float *psum, int BH, int G,
                           int N, int ldn, int T, float alpha, cudaStream_t st, const skv_append *append,
                           int64_t buf_rows, bool dynamic_landmarks, const int32_t *wait_flags,
-                          const int32_t *wait_epoch_dev, int wait_count) {
+                          const int32_t *wait_epoch_dev, int wait_count, bool wait_only) {
   CUtensorMap map;
   int rc = make_tensor_map_2d(&map, lm, uint64_t(BH) * N, kHeadDim, kSmTileRows, 64);
   if (rc) return rc;
@@ -268,6 +274,7 @@ int launch_scores_tcgen05(const skv_bf16 *q, const skv_bf16 *lm, skv_bf16 *score
   if (append) p.ap = *append;
   if (wait_flags && wait_epoch_dev && wait_count > 0) {
     p.wait_flags = wait_flags; p.wait_epoch_dev = wait_epoch_dev; p.wait_count = wait_count;
+    p.wait_only = wait_only ? 1 : 0;
   }
   // two (or three) CTAs per SM; every CTA of a row strides over that row's tiles
   static const int stages = [] { const char *e = getenv("SKV_SCORE_STAGES"); return (e && e[0] == '2') ? 2 : 3; }();

@@ -58,6 +58,15 @@ class DecodeStepGraph:
                 world = dist.get_world_size() if dist.is_initialized() else 1
                 self.out_all = torch.zeros(L, world, B, 1, Hq, D, dtype=dt, device=dev)
                 self.exchange = "NCCL all_gather_into_tensor, one node per layer inside the captured graph"
+        # one GPU: per-row hand-over of a layer's attention output into the next layer's scoring launch
+        # (parallel.RowHandover).  A measured experiment, OFF by default (SKV_OUT_FLAGS=1 enables it): bit-identical, but
+        # not faster than the plain dependent launch -- 61.4 / 61.7 against 61.4 / 60.9 us per layer-step with V on the
+        # host, 32.6 against 31.9 with V in HBM: the fence + flag store of the merging CTA and the poll round trip cost
+        # what the grid's completion signal costs, so the gap between two layers is work (late rows), not launch latency
+        self.handover = None
+        if (not gather_heads and L > 1 and cache.fused_fetch_rebuild and cache.can_fuse_attend()
+                and os.environ.get("SKV_OUT_FLAGS", "0") == "1"):
+            self.handover = parallel.RowHandover(L, B * H, dev)
         if host_io:
             self.q_h = torch.zeros(L, B, Hq, 1, D, dtype=dt).pin_memory()
             self.k_h = torch.zeros(L, B, H, 1, D, dtype=dt).pin_memory()
@@ -102,6 +111,13 @@ class DecodeStepGraph:
             # start before every peer's rows have arrived.  Between layers the next scoring launch waits for the flags
             # itself (SKV_HEAD_WAIT=launch keeps a flag-wait launch per layer); the last layer gets the wait launch
             inline_wait = self.xchg is not None and self.inline_wait
+            if self.handover is not None:
+                # a layer's scoring launch directly follows the previous layer's fused launch on the stream: it starts on
+                # that launch's row words (layer 0 follows the token's bookkeeping nodes and waits as usual)
+                c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
+                               device_counters=True, exchange=self.handover.struct(l),
+                               wait_for=self.handover.wait_spec(l - 1) if l > 0 else None, wait_only=l > 0)
+                continue
             c.decode_layer(l, self.q_d[l], self.k_d[l], self.v_d[l], self.cos_sin, out=self.out_d[l],
                            device_counters=True, exchange=self.xchg.struct(l) if self.xchg is not None else None,
                            wait_for=self.xchg.wait_spec(l - 1) if inline_wait and l > 0 else None)
@@ -114,6 +130,8 @@ class DecodeStepGraph:
         c.advance_device_counters()
         if self.xchg is not None:
             self.xchg.advance()
+        if self.handover is not None:
+            self.handover.advance()
         if self.host_io:
             self.out_h.copy_(self.out_all if self.gather else self.out_d, non_blocking=True)
 

@@ -648,7 +648,8 @@ class ShadowKVCache_CPU:
         return out
 
     def decode_layer(self, layer_idx, query_states, key_states, value_states, cos_sin_cache, out=None,
-                     device_counters=False, after_select=None, before_attention=None, exchange=None, wait_for=None):
+                     device_counters=False, after_select=None, before_attention=None, exchange=None, wait_for=None,
+                     wait_only=False):
         """The whole per-layer sparse-KV decode step, with the reference's stream choreography
         (base.py:320-341): append -> select -> {V fetch on copy_stream || K compact + rebuild} -> attention.
         query_states [B,Hq,1,D], key_states/value_states [B,H,1,D], all post-RoPE.  Returns [B,1,Hq,D].
@@ -685,6 +686,10 @@ class ShadowKVCache_CPU:
             # kv-head split: (flags pointer, count, epoch pointer) of the PREVIOUS layer's exchange; the scoring launch
             # waits for them itself (skv_geom.wait_flags) instead of a flag-wait launch between the layers
             g.wait_flags, g.wait_count, g.wait_epoch_dev = wait_for
+            if wait_only:
+                # the words are raised by the launch right in front of this layer's scoring launch and cover everything
+                # it consumes from it (parallel.RowHandover): wait for them INSTEAD of for that launch's completion
+                g.flags |= _lib.GEOM_WAIT_FLAGS_ONLY
         try:
             pid = self.get_retrieval_position_ids(layer_idx, query_states, append=ap)
         except Exception:
@@ -692,6 +697,7 @@ class ShadowKVCache_CPU:
             raise
         finally:
             g.wait_flags, g.wait_count, g.wait_epoch_dev = None, 0, None
+            g.flags &= ~_lib.GEOM_WAIT_FLAGS_ONLY
         if after_select is not None:
             # hook of the whole-model runner: from here until the attention the step waits on PCIe and leaves HBM
             # idle; the runner uses the window to pull the next dense weights into L2 on its own stream

@@ -166,3 +166,30 @@ class HeadExchange:
     def advance(self):
         """Next token: epoch += 1 on the device (part of the captured step; never rewound)."""
         self.epoch.add_(1)
+
+
+class RowHandover:
+    """One-GPU form of the hand-over ``HeadExchange`` does between ranks: the CTA that merges a (b, kv head) row inside
+    ``skv_fetch_rebuild_attend`` raises that row's word (value = the token's epoch) behind the row's attention output,
+    and the NEXT layer's scoring launch starts on the words of all rows (``SKV_GEOM_WAIT_FLAGS_ONLY``) instead of on the
+    completion and flush of the whole grid; it executes its wait for that completion at its end, so every later kernel
+    keeps the transitive guarantee.  ``flags [layers, rows]`` int32, ``epoch`` a device counter advanced once per token."""
+
+    def __init__(self, layers: int, rows: int, device):
+        self.layers, self.rows = int(layers), int(rows)
+        self.flags = torch.zeros(self.layers, self.rows, dtype=torch.int32, device=device)
+        self.epoch = torch.ones(1, dtype=torch.int32, device=device)       # flags start at 0 < epoch 1
+
+    def struct(self, layer: int):
+        from . import _lib
+        ex = _lib.Exchange(world=1, rank=0)
+        ex.peer_flags[0] = self.flags.data_ptr() + layer * self.rows * 4     # peer_out[0] stays NULL: no copy of the row
+        ex.epoch_dev = self.epoch.data_ptr()
+        return ex
+
+    def wait_spec(self, layer: int):
+        return (self.flags.data_ptr() + layer * self.rows * 4, self.rows, self.epoch.data_ptr())
+
+    def advance(self):
+        self.epoch.add_(1)
+

@@ -114,3 +114,35 @@ def test_peer_store_exchange_single_rank(cuda):
         # warm-up token used epoch 1; this replay is epoch t + 2, and the device counter already points at the next one
         assert int(run.xchg.epoch) == t + 3
         assert bool((run.xchg.flags == t + 2).all()), run.xchg.flags
+
+
+@pytest.mark.parametrize("B,layers", [(1, 6), (4, 3)])
+def test_output_row_handover_equals_plain_dependent_launches(cuda, monkeypatch, B, layers):
+    """One-GPU hand-over of a layer's attention output into the next layer's scoring launch (parallel.RowHandover,
+    SKV_GEOM_WAIT_FLAGS_ONLY): the scoring launch starts on the previous fused launch's row words and waits for that
+    launch's completion at its end.  Chunk tables, K / V buffers and outputs must be bit-identical to the runner with
+    plain dependent launches (SKV_OUT_FLAGS=0) over many tokens, and every row word must carry the token's epoch."""
+    from shadowkv_b200.engine import DecodeStepGraph
+    shape = synth.MODELS["llama-3.1-8b"]
+    prompt_len, budget, tokens = 8192, 1024, 24
+    cs = synth.cos_sin_table(prompt_len + 1024)
+    d_cs = cs.to(cuda)
+    runs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("SKV_OUT_FLAGS", on)
+        c = _cache(cuda, shape, B, prompt_len, budget, layers, cs)
+        runs.append(DecodeStepGraph(c, d_cs, host_io=False).capture(warmup=1))
+    assert runs[0].handover is not None and runs[1].handover is None
+    g = torch.Generator().manual_seed(11)
+    base = torch.randn(layers, B, 32, 1, 128, generator=g)
+    for t in range(tokens):
+        q = (0.95 * base + 0.3 * torch.randn(layers, B, 32, 1, 128, generator=g)).to(torch.bfloat16).to(cuda)
+        k = torch.randn(layers, B, 8, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+        v = torch.randn(layers, B, 8, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+        outs = [r.step_device(q, k, v) for r in runs]
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), f"attention outputs differ at token {t}"
+        assert torch.equal(runs[0].cache.position_ids, runs[1].cache.position_ids), f"chunk table differs at token {t}"
+        assert bool((runs[0].handover.flags == t + 2).all()), runs[0].handover.flags
+    assert torch.equal(runs[0].cache.k_cache_buffer, runs[1].cache.k_cache_buffer)
+    assert torch.equal(runs[0].cache.v_cache_buffer, runs[1].cache.v_cache_buffer)
