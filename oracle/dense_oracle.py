@@ -37,6 +37,8 @@ of the libraries themselves (the image's flashinfer / vllm builds and torch's cu
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 BF16 = torch.bfloat16
@@ -124,3 +126,70 @@ def lm_head(x, norm_w, eps, w_head):
 def greedy(logits: torch.Tensor) -> torch.Tensor:
     """tensor_op.py:291-293 with temperature 0."""
     return logits.argmax(dim=-1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Prompt (prefill) path of the dense stack: models/base.py:131-159 (inference), 296-318 (layer_compute, prefill branch),
+# models/llama.py:354-427.  Same operators as above applied to [B, L, hidden]; the attention of base.py:313
+# (flash_attn_with_kvcache, causal) is restated as a plain fp32 softmax(q k^T / sqrt(128)) v rounded once to bf16.
+# ---------------------------------------------------------------------------------------------------------------------
+def rotary_positions(x: torch.Tensor, cos_sin_rows: torch.Tensor, neox: bool) -> torch.Tensor:
+    """vllm rotary_embedding for x [B, heads, L, 128] bf16 at the L positions whose table rows are cos_sin_rows [L, rot]
+    (fp32 expression, one rounding; see rotary_vllm)."""
+    rot = cos_sin_rows.shape[-1]
+    half = rot // 2
+    c, s = cos_sin_rows[:, :half].float(), cos_sin_rows[:, half:].float()
+    xf = x.float()
+    out = xf.clone()
+    if neox:
+        a, b = xf[..., :half], xf[..., half:rot]
+        out[..., :half] = a * c - b * s
+        out[..., half:rot] = b * c + a * s
+    else:
+        a, b = xf[..., 0:rot:2], xf[..., 1:rot:2]
+        out[..., 0:rot:2] = a * c - b * s
+        out[..., 1:rot:2] = b * c + a * s
+    return out.to(BF16)
+
+
+def causal_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """q [B, Hq, L, 128], k / v [B, H, L, 128] bf16 -> [B, L, Hq * 128] bf16 (query head j uses kv head j // (Hq / H))."""
+    B, Hq, L, D = q.shape
+    g = Hq // k.shape[1]
+    kf, vf = k.float().repeat_interleave(g, dim=1), v.float().repeat_interleave(g, dim=1)
+    mask = torch.ones(L, L, dtype=torch.bool).tril()
+    out = torch.empty(B, Hq, L, D)
+    for b in range(B):
+        for h in range(Hq):
+            sc = (q[b, h].float() @ kf[b, h].T) / math.sqrt(D)
+            sc = sc.masked_fill(~mask, float("-inf"))
+            out[b, h] = torch.softmax(sc, dim=-1) @ vf[b, h]
+    return out.to(BF16).transpose(1, 2).reshape(B, L, Hq * D)
+
+
+def prefill_layer(x, lw, q_heads, kv_heads, cos_sin_rows, rope_mode):
+    """One decoder layer over a prompt.  x [B, L, hidden] bf16; lw: dict with ln1, ln2, eps, wqkv, bqkv, wo, w_gate_up,
+    w_down.  Returns (hidden states [B, L, hidden], dict(k_pre [B,H,L,128], k_roped, v, q_roped))."""
+    B, L, hid = x.shape
+    qkv = linear(rmsnorm(x, lw["ln1"], lw["eps"]), lw["wqkv"], lw.get("bqkv")).view(B, L, q_heads + 2 * kv_heads, 128)
+    q, k, v = (t.transpose(1, 2) for t in qkv.split([q_heads, kv_heads, kv_heads], dim=2))
+    qr, kr = q, k
+    if rope_mode:
+        qr = rotary_positions(q, cos_sin_rows, neox=rope_mode == 1)
+        kr = rotary_positions(k, cos_sin_rows, neox=rope_mode == 1)
+    attn = causal_attention(qr, kr, v)
+    h = add_bf16(x, linear(attn, lw["wo"]))
+    act = silu_and_mul(linear(rmsnorm(h, lw["ln2"], lw["eps"]), lw["w_gate_up"]))
+    return add_bf16(h, linear(act, lw["w_down"])), dict(k_pre=k, k_roped=kr, v=v, q_roped=qr)
+
+
+def prefill_logits(ids, embed, layers, norm_w, eps, w_head, q_heads, kv_heads, cos_sin, rope_mode):
+    """base.py:131-159 for a prompt: ids [B, L] -> (logits of the last position [B, 1, vocab] float32, per-layer dicts of
+    prefill_layer)."""
+    x = embed[ids]
+    rows = cos_sin[: ids.shape[1]]
+    per_layer = []
+    for lw in layers:
+        x, d = prefill_layer(x, lw, q_heads, kv_heads, rows, rope_mode)
+        per_layer.append(d)
+    return lm_head(x[:, -1:, :], norm_w, eps, w_head), per_layer

@@ -5,8 +5,13 @@ kv_cache.py -> Parts 1-2).  One class serves Llama-3 / 3.1, Yi (same architectur
 rotary embedding over 64 dims); the differences are data (``ModelShape.glm_rope``), not code paths.
 
 There is no hub access here, so ``init_parameters`` draws random weights N(0, 0.02) of the named architecture (the
-reference loads them from ``LlamaForCausalLM.from_pretrained``, llama.py:310-352).  Prefill of the dense stack
-(q_len > 1) is outside this path and raises.
+reference loads them from ``LlamaForCausalLM.from_pretrained``, llama.py:310-352).
+
+Prefill (base.py:163-187, 296-318, 500-550): ``prefill`` / ``batch_prefill`` run the prompt
+through the dense stack with LIBRARY kernels, as the reference does -- cuBLAS ``F.linear``, torch scaled-dot-product
+attention (flash backend) in place of ``flash_attn_with_kvcache`` -- and build the decode state of every layer through
+``ShadowKVCache_CPU.get_svd`` / ``prefill_kv_cache`` (this repo's CUDA kernels, csrc/prefill.cu).  It is one-off work
+per prompt, outside the decode step this repo is about; nothing of it runs when a token is decoded.
 """
 from __future__ import annotations
 
@@ -152,8 +157,10 @@ class Llama:
     def layer_compute(self, buffer: LlamaLayer, layer_idx: int, hidden_states, position_ids):
         """base.py:296-349, decode branch: hidden_states [B,1,hidden], position_ids [B,1] (all rows equal, as the
         reference's generate loop makes them, base.py:628-636)."""
+        if hidden_states.shape[1] > 4 * 1024:                            # base.py:296: the prefill branch
+            return self._prefill_layer(buffer, layer_idx, hidden_states, position_ids)
         if hidden_states.shape[1] != 1:
-            raise NotImplementedError("prefill (q_len > 1) of the dense stack is outside the decode path of this repo")
+            raise NotImplementedError("multi-token continuation (1 < q_len <= 4096, base.py:189 prefill_cont) is not built")
         pos = int(position_ids.reshape(-1)[0])
         residual = hidden_states.reshape(-1, self.hidden_size).contiguous()
         q, k, v = self.pre_attention_compute(residual, buffer, self.num_heads, self.num_key_value_heads, self.head_dim,
@@ -162,12 +169,133 @@ class Llama:
         return self.post_attention_compute(attn, residual, buffer).view(-1, 1, self.hidden_size)
 
     def inference(self, input_ids, position_ids):
-        """base.py:131-159 for a decode token: [B,1] ids -> logits [B,1,vocab] float32."""
+        """base.py:131-159: [B,1] ids (decode token) or [B,L] ids with L > 4096 (prompt) -> logits [B,1,vocab] float32
+        (for a prompt only the last position goes through the lm_head, base.py:153-155)."""
         hidden_states = self.embed_tokens[input_ids]                      # F.embedding, base.py:141
         for idx in range(self.num_layers):
             hidden_states = self.layer_compute(self.layers[idx], idx, hidden_states, position_ids)
-        h = dense.rmsnorm(hidden_states.reshape(-1, self.hidden_size), self.norm_weight, self.norm_variance_epsilon)
+        if hidden_states.shape[1] > 16:
+            hidden_states = hidden_states[:, -1:, :]
+        h = dense.rmsnorm(hidden_states.reshape(-1, self.hidden_size).contiguous(), self.norm_weight,
+                          self.norm_variance_epsilon)
         return dense.linear_f32(h, self.lm_head, static_weights=True).view(-1, 1, self.vocab_size)
+
+    # ---- prefill (section 8 f4): library kernels for the dense stack, this repo's kernels for the decode state ------
+    def get_ctx(self, input_ids):
+        """base.py:109-126: position ids of `input_ids` behind what the cache already holds."""
+        past, n = self.kv_cache.get_kv_len(), input_ids.size(1)
+        return torch.arange(past, past + n, device=self.device, dtype=torch.long).unsqueeze(0).repeat(input_ids.size(0), 1)
+
+    def apply_rotary_pos_emb(self, query_states, key_states, position_ids):
+        """llama.py:283-301 / glm.py:406-428 (vllm ``rotary_embedding``: neox pairs (j, j+64) over 128 dims, GLM pairs
+        (2j, 2j+1) over the first 64) for [bsz, heads, L, 128] tensors, every row of position_ids equal: the expression
+        is evaluated in fp32 and rounded once, like the vllm build of this image (oracle/dense_oracle.py)."""
+        rows = self.cos_sin_cache[position_ids[0]]                          # [L, rot] = [cos | sin]
+        half = rows.shape[-1] // 2
+        c, s_ = rows[:, :half].float(), rows[:, half:].float()
+
+        def rot(x):
+            xf = x.float()
+            if not self.shape.glm_rope:
+                a, b = xf[..., :half], xf[..., half:]
+                return torch.cat([a * c - b * s_, b * c + a * s_], dim=-1).to(BF16)
+            a, b = xf[..., 0:2 * half:2], xf[..., 1:2 * half:2]
+            o = torch.stack([a * c - b * s_, b * c + a * s_], dim=-1).flatten(-2)
+            return torch.cat([o, xf[..., 2 * half:]], dim=-1).to(BF16)
+
+        return rot(query_states), rot(key_states)
+
+    @staticmethod
+    def _causal_attention(q, k, v):
+        """Stands in for ``flash_attn_with_kvcache(q, k, v, causal=True)`` of base.py:313 on the prompt: torch SDPA with the
+        memory-efficient backends only (the math backend would materialise an L x L score matrix per head).
+        q [bsz,Hq,L,D], k / v [bsz,H,L,D] -> [bsz,L,Hq*D]."""
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        with sdpa_kernel([SDPBackend.FLASH_ATTENTION, SDPBackend.CUDNN_ATTENTION, SDPBackend.EFFICIENT_ATTENTION]):
+            try:
+                o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
+            except RuntimeError:                                          # a backend without grouped-query support
+                g = q.shape[1] // k.shape[1]
+                o = F.scaled_dot_product_attention(q, k.repeat_interleave(g, dim=1), v.repeat_interleave(g, dim=1),
+                                                   is_causal=True)
+        return o.transpose(1, 2).reshape(q.shape[0], q.shape[2], -1)
+
+    def _prefill_layer(self, buffer: LlamaLayer, layer_idx: int, hidden_states, position_ids, mlp_rows: int = 32768):
+        """base.py:296-318 + llama.py:354-427 for a prompt [bsz, L, hidden] (L > 4096): QKV, low-rank factors of the
+        pre-RoPE keys (get_svd), RoPE, the layer's decode state (prefill_kv_cache), causal attention, o_proj and the MLP
+        (in blocks of `mlp_rows` tokens, which bounds the 2 x FFN-wide intermediate)."""
+        import torch.nn.functional as F
+        bsz, L, hid = hidden_states.shape
+        Hq, H, D = self.num_heads, self.num_key_value_heads, self.head_dim
+        x = hidden_states.reshape(bsz * L, hid)
+        x = x if x.is_contiguous() else x.contiguous()
+        h = dense.rmsnorm(x, buffer.input_layernorm_weight, buffer.input_layernorm_variance_epsilon)
+        qkv = F.linear(h, buffer.wqkv, buffer.bqkv).view(bsz, L, Hq + 2 * H, D)
+        del h
+        q, k, v = (t.transpose(1, 2) for t in qkv.split([Hq, H, H], dim=2))      # [bsz, heads, L, D] views
+        self.kv_cache.get_svd(k, layer_idx=layer_idx)
+        q, k = self.apply_rotary_pos_emb(q, k, position_ids)
+        v = v.contiguous()
+        del qkv
+        self.kv_cache.prefill_kv_cache(v, layer_idx, k, q[:, :, -1:])
+        attn = self._causal_attention(q, k, v)
+        del q, k, v
+        x1 = x + F.linear(attn.reshape(bsz * L, Hq * D), buffer.wo)               # llama.py:408-411
+        del attn
+        ffn = self.shape.intermediate_size
+        out = torch.empty_like(x1)
+        for r0 in range(0, bsz * L, mlp_rows):
+            xs = x1[r0:r0 + mlp_rows]
+            gu = F.linear(dense.rmsnorm(xs, buffer.post_attention_layernorm_weight,
+                                        buffer.post_attention_layernorm_variance_epsilon), buffer.gate_up_proj)
+            act = F.silu(gu[:, :ffn]) * gu[:, ffn:]                               # vllm silu_and_mul, llama.py:416-421
+            out[r0:r0 + mlp_rows] = xs + F.linear(act, buffer.down_proj)          # llama.py:424-426
+        return out.view(bsz, L, hid)
+
+    @torch.inference_mode()
+    def prefill(self, input_ids):
+        """base.py:163-187: clear the cache, run the prompt, return the last position's logits [bsz, 1, vocab]."""
+        self.kv_cache.clear()
+        logits = self.inference(input_ids=input_ids, position_ids=self.get_ctx(input_ids))
+        assert self.kv_cache.get_kv_len() == input_ids.shape[-1], \
+            f"KV length mismatch, got {self.kv_cache.get_kv_len()}, expected {input_ids.shape[-1]}"
+        return logits
+
+    @torch.inference_mode()
+    def batch_prefill(self, input_ids, sub_batch: int | None = None):
+        """base.py:500-550: the prompts of the whole batch in sub-batches (the reference takes 8 sequences at a time
+        between 120K and 200K tokens and 4 otherwise; here the default is 1 above 64K tokens, which keeps the fp32
+        key matrix of get_svd and the attention inputs of a sub-batch within a few GB)."""
+        self.kv_cache.clear()
+        bsz, L = input_ids.shape
+        assert bsz == self.batch_size, f"batch_size mismatch, got {bsz}, expected {self.batch_size}"
+        if L > self.max_length:
+            raise ValueError(f"Input length must be less than {self.max_length}, but got {L}")
+        T = sub_batch or (1 if L > 64 * 1024 else 4)
+        logits = torch.zeros(bsz, 1, self.vocab_size, device=self.device, dtype=torch.float32)
+        for b0 in range(0, bsz, T):
+            ids = input_ids[b0:b0 + T]
+            logits[b0:b0 + T].copy_(self.inference(input_ids=ids, position_ids=self.get_ctx(ids)))
+        assert self.kv_cache.get_kv_len() == L, f"KV length mismatch, got {self.kv_cache.get_kv_len()}, expected {L}"
+        return logits
+
+    @torch.inference_mode()
+    def generate_from_prompt(self, input_ids, gen_len: int = 256, temperature: float = 0.0, top_p: float = -1,
+                             top_k: int = 50, benchmark: bool = False):
+        """``LLM.batch_generate`` of base.py:573-655 from token ids: batch_prefill -> sample the first token -> H2D ->
+        the decode loop (``batch_generate`` below).  Returns [B, 1 + gen_len] ids (first sampled token included)."""
+        from .tensor_op import sample_token
+        logits = self.batch_prefill(input_ids)
+        next_token = sample_token(logits[:, -1, :], temperature=temperature, top_p=top_p, top_k=top_k)
+        self.kv_cache.H2D()
+        self.graph = None                                                 # the captured token belongs to the old state
+        self._prepared = False
+        res = self.batch_generate(next_token, gen_len=gen_len, temperature=temperature, top_p=top_p, top_k=top_k,
+                                  benchmark=benchmark)
+        ids = res[0] if benchmark else res
+        ids = torch.cat([next_token.reshape(-1, 1).to(ids.device), ids], dim=1)
+        return (ids, res[1]) if benchmark else ids
 
     # ---- one decode token with device-side counters: the body of the CUDA graph ---------------------------------
     def _pre_attention_step(self, l: int):
