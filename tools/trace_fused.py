@@ -36,8 +36,11 @@ def main():
     synth.install(cache, states)
     run = DecodeStepGraph(cache, cs, host_io=False).capture(warmup=1)
     base = torch.randn(L, B, 32, 1, 128, device=dev)
+    noise = 0.28                                   # --noise N: query innovation between tokens (1.0: every chunk misses)
+    if "--noise" in sys.argv:
+        noise = float(sys.argv[sys.argv.index("--noise") + 1])
     for t in range(6):
-        q = (0.96 * base + 0.28 * torch.randn(L, B, 32, 1, 128, device=dev)).to(torch.bfloat16)
+        q = ((1.0 - noise * noise) ** 0.5 * base + noise * torch.randn(L, B, 32, 1, 128, device=dev)).to(torch.bfloat16)
         k = torch.randn(L, B, 8, 1, 128, device=dev).to(torch.bfloat16)
         run.step_device(q, k, k)
     torch.cuda.synchronize()
