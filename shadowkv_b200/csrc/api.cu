@@ -52,7 +52,9 @@ const char *skv_active_config(void) {
   snprintf(buf, sizeof(buf),
            "score=%s select=%s rebuild=%s attention=%s attend_fusion=%s pdl=%s score_ring=%s score_ctas=%s",
            on("SKV_SCORE_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05+TMA",
-           (on("SKV_FUSED_SELECT", '1') && !on("SKV_SCORE_IMPL", '1')) ? "fused-with-scoring(experiment)" : "own-launch(cluster8-radix)",
+           (on("SKV_FUSED_SELECT", '1') && !on("SKV_SCORE_IMPL", '1')) ? "fused-with-scoring(experiment)"
+           : (on("SKV_SELECT_FAST", '1') && !on("SKV_SELECT_HINT", '0')) ? "own-launch(1-CTA-hinted+cluster8-radix, experiment)"
+                                                                        : "own-launch(cluster8-radix)",
            on("SKV_REBUILD_IMPL", '1') ? "SIMT(cross-check)" : "tcgen05",
            on("SKV_ATTN_IMPL", '1') ? "SIMT(cross-check)" : "mma.sync+TMA", on("SKV_FUSED_ATTEND", '0') ? "off" : "on",
            skv::pdl_enabled() ? "on" : "off", on("SKV_SCORE_STAGES", '2') ? "2x3" : "3x2", (ctas && *ctas) ? ctas : "default");

@@ -335,6 +335,8 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
                   skv_bf16 *__restrict__ score_out,           // [BH, N] or null
                   int32_t *row_flags,                         // [BH] or null: per-row hand-over to the fetch launch
                   int32_t *hint,                              // [BH] or null: the row's previous threshold key (in/out)
+                  const int32_t *fast_status,                 // [BH] or null: 1 = select_fast_kernel (launched in front of
+                                                              // this grid) has done the row; it also cleared row_flags
                   int G, int N, int ldn, int T, int per) {
   constexpr int kThreads = kT;
   static_assert(kT >= S && kT >= 256 && kT % 32 == 0, "one thread per table entry and per histogram bin");
@@ -363,14 +365,17 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
 
   // early, independent global loads: the (static) landmark ids of this thread's first 8 landmarks.  Under a
   // programmatic launch this and the histogram clearing overlap the tail of the scoring kernel.
-  if (!row_flags) pdl_launch_dependents();
+  if (!row_flags || fast_status) pdl_launch_dependents();
   const int64_t *lidx = landmark_idx + size_t(bh) * N + n_begin;
   int ids0[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) ids0[e] = (tid * 8 + e < count) ? static_cast<int>(lidx[tid * 8 + e]) : 0;   // map.cuh:776
   for (int i = tid; i < 2 * kWarps * 256; i += kThreads) whist1[i] = 0;
   pdl_wait();                                   // scores, partials and the chunk table are the predecessors' outputs
-  if (row_flags) {
+  // Rows the single-CTA fast selection has settled (its launch sits between the scoring launch and this one) are done,
+  // flag raised and all: the whole cluster leaves (uniform: one word per row), before any cluster barrier.
+  if (fast_status && __ldcg(fast_status + bh) == 1) return;
+  if (row_flags && !fast_status) {
     // Row hand-over (skv_geom.row_flags): the dependents of this launch wait for their ROW's word, not for this grid.
     // The word still carries the previous token's 1; every consumer of that value has finished (this kernel's wait
     // covers, transitively, the previous launch that read it), and no consumer of the new value exists before the
@@ -631,11 +636,243 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   if (tid == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 22);
 }
 
+// ------------------------------------------------------------------------------------------------
+// select_fast_kernel: the selection of a row by ONE CTA, without a cluster, when the previous token's threshold is a good
+// guess (skv_geom.select_hint).  The cluster kernel above spends its time in exchanges (three cluster barriers, DSMEM
+// histograms) and in G exact exponentials per landmark.  Here:
+//   1. every thread takes 16 consecutive landmarks and only forms u_g = (s_g - m_g) + log(1 / Z_g) = log p_g per head (one
+//      add per score, no exponential): a landmark whose max_g u_g lies below log(value of key win0 - 1) - 1e-3 provably
+//      has a key below the window [win0, win0 + 253] around the previous threshold (the margin covers the fp32 rounding
+//      of u_g and of the product expf(.) * inv by two orders of magnitude, and a value below the bf16 number win0 - 1
+//      cannot round up to win0), so it can neither be selected nor move the threshold when that lies in the window;
+//   2. the other landmarks (a few hundred: everything within a factor of two of the threshold) are compacted in landmark
+//      order and get their exact key, the same expression as in select_kernel; their window histogram lives in shared
+//      memory, one warp finds the threshold bin;
+//   3. ordered emission, chunk-table update, hint, row hand-over exactly as in select_kernel.
+// When the row has no hint, the threshold falls outside the window, the window reaches down into keys whose products
+// would be denormal, or the candidates overflow the list, the kernel touches nothing and leaves status[bh] = 0: the
+// cluster kernel, launched right behind this one, does the row.  status[bh] = 1: the row is done, flag raised.
+// The result never depends on which kernel produced it (test_select_fast_path_equals_cluster_kernel).
+// EXPERIMENT, not the product path (SKV_SELECT_FAST=1): measured slower than the cluster kernel alone, see the launcher.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFsThreads = 1024;
+constexpr int kFsPer = 16;                       // landmarks per thread: N <= 16384
+constexpr int kFsCap = 2048;                     // candidate list entries
+
+template <int S, bool kInPlace>
+__global__ void __launch_bounds__(kFsThreads, 1)
+    select_fast_kernel(const skv_bf16 *__restrict__ scores, const float *__restrict__ part_max,
+                       const float *__restrict__ part_sum, const int64_t *__restrict__ landmark_idx,
+                       int64_t *__restrict__ resident, int32_t *__restrict__ offsets, int32_t *__restrict__ cnts,
+                       int64_t *__restrict__ selected_out, int32_t *row_flags, int32_t *hint, int32_t *status, int G, int N,
+                       int ldn, int T) {
+  constexpr int kWarps = kFsThreads / 32;
+  __shared__ float s_m[16], s_inv[16], s_linv[16];
+  __shared__ int s_hist[256];
+  __shared__ uint16_t s_cidx[kFsCap], s_ckey[kFsCap];     // candidate: landmark (row-local), exact key
+  __shared__ int s_cval[kFsCap];                          // ... its chunk id (landmark_idx)
+  __shared__ uint2 s_cs[kFsCap];                          // ... its scores of heads 0..3 (G <= 4: no second trip to L2)
+  __shared__ int s_wa[kWarps + 1], s_wb[kWarps + 1], s_res[2];
+  __shared__ int s_new[S], s_sorted[S], s_slot[S], s_warp[33];
+  const int bh = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 256) s_hist[tid] = 0;
+  if (tid == 0) { s_res[0] = 0; s_res[1] = 0; }
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 0);
+  pdl_wait();                                   // scores, partials: the scoring launch; chunk table, hint: earlier launches
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 1);
+  if (row_flags) {                              // see select_kernel: clear the row's word, then let the dependents come
+    if (tid == 0) {
+      asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(0) : "memory");
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  pdl_launch_dependents();
+  const int hint_key = __ldcg(hint + bh);
+  const int win0 = hint_key > 0 ? max(1, hint_key - 126) : 0;
+  // the window must stay clear of keys whose fp32 product could be denormal (relative error bounds end there)
+  const bool usable = win0 >= 0x1000;           // bf16 0x1000 = 2^-95
+  int old_id = 0;
+  if (usable && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);
+  const skv_bf16 *sc = scores + size_t(bh) * G * ldn;
+  const int n0 = tid * kFsPer;
+  // the first four heads' scores of this thread's landmarks, requested together with the partial statistics
+  int4 w[4][2];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    w[g][0] = make_int4(0, 0, 0, 0); w[g][1] = make_int4(0, 0, 0, 0);
+    if (usable && g < G && n0 < N) {
+      w[g][0] = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n0);
+      if (n0 + 8 < ldn) w[g][1] = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n0 + 8);
+    }
+  }
+  for (int g = warp; g < G; g += kWarps) {
+    float m, inv;
+    reduce_partials_fast(part_max + (size_t(bh) * G + g) * T, part_sum + (size_t(bh) * G + g) * T, T, lane, m, inv);
+    if (lane == 0) { s_m[g] = m; s_inv[g] = inv; s_linv[g] = logf(inv); }
+  }
+  __syncthreads();
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 2);
+  if (!usable) {                                // CTA uniform
+    if (tid == 0) status[bh] = -1;              // <= 0: not done (the code says why; tools/exp_select_fast.py)
+    return;
+  }
+  // 1. candidates: max_g log p_g against the lower edge of the window
+  const float cut = logf(bf16_bits_to_f32(uint16_t(win0 - 1))) - 1e-3f;
+  float umax[kFsPer];
+#pragma unroll
+  for (int e = 0; e < kFsPer; ++e) umax[e] = -INFINITY;
+  auto fold = [&](const int4 &a, const int4 &b, const int g) {
+    const uint32_t u[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w,
+                           (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+    const float m = s_m[g], li = s_linv[g];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      umax[2 * e] = fmaxf(umax[2 * e], (bf16_lo(u[e]) - m) + li);
+      umax[2 * e + 1] = fmaxf(umax[2 * e + 1], (bf16_hi(u[e]) - m) + li);
+    }
+  };
+  if (n0 < N) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < G) fold(w[g][0], w[g][1], g);
+    for (int g = 4; g < G; ++g) {
+      const int4 a = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n0);
+      const int4 b = n0 + 8 < ldn ? *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n0 + 8) : make_int4(0, 0, 0, 0);
+      fold(a, b, g);
+    }
+  }
+  unsigned mask = 0;
+#pragma unroll
+  for (int e = 0; e < kFsPer; ++e) mask |= (n0 + e < N && umax[e] >= cut) ? (1u << e) : 0u;
+  int total;
+  int off = block_excl_scan(__popc(mask), s_warp, total);
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 3);
+#ifdef SKV_TRACE
+  if (tid == 0 && bh == 0) g_skv_trace[16 * 32 + 12] = total;
+#endif
+  if (total > kFsCap || total < S) {            // CTA uniform.  Fewer than S candidates: the threshold is below the window
+    if (tid == 0) status[bh] = total > kFsCap ? -2 : -3;
+    return;
+  }
+  if (mask) {                                   // ascending landmark order
+#pragma unroll
+    for (int e = 0; e < kFsPer; ++e) {
+      if (mask & (1u << e)) {
+        s_cidx[off] = uint16_t(n0 + e);
+        uint32_t b[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int4 &q4 = w[g][e >> 3];
+          const int c = (e & 7) >> 1;
+          const uint32_t word = uint32_t(c == 0 ? q4.x : c == 1 ? q4.y : c == 2 ? q4.z : q4.w);
+          b[g] = (e & 1) ? (word >> 16) : (word & 0xFFFFu);
+        }
+        s_cs[off] = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+        ++off;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 4);
+  // 2. exact keys of the candidates (the expression of select_kernel), window histogram in shared memory
+  const int64_t *lidx = landmark_idx + size_t(bh) * N;
+  for (int i = tid; i < total; i += kFsThreads) {
+    const int n = s_cidx[i];
+    const int64_t id = lidx[n];                 // requested here, needed at the emission
+    uint16_t key = 0;
+    if (G <= 4) {
+      const uint2 cs = s_cs[i];
+      const uint16_t sb[4] = {uint16_t(cs.x & 0xFFFFu), uint16_t(cs.x >> 16), uint16_t(cs.y & 0xFFFFu), uint16_t(cs.y >> 16)};
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g < G) {
+          const uint16_t k = f32_to_bf16_bits(expf(bf16_bits_to_f32(sb[g]) - s_m[g]) * s_inv[g]);
+          key = k > key ? k : key;
+        }
+      }
+    } else {
+      for (int g = 0; g < G; ++g) {
+        const uint16_t k = f32_to_bf16_bits(expf(bf16_bits_to_f32(sc[size_t(g) * ldn + n]) - s_m[g]) * s_inv[g]);
+        key = k > key ? k : key;
+      }
+    }
+    s_ckey[i] = key;
+    s_cval[i] = static_cast<int>(id);
+    atomicAdd(&s_hist[key < win0 ? 0 : min(255, int(key) - win0 + 1)], 1);
+  }
+  __syncthreads();
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 5);
+  if (warp == 0) {                              // threshold bin: the largest b with count(bins >= b) >= S
+    int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; tot += c[j]; }
+    int suf = tot;                              // sum over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, suf, o);
+      if (lane + o < 32) suf += v;
+    }
+    const int above_lane = suf - tot;
+    if (above_lane < S && suf >= S) {
+      int acc = above_lane;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (acc < S && acc + c[j] >= S) { s_res[0] = lane * 8 + j; s_res[1] = acc; }
+        acc += c[j];
+      }
+    }
+  }
+  __syncthreads();
+  const int b0 = s_res[0], above = s_res[1];
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 6);
+  if (b0 < 1 || b0 > 254) {                     // CTA uniform: the threshold left the window
+    if (tid == 0) status[bh] = b0 < 1 ? -4 : -5;
+    return;
+  }
+  const unsigned thr = unsigned(win0 + b0 - 1);
+  const int need_eq = S - above;
+  // 3. ordered emission: thread t owns the candidates [t * seg, (t + 1) * seg)
+  {
+    const int seg = (total + kFsThreads - 1) / kFsThreads;
+    const int i0 = min(total, tid * seg), i1 = min(total, i0 + seg);
+    int gt = 0, eq = 0;
+    for (int i = i0; i < i1; ++i) { const unsigned k = s_ckey[i]; gt += k > thr; eq += k == thr; }
+    int pg, pe, tg, te;
+    block_excl_scan2<kWarps>(gt, eq, s_wa, s_wb, pg, pe, tg, te);
+    for (int i = i0; i < i1; ++i) {
+      const unsigned k = s_ckey[i];
+      if (k > thr || (k == thr && pe < need_eq)) s_new[pg + min(pe, need_eq)] = s_cval[i];
+      pg += k > thr; pe += k == thr;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 7);
+  int new_id = 0;
+  if (tid < S) {
+    new_id = s_new[tid];
+    if (selected_out) selected_out[size_t(bh) * S + tid] = static_cast<int64_t>(new_id);
+  }
+  ChunkTableSmem sm{s_sorted, s_slot, s_warp};
+  chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
+                                  cnts + bh);
+  if (tid == 0) { hint[bh] = int(thr); status[bh] = 1; }
+  if (tid == 0) SKV_STAMP_NS(bh == 0 ? 16 : -1, 8);
+  if (row_flags) {                              // the row's chunk table is written: release it
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(1) : "memory");
+    }
+  }
+}
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct SelectWorkspace {
   skv_bf16 *scores;      // [BH, G, ldn], ldn = N rounded up to 8 so every row is 16-byte aligned
   float *pmax, *psum;
+  int32_t *fast_status;  // [BH] select_fast_kernel -> select_kernel: 1 = row done
   int T, ldn;
 };
 
@@ -650,6 +887,8 @@ static SelectWorkspace carve(const skv_geom *g, void *ws) {
   w.pmax = reinterpret_cast<float *>(p);
   p += align_up(BH * g->q_groups * w.T * 4, 256);
   w.psum = reinterpret_cast<float *>(p);
+  p += align_up(BH * g->q_groups * w.T * 4, 256);
+  w.fast_status = reinterpret_cast<int32_t *>(p);
   return w;
 }
 
@@ -682,7 +921,7 @@ int64_t skv_select_workspace_bytes(const skv_geom *g) {
   const int64_t BH = int64_t(g->batch) * g->kv_heads;
   const int64_t T = (g->n_landmarks + 127) / 128;
   const int64_t ldn = (g->n_landmarks + 7) / 8 * 8;
-  return align_up(BH * g->q_groups * ldn * 2, 256) + 2 * align_up(BH * g->q_groups * T * 4, 256);
+  return align_up(BH * g->q_groups * ldn * 2, 256) + 2 * align_up(BH * g->q_groups * T * 4, 256) + align_up(BH * 4, 256);
 }
 
 static int check_select_geom(const skv_geom *g, const char *who) {
@@ -739,7 +978,7 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT, CAP>), smem, "select_kernel")) return rc; \
     cudaError_t e = launch_kernel(select_kernel<SV, IP, KT, CAP>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,  \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
-                                  score_out, g->row_flags, sel_hint, G, N, w.ldn, w.T, per);                      \
+                                  score_out, g->row_flags, sel_hint, fast_status, G, N, w.ldn, w.T, per);         \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
@@ -772,6 +1011,33 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const bool wide = per >= ((wf && *wf) ? atoi(wf) : 3072);  // landmarks per CTA from which 512 threads pay
   const char *wf2 = getenv("SKV_SELECT_WIDE2_FROM");
   const bool wide2 = per >= ((wf2 && *wf2) ? atoi(wf2) : 6144);  // ... and 1024 threads
+  // Single-CTA hinted selection in front of the cluster kernel (select_fast_kernel): rows whose threshold stays inside the
+  // hint window are settled there, the cluster kernel only does the others.  A measured experiment, OFF by default
+  // (SKV_SELECT_FAST=1 enables it): bit-identical results, but one SM is too slow for a row -- 14.4 us behind its wait at
+  // 122K (%globaltimer stamps: 124 KB of scores into one SM 4.7, filter + scan 2.6, compaction 2.2, exact keys of 1 600
+  // candidates 1.7, emission 1.4, table 1.5; 1024-thread barriers cost 0.2-0.3 us each) against 7.5 us for the 8-CTA
+  // cluster kernel, and its 1024 x 64 registers keep every other CTA off its SM: 67.7 against 61.1 us per layer-step
+  const char *fse = getenv("SKV_SELECT_FAST");
+  const int32_t *fast_status = nullptr;
+  if ((fse && fse[0] == '1') && sel_hint && !score_out && N <= kFsThreads * kFsPer && N >= g->select) {
+#define SKV_FAST(SV)                                                                                              \
+  case SV: {                                                                                                      \
+    cudaError_t e = g->table_mode                                                                                 \
+        ? launch_kernel(select_fast_kernel<SV, true>, dim3(BH), dim3(kFsThreads), 0, st, true, w.scores, w.pmax,    \
+                        w.psum, landmark_idx, resident, offsets, cnts, selected_out, g->row_flags, sel_hint,        \
+                        w.fast_status, G, N, w.ldn, w.T)                                                            \
+        : launch_kernel(select_fast_kernel<SV, false>, dim3(BH), dim3(kFsThreads), 0, st, true, w.scores, w.pmax,   \
+                        w.psum, landmark_idx, resident, offsets, cnts, selected_out, g->row_flags, sel_hint,        \
+                        w.fast_status, G, N, w.ldn, w.T);                                                           \
+    if (e != cudaSuccess) { set_error("select_fast_kernel: %s", cudaGetErrorString(e)); return int(e); }          \
+  } break;
+    switch (g->select) {
+      SKV_FAST(128) SKV_FAST(256) SKV_FAST(512) SKV_FAST(1024)
+      default: return SKV_ERR_UNSUPPORTED;
+    }
+#undef SKV_FAST
+    fast_status = w.fast_status;
+  }
   switch (g->select) {
     SKV_SEL(128) SKV_SEL(256) SKV_SEL(512) SKV_SEL(1024)
     default: return SKV_ERR_UNSUPPORTED;

@@ -82,6 +82,8 @@ class DecodeStepGraph:
         per_layer = (4 if fused else 5) + (0 if cache.table_mode == "inplace" else (1 if fused else 2))
         if fused and cache.can_fuse_attend():
             per_layer = 3                      # score (+append), select, fetch + rebuild + attention
+        if cache.select_fast_active():
+            per_layer += 1                     # select_fast_kernel in front of the cluster selection
         self.launches_per_step = L * (per_layer + (1 if cache.hbm_store_ways else 0))
         self._per_layer = per_layer
         self.inline_wait = os.environ.get("SKV_HEAD_WAIT", "inline") != "launch"

@@ -589,6 +589,13 @@ class ShadowKVCache_CPU:
                                         self.cnts.data_ptr(), self.offsets.data_ptr(),
                                         C.byref(vs) if vs is not None else None, st), "fetch_and_rebuild")
 
+    def select_fast_active(self) -> bool:
+        """Whether the selection launches select_fast_kernel in front of the cluster kernel (csrc/score.cu; an experiment
+        that measured slower, enabled only by SKV_SELECT_FAST=1: threshold hints on, at most 16384 landmarks)."""
+        n = self.k_landmark.shape[-2] if self.k_landmark is not None else 0
+        return (0 < n <= 16384 and os.environ.get("SKV_SELECT_FAST", "0") == "1"
+                and os.environ.get("SKV_SELECT_HINT", "1") != "0")
+
     def can_fuse_attend(self) -> bool:
         """skv_fetch_rebuild_attend handles the in-place chunk table, G <= 8 and the tcgen05 rebuild."""
         return (self.fused_attend and self.table_mode == "inplace" and self.num_key_value_groups <= 8

@@ -301,3 +301,115 @@ def test_select_wide_cta_equals_base(cuda, monkeypatch, model, B, N, S):
     assert torch.equal(s1, s2) and torch.equal(c1, c2) and torch.equal(r1, r2), "selection / chunk table differs"
     live = torch.arange(S).view(1, -1) < (S - c1.long()).view(-1, 1)
     assert torch.equal(o1.view(B * H, S)[live], o2.view(B * H, S)[live])
+
+
+def _fast_status(ws, B, H, G, N):
+    """The per-row words select_fast_kernel leaves behind the partial sums of the select workspace (1 = row done there,
+    <= 0 = left to the cluster kernel: -1 no usable hint, -2 candidate list overflow, -3 / -4 threshold below the window,
+    -5 above it)."""
+    al = lambda x: (x + 255) // 256 * 256   # noqa: E731
+    ldn, T = (N + 7) // 8 * 8, (N + 127) // 128
+    off = al(B * H * G * ldn * 2) + 2 * al(B * H * G * T * 4)
+    return ws[off:off + B * H * 4].view(torch.int32).cpu()
+
+
+@pytest.mark.parametrize("model,N,S", [("llama-3.1-8b", 15560, 256), ("glm-4-9b-1m", 16328, 256), ("llama-3.1-8b", 4044, 512),
+                                       ("llama-3.1-8b", 1024, 128)])
+def test_select_fast_path_equals_cluster_kernel(cuda, monkeypatch, model, N, S):
+    """select_fast_kernel (one CTA per row: log-domain candidate filter below the hint window, exact keys only for the
+    candidates, shared-memory histogram) must leave exactly what the cluster kernel leaves -- chunk table, offsets, hit
+    counts, selected ids, hint word -- whenever it settles a row, and must leave the row alone otherwise."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    monkeypatch.setenv("SKV_SELECT_FAST", "1")       # an experiment, off by default (measured slower than the cluster kernel)
+    shape = synth.MODELS[model]
+    B = 2
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(N * 5 + S)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16).to(cuda)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N).to(cuda)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S].to(cuda)] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+
+    def run(hint, with_scores=False):
+        res = resident.clone()
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+        geom.select_hint = hint.data_ptr() if hint is not None else None
+        _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.data_ptr(), lm.data_ptr(), idx.data_ptr(), res.data_ptr(),
+                                              off.data_ptr(), cnt.data_ptr(), sel.data_ptr(),
+                                              score.data_ptr() if with_scores else None, ws.data_ptr(),
+                                              None, torch.cuda.current_stream().cuda_stream), "select")
+        torch.cuda.synchronize()
+        return res.cpu(), off.cpu(), cnt.cpu(), sel.cpu(), score.cpu()
+
+    base = run(None, with_scores=True)               # the cluster kernel alone (no hint, score output requested)
+    keys = base[4].view(torch.int16).int().view(B * H, N)
+    thr = torch.sort(keys, dim=1, descending=True).values[:, S - 1].to(torch.int32)
+    R = B * H
+    cases = {"zero (first token)": (torch.zeros_like(thr), -1), "exact": (thr.clone(), 1),
+             "a few steps off": (thr + torch.arange(R, dtype=torch.int32) * 7 - 20, 1),
+             "window edges": (thr + torch.tensor([126, -127] * (R // 2), dtype=torch.int32), 1),
+             "just outside": (thr + torch.tensor([127, -128] * (R // 2), dtype=torch.int32), None),
+             "far above": (thr + 3000, None), "far below": ((thr - 3000).clamp(min=1), None)}
+    took = {}
+    for name, (h, want_status) in cases.items():
+        hint = h.to(cuda)
+        got = run(hint)
+        status = _fast_status(ws, B, H, G, N)
+        took[name] = status.tolist()
+        for a, b, what in zip(got[:4], base[:4], ("resident", "offsets", "cnts", "selected")):
+            assert torch.equal(a, b), f"hint '{name}' (fast status {status.tolist()}): {what} differs from the cluster kernel's"
+        assert torch.equal(hint.cpu(), thr), f"hint '{name}': the word must come back as this selection's threshold key"
+        if want_status == 1:
+            assert bool(((status == 1) | (status == -2)).all()), f"hint '{name}': rows not settled by the fast path: {status.tolist()}"
+        elif want_status is not None:
+            assert bool((status == want_status).all()), f"hint '{name}': fast status {status.tolist()}"
+        else:
+            assert bool((status <= 0).all()), f"hint '{name}': the fast path must leave these rows alone: {status.tolist()}"
+        # A/B switch: the cluster kernel with the same hint
+        monkeypatch.setenv("SKV_SELECT_FAST", "0")
+        ref = run(h.to(cuda))
+        monkeypatch.setenv("SKV_SELECT_FAST", "1")
+        for a, b, what in zip(got[:4], ref[:4], ("resident", "offsets", "cnts", "selected")):
+            assert torch.equal(a, b), f"hint '{name}': {what} differs between SKV_SELECT_FAST=1 and 0"
+    print(f"\n[{model} N={N} S={S}] fast-path status per case: {took}")
+    assert any(v == 1 for v in took["exact"]), "the fast path never fired with an exact hint"
+
+
+def test_select_fast_path_ties_take_the_lowest_indices(cuda, monkeypatch):
+    """All landmarks identical -> every key ties at the threshold; with an exact hint the single-CTA path takes the S
+    lowest landmark indices, like the cluster kernel."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    monkeypatch.setenv("SKV_SELECT_FAST", "1")
+    B, H, G, N, S = 1, 2, 4, 1500, 256
+    q = torch.randn(B, H * G, 1, 128).to(torch.bfloat16)
+    lm = torch.ones(B, H, N, 128, dtype=torch.bfloat16) * 0.01
+    idx = torch.arange(N).expand(B, H, N).contiguous() * 3
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=4000, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+    hint = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+    geom.select_hint = hint.data_ptr()
+    d_q, d_lm, d_idx = q.to(cuda), lm.to(cuda), idx.to(cuda)
+    sels = []
+    for rep in range(2):                             # first call: no hint (cluster kernel); second: its threshold as the hint
+        res = torch.full((B, H, S), -1, dtype=torch.int64, device=cuda)
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), d_q.data_ptr(), d_lm.data_ptr(), d_idx.data_ptr(),
+                                              res.data_ptr(), off.data_ptr(), cnt.data_ptr(), sel.data_ptr(), None,
+                                              ws.data_ptr(), None, torch.cuda.current_stream().cuda_stream), "select")
+        torch.cuda.synchronize()
+        sels.append(sel.cpu())
+        status = _fast_status(ws, B, H, G, N)
+        assert bool((status == (1 if rep else -1)).all()), status
+    want = (torch.arange(S) * 3).expand(B, H, S)
+    assert torch.equal(sels[0], want) and torch.equal(sels[1], want)

@@ -54,6 +54,10 @@ def main():
     merged = [fa[t][14] for t in range(256) if fa[t][14] > t0]
     print(f"fused launch: row 0 merged {us(max(merged)) if merged else '-'} (a step takes one period; the previous layer's merge = this minus the period)")
     print(f"select row 0   : past its wait {us(se[0][21])} table written {us(se[0][22])}")
+    f = se[16]
+    if f[0]:
+        names_f = ["start", "past wait", "stats", "filter+scan", "compact", "keys+hist", "threshold", "emit", "table"]
+        print("select_fast row 0: " + " ".join(f"{n} {us(f[i])}" for i, n in enumerate(names_f)) + f"  candidates {f[12]}")
     names = ["start", "idx", "ldV", "mma", "stats", "V1st", "issued", "landed", "Vall", "sync", "part", "waited", "dots", "end", "MERGED"]
     print("tile CTAs of row 0:  " + " ".join(f"{n:>7}" for n in names))
     for t in range(64):
