@@ -337,7 +337,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
                   int32_t *hint,                              // [BH] or null: the row's previous threshold key (in/out)
                   const int32_t *fast_status,                 // [BH] or null: 1 = select_fast_kernel (launched in front of
                                                               // this grid) has done the row; it also cleared row_flags
-                  int G, int N, int ldn, int T, int per) {
+                  int G, int N, int ldn, int T, int per, int filter_on) {
   constexpr int kThreads = kT;
   static_assert(kT >= S && kT >= 256 && kT % 32 == 0, "one thread per table entry and per histogram bin");
   constexpr int kWarps = kThreads / 32;
@@ -345,7 +345,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   int *whist1 = reinterpret_cast<int *>(sel_smem);                                 // [kWarps][256] level 1
   int *whist2 = whist1 + kWarps * 256;                                             // [kWarps][256] level 2
   uint16_t *keys = reinterpret_cast<uint16_t *>(sel_smem + 2 * kWarps * 256 * 4);  // [per rounded to 8]
-  __shared__ float s_m[16], s_inv[16];
+  __shared__ float s_m[16], s_inv[16], s_linv[16];
   // level-1 / level-2 histograms of all 8 CTAs (each CTA stores its own into every CTA), two 16-bit counts per word:
   // a CTA's slice has fewer than 65536 landmarks (check_select_geom), and the exchange is 4 KiB per CTA instead of 8
   __shared__ uint32_t s_parts1[kSelCluster][128];
@@ -362,6 +362,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   const int n_begin = min(N, rank * per), n_end = min(N, n_begin + per);
   const int count = n_end - n_begin;            // only the last slice can be ragged (N % 8 != 0)
   SKV_STAMP(bh == 0 ? rank : 999, 0);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 0);
 
   // early, independent global loads: the (static) landmark ids of this thread's first 8 landmarks.  Under a
   // programmatic launch this and the histogram clearing overlap the tail of the scoring kernel.
@@ -413,15 +414,17 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   for (int g = warp; g < G; g += kWarps) {
     float m, inv;
     reduce_partials_fast(part_max + (size_t(bh) * G + g) * T, part_sum + (size_t(bh) * G + g) * T, T, lane, m, inv);
-    if (lane == 0) { s_m[g] = m; s_inv[g] = inv; }
+    if (lane == 0) { s_m[g] = m; s_inv[g] = inv; s_linv[g] = logf(inv); }
   }
   __syncthreads();
   SKV_STAMP(bh == 0 ? rank : 999, 1);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 1);
 
   // 1. p = bf16(exp(s - max) * inv); key = max over heads (bf16 bits are monotone for p >= 0);
   //    first-level histogram on the high byte.  8 consecutive landmarks per thread: 16-byte loads.
   int *my_h1 = whist1 + warp * 256, *my_h2 = whist2 + warp * 256;
-  for (int base = 0; base < count; base += kThreads * 8) {
+  // all keys of round `base` exactly (G exponentials per landmark) into `keys`; with_hist: also the first histogram
+  auto full_keys_round = [&](const int base, const bool first_regs, const bool with_hist) {
     const int off = base + tid * 8;
     const bool on = off < count;
     uint16_t best[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -442,7 +445,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
       };
 #pragma unroll
       for (int g = 0; g < 4; ++g)                          // the first round's loads are already in registers
-        if (g < G) fold(base == 0 ? w0[g] : *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n), g);
+        if (g < G) fold(first_regs ? w0[g] : *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n), g);
 #pragma unroll 4
       for (int g = 4; g < G; ++g) fold(*reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n), g);
 #pragma unroll
@@ -461,14 +464,94 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
         }
       }
     }
+    if (with_hist) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = best[e];
-      const unsigned bin = win0 ? (k < win0 ? 0u : unsigned(min(255, k - win0 + 1))) : unsigned(k >> 8);
-      hist_add_private(my_h1, (on && off + e < count) ? bin : 0xFFFFu);
+      for (int e = 0; e < 8; ++e) {
+        const int k = best[e];
+        const unsigned bin = win0 ? (k < win0 ? 0u : unsigned(min(255, k - win0 + 1))) : unsigned(k >> 8);
+        hist_add_private(my_h1, (on && off + e < count) ? bin : 0xFFFFu);
+      }
+    }
+  };
+  // With a usable hint the exponentials are only taken for CANDIDATES: log p_g = (s_g - m_g) + log(1 / Z_g) costs one
+  // add per score, and a landmark whose max_g log p_g lies below log(value of key win0 - 1) - 1e-3 provably has a key
+  // below the window (the margin covers the fp32 rounding of log p_g, of logf and of the product expf(.) * inv by two
+  // orders of magnitude; a product below the bf16 number win0 - 1 cannot round up to win0; the window stays clear of
+  // products that could be denormal).  Such a landmark can neither be selected nor move a threshold that lies inside the
+  // window: it is counted in bin 0 with key 0.  The few hundred candidates of the row (everything within about a factor
+  // of two of the previous threshold) are compacted per warp and get their exact key.  If the threshold turns out to lie
+  // outside the window, all keys are formed after all (below) and the two-level search runs as without a hint.
+  const bool filt = filter_on && win0 >= 0x1000 && score_out == nullptr;
+  if (!filt) {
+    for (int base = 0; base < count; base += kThreads * 8) full_keys_round(base, base == 0, true);
+  } else {
+    const float cut = logf(bf16_bits_to_f32(uint16_t(win0 - 1))) - 1e-3f;
+    uint8_t *wl = reinterpret_cast<uint8_t *>(my_h2);       // this warp's candidate list (whist2 is re-cleared before use)
+    uint16_t *sraw = keys + per;                            // [G][per] raw scores of the slice (per is a multiple of 8)
+    for (int base = 0; base < count; base += kThreads * 8) {
+      const int off = base + tid * 8;
+      const bool on = off < count;
+      float umax[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) umax[e] = -INFINITY;
+      if (on) {
+        const int n = n_begin + off;
+        auto fold_u = [&](const int4 &w, const int g) {
+          const uint32_t u[4] = {(uint32_t)w.x, (uint32_t)w.y, (uint32_t)w.z, (uint32_t)w.w};
+          const float m = s_m[g], li = s_linv[g];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            umax[2 * e] = fmaxf(umax[2 * e], (bf16_lo(u[e]) - m) + li);
+            umax[2 * e + 1] = fmaxf(umax[2 * e + 1], (bf16_hi(u[e]) - m) + li);
+          }
+        };
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < G) {
+            const int4 w = base == 0 ? w0[g] : *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n);
+            fold_u(w, g);
+            *reinterpret_cast<int4 *>(sraw + g * per + off) = w;     // raw scores for the candidates' exact keys
+          }
+#pragma unroll 4
+        for (int g = 4; g < G; ++g) {
+          const int4 w = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n);
+          fold_u(w, g);
+          *reinterpret_cast<int4 *>(sraw + g * per + off) = w;
+        }
+        *reinterpret_cast<int4 *>(keys + off) = make_int4(0, 0, 0, 0);
+      }
+      __syncwarp();                                           // the zeroed keys precede the candidates' keys below
+      int n_c = 0;                                            // warp uniform: candidates of this warp's 256 landmarks
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool c = on && off + e < count && umax[e] >= cut;
+        const unsigned b = __ballot_sync(0xffffffffu, c);
+        if (c) wl[n_c + __popc(b & ((1u << lane) - 1u))] = uint8_t(lane * 8 + e);
+        n_c += __popc(b);
+      }
+      __syncwarp();
+      const int wbase = base + warp * 256;                    // first landmark (slice-local) of this warp in this round
+      for (int i0 = 0; i0 < n_c; i0 += 32) {
+        const bool have = i0 + lane < n_c;
+        unsigned bin = 0xFFFFu;
+        if (have) {
+          const int o = wbase + wl[i0 + lane];
+          uint16_t key = 0;
+          for (int g = 0; g < G; ++g) {
+            const uint16_t k = f32_to_bf16_bits(expf(bf16_bits_to_f32(sraw[g * per + o]) - s_m[g]) * s_inv[g]);
+            key = k > key ? k : key;
+          }
+          keys[o] = key;
+          bin = key < win0 ? 0u : unsigned(min(255, int(key) - win0 + 1));
+        }
+        hist_add_private(my_h1, bin);
+      }
+      if (lane == 0) my_h1[0] += max(0, min(256, count - wbase)) - n_c;   // everything below the window
+      __syncwarp();
     }
   }
   SKV_STAMP(bh == 0 ? rank : 999, 2);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 2);
   // sum of the warp-private histograms `wh`, two 16-bit counts per word, into row `rank` of `parts` of every CTA
   auto push_hist = [&](const int *wh, uint32_t (*parts)[128]) {
     __syncthreads();
@@ -511,6 +594,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   if (win0) {                                   // cluster uniform (the hint word is the same for all eight CTAs)
     push_hist(whist1, s_parts0);
     SKV_STAMP(bh == 0 ? rank : 999, 3);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 3);
     find_threshold_parts(s_parts0, S, s_res, s_wa);
     const int b0 = s_res[0], above0 = s_res[1];
     if (b0 >= 1 && b0 <= 254) {                 // the threshold is a key of the window: done after ONE exchange
@@ -520,7 +604,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
       settled = true;
     } else {                                    // outside: the level-1 histogram of the two-level search, from the keys
       __syncthreads();
-      for (int i = tid; i < kWarps * 256; i += kThreads) whist1[i] = 0;
+      if (filt) {                               // only the candidates have their key so far: form all of them now
+        for (int base = 0; base < count; base += kThreads * 8) full_keys_round(base, false, false);
+      }
+      for (int i = tid; i < kWarps * 256; i += kThreads) { whist1[i] = 0; whist2[i] = 0; }   // whist2 held the lists
       __syncthreads();
       for (int base = 0; base < count; base += kThreads * 8) {
         const int off = base + tid * 8;
@@ -541,9 +628,11 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   if (!settled) {
   push_hist(whist1, s_parts1);
   SKV_STAMP(bh == 0 ? rank : 999, 3);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 3);
   find_threshold_parts(s_parts1, S, s_res, s_wa);
   const int b1 = s_res[0], above1 = s_res[1];
   SKV_STAMP(bh == 0 ? rank : 999, 4);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 4);
 
   // 2. second level: low byte of the keys inside the threshold bin
   for (int base = 0; base < count; base += kThreads * 8) {
@@ -561,18 +650,22 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
     }
   }
   SKV_STAMP(bh == 0 ? rank : 999, 5);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 5);
   push_hist(whist2, s_parts2);
   SKV_STAMP(bh == 0 ? rank : 999, 6);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 6);
   find_threshold_parts(s_parts2, S - above1, s_res + 2, s_wa);
   thr = (unsigned(b1) << 8) | unsigned(s_res[2]);
   need_eq = S - (above1 + s_res[3]);                // how many keys equal to thr are taken (>= 1)
   SKV_STAMP(bh == 0 ? rank : 999, 7);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 7);
 
   // 3. (greater, equal) counts of the lower-ranked CTAs: every CTA already holds all eight partial
   //    histograms, so no further exchange is needed
   counts_before(s_parts1, b1, s_parts2, s_res[2]);
   }
   SKV_STAMP(bh == 0 ? rank : 999, 10);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 10);
 
   // 4. ordered emission (ascending landmark index): thread t owns 8 consecutive landmarks per round, so the
   //    position of a taken key = (#greater before it) + min(#equal before it, need_eq), by a block scan.
@@ -610,8 +703,10 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
     }
   }
   SKV_STAMP(bh == 0 ? rank : 999, 11);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 11);
   cluster.sync();
   SKV_STAMP(bh == 0 ? rank : 999, 12);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 12);
   if (rank != 0) return;
 
   // 5. chunk-table update (CTA 0)
@@ -621,10 +716,12 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
     if (selected_out) selected_out[size_t(bh) * S + tid] = static_cast<int64_t>(new_id);
   }
   SKV_STAMP(bh == 0 ? rank : 999, 13);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 13);
   ChunkTableSmem sm{s_sorted, s_slot, s_warp};
   chunk_table_update<S, kInPlace>(tid, old_id, new_id, sm, resident + size_t(bh) * S, offsets + size_t(bh) * S,
                                   cnts + bh);
   SKV_STAMP(bh == 0 ? rank : 999, 14);
+  if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 14);
   if (hint && tid == 0) hint[bh] = int(thr);      // read by this row's selection of the next token, behind its wait
   if (row_flags) {                              // the row's chunk table (resident, offsets, cnt) is written: release it
     __syncthreads();
@@ -973,12 +1070,12 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const int per = ((N + 8 * kSelCluster - 1) / (8 * kSelCluster)) * 8;       // landmarks per CTA, multiple of 8
 #define SKV_SEL_LAUNCH2(SV, IP, KT, CAP)                                                                          \
   {                                                                                                              \
-    const int smem0 = 2 * (KT / 32) * 1024 + int(align_up(int64_t(per) * 2, 16));                                  \
+    const int smem0 = 2 * (KT / 32) * 1024 + (1 + (filter_on ? G : 0)) * int(align_up(int64_t(per) * 2, 16));      \
     const int smem = smem0 + (pad >= 0 ? pad : (spread ? std::max(0, (kSelSpreadBytes - smem0) / 1024 * 1024) : 0)); \
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(select_kernel<SV, IP, KT, CAP>), smem, "select_kernel")) return rc; \
     cudaError_t e = launch_kernel(select_kernel<SV, IP, KT, CAP>, dim3(kSelCluster, BH), dim3(KT), smem, st, true,  \
                                   w.scores, w.pmax, w.psum, landmark_idx, resident, offsets, cnts, selected_out,   \
-                                  score_out, g->row_flags, sel_hint, fast_status, G, N, w.ldn, w.T, per);         \
+                                  score_out, g->row_flags, sel_hint, fast_status, G, N, w.ldn, w.T, per, filter_on); \
     if (e != cudaSuccess) { set_error("select_kernel: %s", cudaGetErrorString(e)); return int(e); }               \
   }
 #define SKV_SEL_LAUNCH(SV, IP, KT)                                                                                \
@@ -998,6 +1095,8 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   // SKV_SELECT_PAD_KB (extra dynamic shared memory = fewer CTAs of this kernel per SM) are A/B switches
   const char *he = getenv("SKV_SELECT_HINT");               // A/B switch: 0 ignores skv_geom.select_hint
   int32_t *sel_hint = (he && he[0] == '0') ? nullptr : g->select_hint;
+  const char *fle = getenv("SKV_SELECT_FILTER");            // A/B switch: 0 = exact keys for every landmark even with a hint
+  const int filter_on = (fle && fle[0] == '0') ? 0 : 1;
   const char *ce = getenv("SKV_SELECT_CAP"), *pe = getenv("SKV_SELECT_PAD_KB");
   const bool cap = (ce && *ce) ? ce[0] == '1' : BH * kSelCluster > kNumSMs;
   // One CTA of this kernel per SM while the grid covers at most half of the SMs (batch 1): the dynamic shared memory is

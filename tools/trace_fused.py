@@ -54,6 +54,11 @@ def main():
     merged = [fa[t][14] for t in range(256) if fa[t][14] > t0]
     print(f"fused launch: row 0 merged {us(max(merged)) if merged else '-'} (a step takes one period; the previous layer's merge = this minus the period)")
     print(f"select row 0   : past its wait {us(se[0][21])} table written {us(se[0][22])}")
+    k2 = se[17]
+    if k2[1]:
+        names_k = {1: "stats", 2: "keys+hist", 3: "exchange1", 4: "thr1", 5: "h2", 6: "exchange2", 7: "thr2", 10: "counts", 11: "emit",
+                   12: "csync", 13: "ids", 14: "table"}
+        print("select cluster kernel, row 0 CTA 0 (wall clock): " + " ".join(f"{n} {us(k2[i])}" for i, n in names_k.items() if k2[i] > t0))
     f = se[16]
     if f[0]:
         names_f = ["start", "past wait", "stats", "filter+scan", "compact", "keys+hist", "threshold", "emit", "table"]
