@@ -376,21 +376,9 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
   // Rows the single-CTA fast selection has settled (its launch sits between the scoring launch and this one) are done,
   // flag raised and all: the whole cluster leaves (uniform: one word per row), before any cluster barrier.
   if (fast_status && __ldcg(fast_status + bh) == 1) return;
-  if (row_flags && !fast_status) {
-    // Row hand-over (skv_geom.row_flags): the dependents of this launch wait for their ROW's word, not for this grid.
-    // The word still carries the previous token's 1; every consumer of that value has finished (this kernel's wait
-    // covers, transitively, the previous launch that read it), and no consumer of the new value exists before the
-    // trigger below: clear it, make the store visible, and only then let the dependent grid be scheduled.
-    if (rank == 0) {
-      if (tid == 0) {
-        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(0) : "memory");
-        __threadfence();
-      }
-      __syncthreads();
-    }
-    pdl_launch_dependents();
-  }
   if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 0 : -1, 21);
+  // (the loads below are requested BEFORE the row word is cleared: the fence behind the clear then overlaps their L2 round
+  // trip instead of preceding it in CTA 0, the CTA that ends the chain)
   int old_id = 0;
   if (rank == 0 && tid < S) old_id = static_cast<int>(resident[size_t(bh) * S + tid]);                       // map.cuh:771
   // the scores of this thread's first 8 landmarks for the first four heads, requested together with the partial
@@ -410,6 +398,20 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
       if (g < G) w0[g] = *reinterpret_cast<const int4 *>(sc + size_t(g) * ldn + n_begin + tid * 8);
   }
 
+  if (row_flags && !fast_status) {
+    // Row hand-over (skv_geom.row_flags): the dependents of this launch wait for their ROW's word, not for this grid.
+    // The word still carries the previous token's 1; every consumer of that value has finished (this kernel's wait
+    // covers, transitively, the previous launch that read it), and no consumer of the new value exists before the
+    // trigger below: clear it, make the store visible, and only then let the dependent grid be scheduled.
+    // The clear and its fence are done by the first lane of the LAST warp, which has no head to reduce below when
+    // G < 8: the fence overlaps the L2 round trip of the statistics instead of standing in front of it; the trigger
+    // follows the barrier that ends the statistics (the clearing thread is past its fence by then).
+    if (rank == 0 && tid == kThreads - 32) {
+      asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(row_flags + bh), "r"(0) : "memory");
+      __threadfence();
+    }
+  }
+
   // 0. final softmax statistics per head (every CTA redundantly: G x T floats)
   for (int g = warp; g < G; g += kWarps) {
     float m, inv;
@@ -417,6 +419,7 @@ __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kT, kCap ?
     if (lane == 0) { s_m[g] = m; s_inv[g] = inv; s_linv[g] = logf(inv); }
   }
   __syncthreads();
+  if (row_flags && !fast_status) pdl_launch_dependents();
   SKV_STAMP(bh == 0 ? rank : 999, 1);
   if (tid == 0 && rank == 0) SKV_STAMP_NS(bh == 0 ? 17 : -1, 1);
 
