@@ -413,3 +413,58 @@ def test_select_fast_path_ties_take_the_lowest_indices(cuda, monkeypatch):
         assert bool((status == (1 if rep else -1)).all()), status
     want = (torch.arange(S) * 3).expand(B, H, S)
     assert torch.equal(sels[0], want) and torch.equal(sels[1], want)
+
+
+@pytest.mark.parametrize("model,N,S", [("llama-3.1-8b", 15560, 256), ("yi-9b-200k", 25544, 256), ("llama-3-8b-1m", 65480, 256),
+                                       ("glm-4-9b-1m", 16328, 512), ("llama-3.1-8b", 2050, 128)])
+def test_select_candidate_filter_equals_full_keys(cuda, monkeypatch, model, N, S):
+    """The hinted selection forms exact keys only for the landmarks its log-domain filter cannot rule out
+    (SKV_SELECT_FILTER, default on).  Chunk table, offsets, hit counts, selected ids and the hint word must equal the run
+    that forms every key (SKV_SELECT_FILTER=0) and the run without a hint, for hints inside, at the edges of and outside
+    the window, at every CTA width (256 / 512 / 1024 threads: N = 15560 / 25544 / 65480) and for ragged slices."""
+    from shadowkv_b200 import _lib
+    import ctypes as C
+    shape = synth.MODELS[model]
+    B = 2
+    H, G = shape.num_key_value_heads, shape.num_attention_heads // shape.num_key_value_heads
+    g = torch.Generator().manual_seed(N * 7 + S)
+    q = torch.randn(B, H * G, 1, 128, generator=g).to(torch.bfloat16).to(cuda)
+    lm = torch.randn(B, H, N, 128, generator=g).to(torch.bfloat16).to(cuda)
+    idx = torch.stack([torch.randperm(N + 48, generator=g)[:N].sort().values for _ in range(B * H)]).view(B, H, N).to(cuda)
+    resident = torch.stack([idx.view(B * H, N)[r][torch.randperm(N, generator=g)[:S].to(cuda)] for r in range(B * H)]).view(B, H, S)
+    geom = _lib.Geom(batch=B, kv_heads=H, q_groups=G, head_dim=128, chunk=8, select=S, n_landmarks=N, rank=160,
+                     seq_len=N * 8, buf_len=S * 8 + 600, sparse_start=448)
+    ws = torch.empty(_lib.lib.skv_select_workspace_bytes(C.byref(geom)), dtype=torch.uint8, device=cuda)
+
+    def run(hint, with_scores=False):
+        res = resident.clone()
+        off = torch.zeros(B * H * S, dtype=torch.int32, device=cuda)
+        cnt = torch.zeros(B * H, dtype=torch.int32, device=cuda)
+        sel = torch.zeros(B, H, S, dtype=torch.int64, device=cuda)
+        score = torch.zeros(B, H, N, dtype=torch.bfloat16, device=cuda)
+        geom.select_hint = hint.data_ptr() if hint is not None else None
+        _lib.check(_lib.lib.skv_select_chunks(C.byref(geom), q.data_ptr(), lm.data_ptr(), idx.data_ptr(), res.data_ptr(),
+                                              off.data_ptr(), cnt.data_ptr(), sel.data_ptr(),
+                                              score.data_ptr() if with_scores else None, ws.data_ptr(),
+                                              None, torch.cuda.current_stream().cuda_stream), "select")
+        torch.cuda.synchronize()
+        return res.cpu(), off.cpu(), cnt.cpu(), sel.cpu(), score.cpu()
+
+    base = run(None, with_scores=True)
+    keys = base[4].view(torch.int16).int().view(B * H, N)
+    thr = torch.sort(keys, dim=1, descending=True).values[:, S - 1].to(torch.int32)
+    R = B * H
+    cases = {"exact": thr.clone(), "a few steps off": thr + torch.arange(R, dtype=torch.int32) * 5 - 12,
+             "window edges": thr + torch.tensor([126, -127] * (R // 2), dtype=torch.int32),
+             "just outside": thr + torch.tensor([127, -128] * (R // 2), dtype=torch.int32),
+             "far above": thr + 3000, "far below": (thr - 3000).clamp(min=1)}
+    for name, h in cases.items():
+        outs = {}
+        for flt in ("1", "0"):
+            monkeypatch.setenv("SKV_SELECT_FILTER", flt)
+            hint = h.to(cuda)
+            outs[flt] = run(hint)
+            assert torch.equal(hint.cpu(), thr), f"hint '{name}' filter={flt}: the word must come back as the threshold key"
+        for what, a, b, c in zip(("resident", "offsets", "cnts", "selected"), outs["1"][:4], outs["0"][:4], base[:4]):
+            assert torch.equal(a, c), f"hint '{name}': {what} with the candidate filter differs from the run without a hint"
+            assert torch.equal(b, c), f"hint '{name}': {what} without the filter differs from the run without a hint"
