@@ -1112,7 +1112,9 @@ int skv_select_from_scores(const skv_geom *g, const int64_t *landmark_idx, int64
   const char *wf = getenv("SKV_SELECT_WIDE_FROM");          // read per call: tests and A/B runs flip it
   const bool wide = per >= ((wf && *wf) ? atoi(wf) : 3072);  // landmarks per CTA from which 512 threads pay
   const char *wf2 = getenv("SKV_SELECT_WIDE2_FROM");
-  const bool wide2 = per >= ((wf2 && *wf2) ? atoi(wf2) : 6144);  // ... and 1024 threads
+  // ... and 1024 threads.  With the candidate filter the key pass is cheap and the 1024-thread barriers are not: at 512K
+  // (8192 landmarks per CTA) 512 threads take 12.4 us against 13.4 us, so 1024 threads are left to 1M-token slices
+  const bool wide2 = per >= ((wf2 && *wf2) ? atoi(wf2) : 12288);
   // Single-CTA hinted selection in front of the cluster kernel (select_fast_kernel): rows whose threshold stays inside the
   // hint window are settled there, the cluster kernel only does the others.  A measured experiment, OFF by default
   // (SKV_SELECT_FAST=1 enables it): bit-identical results, but one SM is too slow for a row -- 14.4 us behind its wait at
