@@ -16,9 +16,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
   -k 'regex:score_|select_|fetch_|rebuild_|attention_|compact_|vstore|append_|advance' -c 1200 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-kernel-table --no-cpu-baseline \
   --no-hbm-first --no-hit-sweep --no-whole-model --no-reference-cuda > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"; wc -l gpurun_out/launches.csv
-# one full-set capture of one launch of each product kernel of the step (steady state: skip the warm-up token's launches)
+# one full-set capture of one launch of each product kernel of the step (steady state: the seventh token, so the chunk cache and the threshold hints are warm)
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k 'regex:score_tcgen05|select_kernel|fetch_rebuild_attend' -s 96 -c 3 -f -o gpurun_out/r02_full \
+  -k 'regex:score_tcgen05|select_kernel|fetch_rebuild_attend' -s 576 -c 3 -f -o gpurun_out/r02_full \
   python bench.py --steps 2 --warmup 3 --no-kernel-table --no-cpu-baseline --no-hbm-first --no-hit-sweep --no-whole-model \
   --no-reference-cuda > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; ls -la gpurun_out/r02_full.ncu-rep
 python - <<'PY'
