@@ -23,6 +23,22 @@ from .kv_cache import ShadowKVCache_CPU
 BF16 = torch.bfloat16
 
 
+def rotary_embedding_rows(x: torch.Tensor, cos_sin_rows: torch.Tensor, glm: bool) -> torch.Tensor:
+    """vllm ``rotary_embedding`` (reference llama.py:296, glm.py:421) as torch ops, for the prompt path: x [..., L, 128]
+    bf16 at the L positions whose table rows are cos_sin_rows [L, rot] = [cos | sin]; neox pairs (j, j + 64) over 128 dims,
+    GLM pairs (2j, 2j + 1) over the first 64 (dims 64..127 pass through).  The expression is evaluated in fp32 and rounded
+    once, like the vllm build of this image (oracle/dense_oracle.py ``rotary_vllm``, pinned to its golden vectors)."""
+    half = cos_sin_rows.shape[-1] // 2
+    c, s_ = cos_sin_rows[:, :half].float(), cos_sin_rows[:, half:].float()
+    xf = x.float()
+    if not glm:
+        a, b = xf[..., :half], xf[..., half:]
+        return torch.cat([a * c - b * s_, b * c + a * s_], dim=-1).to(BF16)
+    a, b = xf[..., 0:2 * half:2], xf[..., 1:2 * half:2]
+    o = torch.stack([a * c - b * s_, b * c + a * s_], dim=-1).flatten(-2)
+    return torch.cat([o, xf[..., 2 * half:]], dim=-1).to(BF16)
+
+
 class LlamaLayer:
     """Weights of one decoder layer, named as in reference models/llama.py:62-123 (``GLMLayer``: glm.py:79-131, whose
     fused gate/up matrix is called ``up_proj`` there and whose QKV projection has a bias ``bqkv``)."""
@@ -187,23 +203,10 @@ class Llama:
         return torch.arange(past, past + n, device=self.device, dtype=torch.long).unsqueeze(0).repeat(input_ids.size(0), 1)
 
     def apply_rotary_pos_emb(self, query_states, key_states, position_ids):
-        """llama.py:283-301 / glm.py:406-428 (vllm ``rotary_embedding``: neox pairs (j, j+64) over 128 dims, GLM pairs
-        (2j, 2j+1) over the first 64) for [bsz, heads, L, 128] tensors, every row of position_ids equal: the expression
-        is evaluated in fp32 and rounded once, like the vllm build of this image (oracle/dense_oracle.py)."""
+        """llama.py:283-301 / glm.py:406-428 for [bsz, heads, L, 128] tensors, every row of position_ids equal."""
         rows = self.cos_sin_cache[position_ids[0]]                          # [L, rot] = [cos | sin]
-        half = rows.shape[-1] // 2
-        c, s_ = rows[:, :half].float(), rows[:, half:].float()
-
-        def rot(x):
-            xf = x.float()
-            if not self.shape.glm_rope:
-                a, b = xf[..., :half], xf[..., half:]
-                return torch.cat([a * c - b * s_, b * c + a * s_], dim=-1).to(BF16)
-            a, b = xf[..., 0:2 * half:2], xf[..., 1:2 * half:2]
-            o = torch.stack([a * c - b * s_, b * c + a * s_], dim=-1).flatten(-2)
-            return torch.cat([o, xf[..., 2 * half:]], dim=-1).to(BF16)
-
-        return rot(query_states), rot(key_states)
+        return (rotary_embedding_rows(query_states, rows, self.shape.glm_rope),
+                rotary_embedding_rows(key_states, rows, self.shape.glm_rope))
 
     @staticmethod
     def _causal_attention(q, k, v):

@@ -81,3 +81,28 @@ def test_properties():
     gu = torch.randn(3, 512, generator=g).to(torch.bfloat16)
     ref = torch.nn.functional.silu(gu[:, :256].float()) * gu[:, 256:].float()
     assert float((DO.silu_and_mul(gu).float() - ref).abs().max()) < 0.03
+
+
+def test_prompt_path_rotary_embedding_equals_the_oracle_bit_for_bit():
+    """shadowkv_b200.llama.rotary_embedding_rows (torch ops of the prompt path) against the
+    oracle's restatement of vllm rotary_embedding at many positions, Llama (neox) and GLM (interleaved, 64 dims) forms;
+    and the oracle's multi-position form against its single-position form that the library golden vectors pin."""
+    import torch
+    from oracle import dense_oracle as DO
+    from shadowkv_b200 import synth
+    from shadowkv_b200.llama import rotary_embedding_rows
+    g = torch.Generator().manual_seed(4)
+    L = 300
+    x = (torch.randn(2, 3, L, 128, generator=g) * 2).to(torch.bfloat16)
+    for glm in (False, True):
+        cs = synth.cos_sin_table(5000, theta=10000.0 if glm else 500000.0, glm=glm)
+        pos = torch.arange(4321, 4321 + L)
+        rows = cs[pos]
+        got = rotary_embedding_rows(x, rows, glm)
+        want = DO.rotary_positions(x, rows, neox=not glm)
+        assert torch.equal(got, want)
+        for t in (0, 17, L - 1):
+            one = DO.rotary_vllm(x[:, :, t], cs[pos[t]], neox=not glm)
+            assert torch.equal(want[:, :, t], one)
+        if glm:
+            assert torch.equal(got[..., 64:], x[..., 64:])
