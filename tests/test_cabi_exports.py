@@ -136,3 +136,33 @@ def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", libdir, "-lshadowkv_b200", f"-Wl,-rpath,{libdir}"])
     assert subprocess.call([str(exe)]) == 0
+
+
+def test_fused_attention_entry_point_checks_its_exchange_without_a_gpu():
+    """skv_fetch_rebuild_attend validates the kv-head split's exchange before it touches CUDA: every peer needs a flag
+    pointer and an epoch; an output pointer may only be NULL in the one-GPU form (world == 1: the row's flag word only)."""
+    import ctypes as C
+    from shadowkv_b200 import _lib
+    lib = _lib.lib
+    g = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=128, chunk=8, select=256, n_landmarks=15560, rank=160,
+                  seq_len=124928, buf_len=2592, sparse_start=448, table_mode=1)
+
+    def call(ex, geom=g):
+        return lib.skv_fetch_rebuild_attend(C.byref(geom), 1, 0, 1, 1, 1, 1, 1, 1, 1, 1, None, 1, 1, 2497, 0, 0.088, 1,
+                                            C.byref(ex) if ex is not None else None, 0)
+
+    two = _lib.Exchange(world=2, rank=0)
+    two.peer_out[0], two.peer_flags[0], two.peer_flags[1], two.epoch_dev = 1, 1, 1, 1
+    assert call(two) == -2 and b"null peer pointer" in lib.skv_last_error()        # peer 1 has no output buffer
+    one = _lib.Exchange(world=1, rank=0)
+    one.epoch_dev = 1
+    assert call(one) == -2 and b"null peer pointer" in lib.skv_last_error()        # the one-GPU form still needs its flag word
+    one.peer_flags[0] = 1
+    one.epoch_dev = None
+    assert call(one) == -2 and b"epoch_dev" in lib.skv_last_error()
+    nine = _lib.Exchange(world=9, rank=0)
+    nine.epoch_dev = 1
+    assert call(nine) == -2
+    ref_table = _lib.Geom(batch=1, kv_heads=8, q_groups=4, head_dim=128, chunk=8, select=256, n_landmarks=15560, rank=160,
+                          seq_len=124928, buf_len=2592, sparse_start=448, table_mode=0)
+    assert call(None, ref_table) == -1                                             # needs the in-place chunk table
